@@ -1,0 +1,172 @@
+/*
+ * pnmol_b200.h -- C ABI of the B200-native EK1 filter loop (libpnmol_b200.so).
+ *
+ * The reference (schmidtjonathan/pnmol-experiments) is pure Python/JAX and has no FFI
+ * layer; the drop-in boundary is its Python solver API.  This header is the C ABI the
+ * Python host package (pnmol_b200) binds with ctypes, one entry point per reference
+ * interface on the hot path.  Citations are file:line in the reference tree.
+ *
+ * Conventions
+ *  - all floating point is IEEE double; matrices are row-major unless stated;
+ *  - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers are
+ *    ordinary host memory; the caller owns every buffer it passes, the library owns only
+ *    the workspace inside the handle;
+ *  - every function returns 0 on success and a negative code on error, with a
+ *    human-readable message available from pnmol_b200_last_error();
+ *  - compute calls are asynchronous on the cudaStream_t passed as `stream`
+ *    (NULL = legacy default stream); a handle is bound to one device and is not
+ *    thread-safe; no exceptions or callbacks cross the boundary;
+ *  - a per-member int32 status word is written by the kernels: 0 = finite results,
+ *    1 = a non-finite value was produced (reference behaviour: NaNs propagate silently,
+ *    tests/test_pdefilter.py:143-146 only checks for them afterwards).
+ *
+ * State layout (per ensemble member), identical to the reference's PDEFilterState
+ * (src/pnmol/pdefilter.py:17-22, src/pnmol/base/rv.py:9-14):
+ *    mean      (n, dd)  row i = i-th time derivative; dd = d (white) or 2d (latent, state
+ *                       columns then latent-force columns: src/pnmol/latent.py:165-176);
+ *    cov_sqrtm (D, D)   D = n*dd, lower triangular up to the sign of its columns.
+ */
+#ifndef PNMOL_B200_H
+#define PNMOL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pnmol_b200_handle pnmol_b200_handle;
+
+/* Solver kinds: the four PDEFilter subclasses of src/pnmol/white.py:169,189 and
+ * src/pnmol/latent.py:237,266. */
+enum {
+    PNMOL_B200_WHITE_LINEAR = 0,
+    PNMOL_B200_WHITE_SEMILINEAR = 1,
+    PNMOL_B200_LATENT_LINEAR = 2,
+    PNMOL_B200_LATENT_SEMILINEAR = 3
+};
+
+/* Point-wise reaction terms f / df shipped with the reference
+ * (src/pnmol/pde/examples.py:151-165, 228-235, 311-315), evaluated on the device. */
+enum {
+    PNMOL_B200_REACTION_NONE = 0,
+    PNMOL_B200_REACTION_SPRUCE = 1,        /* params: growth_rate               (1 component)  */
+    PNMOL_B200_REACTION_SIR = 2,           /* params: beta, gamma               (3 components) */
+    PNMOL_B200_REACTION_LOTKA_VOLTERRA = 3 /* params: a, b, c, d                (2 components) */
+};
+
+#define PNMOL_B200_MAX_REACTION_PARAMS 4
+
+/* Flags for pnmol_b200_step / pnmol_b200_run. */
+#define PNMOL_B200_FLAG_DENSE_FACTOR 1 /* input cov_sqrtm is not lower triangular */
+#define PNMOL_B200_FLAG_NO_ERROR_ESTIMATE 2 /* skip white.py:153-162 (unused by Constant steps) */
+
+const char* pnmol_b200_last_error(void);
+int pnmol_b200_version(void);
+
+/* Number of kernels this library has launched since it was loaded (bench.py's
+ * gpu_launches claim). */
+int64_t pnmol_b200_launch_count(void);
+
+/* Create a solver handle for `batch` independent members of one discretised problem.
+ * Replaces PDEFilter.__init__ + the shape bookkeeping of initialize()
+ * (src/pnmol/pdefilter.py:37-70, src/pnmol/white.py:17, src/pnmol/latent.py:52).
+ *   d = pde.L.shape[0], nb = pde.B.shape[0], ncomp = number of PDE components,
+ *   num_derivatives = nu.  device = CUDA ordinal. */
+int pnmol_b200_create(pnmol_b200_handle** out, int kind, int d, int num_derivatives, int nb, int ncomp,
+                      int batch, int reaction_id, int device);
+int pnmol_b200_destroy(pnmol_b200_handle* h);
+
+/* Discretised operator (host pointers, copied): the attributes the solvers read from the
+ * problem object, src/pnmol/pde/mixins.py:37-54,98-117.
+ *   L as ELL rows: L_col/L_val [d, wl] (col < 0 = padding); E_diag [d] = diag(pde.E_sqrtm);
+ *   B as ELL rows: B_col/B_val [nb, wb]; R_sqrtm [nb, nb] dense. */
+int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const double* L_val, int wl,
+                            const double* E_diag, const int32_t* B_col, const double* B_val, int wb,
+                            const double* R_sqrtm);
+
+/* IWP prior (host pointers, copied): A_1d, L_Q1d [n, n] of
+ * IntegratedWienerTransition.preconditioned_discretize_1d (src/pnmol/base/iwp.py:13-30) and
+ * Lk = chol(k(X, X)) [d, d] (src/pnmol/white.py:85, src/pnmol/latent.py:139). */
+int pnmol_b200_set_prior(pnmol_b200_handle* h, const double* A1d, const double* LQ1d, const double* Lk);
+
+/* Per-member ensemble axes (host pointers, copied; NULL = all ones / reaction defaults):
+ *   diff_scale [batch, ncomp] multiplies L and E_sqrtm per component
+ *   (src/pnmol/pde/mixins.py:37-38,87-89); prior_scale [batch] multiplies Lk;
+ *   reaction_params [batch, nparams]. */
+int pnmol_b200_set_members(pnmol_b200_handle* h, const double* diff_scale, const double* prior_scale,
+                           const double* reaction_params, int nparams);
+
+/* Householder row-support envelopes the kernels use for the two QR factorisations
+ * (host-only arithmetic, no GPU needed; exported so that the structure model can be
+ * tested on CPU).  te_p/be_p [D]: predict stack [(A Cl)^T ; Ql^T]; te_u/be_u [m + D]:
+ * update block matrix of src/pnmol/base/sqrt.py:60-65.  Entry j = last (inclusive) row of
+ * the top / bottom row segment that column j may touch. */
+int pnmol_b200_structure(int kind, int d, int num_derivatives, int nb, const int32_t* L_col, int wl,
+                         const int32_t* B_col, int wb, int ncomp, int dense_factor, int32_t* te_p,
+                         int32_t* be_p, int32_t* te_u, int32_t* be_u);
+
+/* initialize(pde) of src/pnmol/white.py:12-80 / src/pnmol/latent.py:20-134.
+ *   y0 dev [batch, d]; mean_out dev [batch, n, dd]; chol_out dev [batch, D, D];
+ *   status dev [batch] int32. */
+int pnmol_b200_initialize(pnmol_b200_handle* h, const double* y0, double t0, double diffuse_prior_scale,
+                          double* mean_out, double* chol_out, int32_t* status, void* stream);
+
+/* attempt_step(state, dt, pde) of src/pnmol/white.py:96-146 / src/pnmol/latent.py:155-225.
+ *   precond/precond_inv host [n]: nordsieck_preconditioner_1d_raw(dt)
+ *   (src/pnmol/base/iwp.py:55-62), computed by the caller so that both sides use the same
+ *   libm pow; t_new = state.t + dt is passed to the reaction term;
+ *   err_out dev [batch, d] (error_estimate, white only), ref_out dev [batch, d]
+ *   (reference_state = |m_new[0]|, white only), diff_out dev [batch]
+ *   (diffusion_squared_local); err_out / ref_out may be NULL. */
+int pnmol_b200_step(pnmol_b200_handle* h, double t_new, double dt, const double* precond,
+                    const double* precond_inv, const double* mean_in, const double* chol_in,
+                    double* mean_out, double* chol_out, double* err_out, double* ref_out, double* diff_out,
+                    int32_t* status, int flags, void* stream);
+
+/* The time loop of solution_generator / perform_full_step with step.Constant
+ * (src/pnmol/pdefilter.py:118-227, src/pnmol/odetools/step.py:30-55) as ONE persistent
+ * launch: nsteps steps with step sizes dts host [nsteps], preconditioners host
+ * [nsteps, n] each.  mean / chol dev are updated in place (scratch = second state buffer
+ * owned by the caller: mean_tmp, chol_tmp).  diff_sum dev [batch] receives the sum of the
+ * local diffusions (for the mean of src/pnmol/pdefilter.py:95,113).  If mean_traj /
+ * chol_traj are non-NULL they receive every step's state ([nsteps, batch, ...]). */
+int pnmol_b200_run(pnmol_b200_handle* h, double t0, const double* dts, const double* precond,
+                   const double* precond_inv, int nsteps, double* mean, double* chol, double* mean_tmp,
+                   double* chol_tmp, double* err_out, double* ref_out, double* diff_last, double* diff_sum,
+                   double* mean_traj, double* chol_traj, int32_t* status, int flags, void* stream);
+
+/* cov_sqrtm <- cov_sqrtm * sqrt(mean of the local diffusions), the last line of
+ * simulate_final_state (src/pnmol/pdefilter.py:113-116).  chol dev [batch, D, D] in place,
+ * diff_sum dev [batch] as returned by pnmol_b200_run, diff_cal_out dev [batch] or NULL
+ * receives diffusion_squared_calibrated = diff_sum / nsteps. */
+int pnmol_b200_rescale(pnmol_b200_handle* h, double* chol, const double* diff_sum, int nsteps,
+                       double* diff_cal_out, void* stream);
+
+/* simulate_final_state (src/pnmol/pdefilter.py:105-116) through HOST buffers: copies y0
+ * host [batch, d] to the device, runs initialize + the constant-step loop, rescales the
+ * factor by sqrt(mean local diffusion) and copies mean [batch, n, dd], chol [batch, D, D],
+ * diffusion_calibrated [batch] and status [batch] back.  Blocks until done. */
+int pnmol_b200_simulate_final_state_host(pnmol_b200_handle* h, const double* y0_host, double t0,
+                                         double diffuse_prior_scale, const double* dts, const double* precond,
+                                         const double* precond_inv, int nsteps, double* mean_host,
+                                         double* chol_host, double* diff_cal_host, int32_t* status_host,
+                                         int flags, void* stream);
+
+/* propagate_cholesky_factor(S1, S2) of src/pnmol/base/sqrt.py:9-23 (batched like
+ * batched_propagate_cholesky_factor, sqrt.py:27-29): S1 dev [batch, r, c1], S2 dev
+ * [batch, r, c2] (c2 may be 0), out dev [batch, r, min(r, c1 + c2)]. */
+int pnmol_b200_sqrt_propagate(const double* S1, const double* S2, double* out, int r, int c1, int c2,
+                              int batch, int device, void* stream);
+
+/* update_sqrt(H, C, meascov_sqrtm) / update_sqrt_no_meascov(H, C) of
+ * src/pnmol/base/sqrt.py:34-95 for dense inputs: H dev [batch, m, D], C dev [batch, D, D],
+ * meascov dev [batch, m, m] or NULL; outputs C_out [batch, D, D], K_out [batch, D, m],
+ * S_out [batch, m, m]. */
+int pnmol_b200_sqrt_update(const double* H, const double* C, const double* meascov, double* C_out,
+                           double* K_out, double* S_out, int m, int D, int batch, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNMOL_B200_H */

@@ -1,0 +1,466 @@
+// C ABI of libpnmol_b200.so (see include/pnmol_b200.h).  Host-side orchestration only:
+// argument checking, device-buffer ownership, envelope computation, kernel launches.
+#include "../../include/pnmol_b200.h"
+#include "ek1_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pnmol;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(-2, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                                std::to_string(__LINE__) + ")");                                   \
+    } while (0)
+
+void compute_structure(int latent, int semilinear, int d, int n, int nb, int ncomp, const int32_t* Lcol, int wl,
+                       const int32_t* Bcol, int wb, int dense, int32_t* te_p, int32_t* be_p, int32_t* te_u,
+                       int32_t* be_u) {
+    const int dd = latent ? 2 * d : d, D = n * dd, m = d + nb, npts = d / ncomp;
+    for (int i = 0; i < D; ++i) {
+        te_p[i] = dense ? D - 1 : std::min(D - 1, n * (i / n) + n - 1);
+        be_p[i] = D + i;
+    }
+    int run = 0, brun = D - 1;
+    for (int r = 0; r < m; ++r) {
+        int last = 0;
+        if (r < d) {
+            for (int w = 0; w < wl; ++w) {
+                const int c = Lcol[(size_t)r * wl + w];
+                if (c >= 0) last = std::max(last, c * n);
+            }
+            if (semilinear) last = std::max(last, ((ncomp - 1) * npts + r % npts) * n);
+            last = std::max(last, r * n + 1);
+            if (latent) last = std::max(last, (d + r) * n);
+        } else {
+            for (int w = 0; w < wb; ++w) {
+                const int c = Bcol[(size_t)(r - d) * wb + w];
+                if (c >= 0) last = std::max(last, c * n);
+            }
+        }
+        run = std::max(run, std::max(last, r));
+        te_u[r] = std::min(D - 1, run);
+        if (!latent) brun = std::max(brun, D + (r < d ? r : m - 1));
+        be_u[r] = brun;
+    }
+    for (int k = 0; k < D; ++k) {
+        te_u[m + k] = std::min(D - 1, std::max(te_u[m - 1], m + k));
+        be_u[m + k] = latent ? D - 1 : D + m - 1;
+    }
+}
+
+}  // namespace
+
+struct pnmol_b200_handle {
+    int kind, device, grid, num_sms;
+    Problem P;
+    std::vector<void*> allocs;
+    size_t smem_bytes;
+    bool have_op = false, have_prior = false;
+    double* steparr = nullptr;  // device: dts | tnew | pv | pinv
+    int steparr_cap = 0;
+    // host-path state (pnmol_b200_simulate_final_state_host)
+    double *hs_y0 = nullptr, *hs_mean_a = nullptr, *hs_mean_b = nullptr, *hs_chol_a = nullptr, *hs_chol_b = nullptr,
+           *hs_diffsum = nullptr, *hs_diffcal = nullptr;
+    int32_t* hs_status = nullptr;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(pnmol_b200_handle* h, T** out, size_t count) {
+    void* p = nullptr;
+    CU(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    h->allocs.push_back(p);
+    *out = static_cast<T*>(p);
+    return 0;
+}
+
+template <typename T>
+int dev_upload(pnmol_b200_handle* h, const T** out, const T* host, size_t count) {
+    T* p = nullptr;
+    int rc = dev_alloc(h, &p, count);
+    if (rc) return rc;
+    CU(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = p;
+    return 0;
+}
+
+int ensure_ready(pnmol_b200_handle* h) {
+    if (!h) return fail(-1, "null handle");
+    if (!h->have_op) return fail(-1, "pnmol_b200_set_operator has not been called");
+    if (!h->have_prior) return fail(-1, "pnmol_b200_set_prior has not been called");
+    if (h->P.semilinear && !h->P.rparams) return fail(-1, "semi-linear solver needs reaction parameters (pnmol_b200_set_members)");
+    CU(cudaSetDevice(h->device));
+    return 0;
+}
+
+int upload_steps(pnmol_b200_handle* h, int nsteps, double t0, const double* dts, const double* pv, const double* pinv,
+                 cudaStream_t st, RunArgs* a) {
+    const int n = h->P.n;
+    const size_t per = (size_t)nsteps * (2 + 2 * n);
+    if (h->steparr_cap < (int)per) {
+        CU(cudaStreamSynchronize(st));
+        if (h->steparr) CU(cudaFree(h->steparr));
+        CU(cudaMalloc((void**)&h->steparr, per * sizeof(double)));
+        h->steparr_cap = (int)per;
+    }
+    std::vector<double> buf(per);
+    double t = t0;
+    for (int s = 0; s < nsteps; ++s) {
+        buf[s] = dts[s];
+        t = t + dts[s];  // same floating-point accumulation as pdefilter.py:140 / white.py:139
+        buf[nsteps + s] = t;
+    }
+    std::memcpy(buf.data() + 2 * (size_t)nsteps, pv, sizeof(double) * nsteps * n);
+    std::memcpy(buf.data() + 2 * (size_t)nsteps + (size_t)nsteps * n, pinv, sizeof(double) * nsteps * n);
+    CU(cudaMemcpyAsync(h->steparr, buf.data(), per * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // buf is a stack-owned staging vector
+    a->dts = h->steparr;
+    a->tnew = h->steparr + nsteps;
+    a->pv = h->steparr + 2 * (size_t)nsteps;
+    a->pinv = h->steparr + 2 * (size_t)nsteps + (size_t)nsteps * n;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pnmol_b200_last_error(void) { return g_err.c_str(); }
+int pnmol_b200_version(void) { return 100; }
+int64_t pnmol_b200_launch_count(void) { return g_launches.load(); }
+
+int pnmol_b200_structure(int kind, int d, int num_derivatives, int nb, const int32_t* L_col, int wl,
+                         const int32_t* B_col, int wb, int ncomp, int dense_factor, int32_t* te_p, int32_t* be_p,
+                         int32_t* te_u, int32_t* be_u) {
+    if (kind < 0 || kind > 3 || d <= 0 || num_derivatives < 1 || nb < 0 || ncomp <= 0 || d % ncomp)
+        return fail(-1, "pnmol_b200_structure: invalid shape arguments");
+    compute_structure(kind >= 2, kind & 1, d, num_derivatives + 1, nb, ncomp, L_col, wl, B_col, wb, dense_factor, te_p,
+                      be_p, te_u, be_u);
+    return 0;
+}
+
+int pnmol_b200_create(pnmol_b200_handle** out, int kind, int d, int num_derivatives, int nb, int ncomp, int batch,
+                      int reaction_id, int device) {
+    if (!out) return fail(-1, "null output handle");
+    if (kind < 0 || kind > 3) return fail(-1, "unknown solver kind");
+    const int n = num_derivatives + 1;
+    if (d <= 0 || batch <= 0 || nb < 0 || ncomp <= 0 || ncomp > kMaxComp || d % ncomp) return fail(-1, "invalid d / batch / nb / ncomp");
+    if (n < 2 || n > kMaxN) return fail(-1, "num_derivatives must be in 1..7");
+    const bool semil = kind & 1;
+    if (semil && (reaction_id < 1 || reaction_id > 3)) return fail(-1, "semi-linear solver needs a device reaction id (1..3)");
+    if (reaction_id == PNMOL_B200_REACTION_SPRUCE && ncomp != 1) return fail(-1, "spruce reaction has 1 component");
+    if (reaction_id == PNMOL_B200_REACTION_SIR && ncomp != 3) return fail(-1, "SIR reaction has 3 components");
+    if (reaction_id == PNMOL_B200_REACTION_LOTKA_VOLTERRA && ncomp != 2) return fail(-1, "Lotka-Volterra reaction has 2 components");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(-3, "no such CUDA device (libpnmol_b200 has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    auto* h = new pnmol_b200_handle();
+    std::memset(&h->P, 0, sizeof(Problem));
+    h->kind = kind;
+    h->device = device;
+    Problem& P = h->P;
+    P.latent = kind >= 2;
+    P.semilinear = semil;
+    P.reaction = semil ? reaction_id : 0;
+    P.d = d; P.n = n; P.nb = nb; P.ncomp = ncomp; P.npts = d / ncomp;
+    P.dd = P.latent ? 2 * d : d;
+    P.D = n * P.dd;
+    P.m = d + nb;
+    P.batch = batch;
+    P.ld = 2 * P.D;
+    if (P.D < P.m) { delete h; return fail(-1, "update_sqrt needs D >= m (src/pnmol/base/sqrt.py:55-57)"); }
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_bytes = smem_doubles(P.D, P.m, P.dd) * sizeof(double);
+    if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { delete h; return fail(-1, "state dimension too large for the single-CTA path"); }
+    *out = h;
+    return 0;
+}
+
+int pnmol_b200_destroy(pnmol_b200_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->steparr) cudaFree(h->steparr);
+    for (void* p : {(void*)h->hs_y0, (void*)h->hs_mean_a, (void*)h->hs_mean_b, (void*)h->hs_chol_a, (void*)h->hs_chol_b,
+                    (void*)h->hs_diffsum, (void*)h->hs_diffcal, (void*)h->hs_status})
+        if (p) cudaFree(p);
+    delete h;
+    return 0;
+}
+
+int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const double* L_val, int wl, const double* E_diag,
+                            const int32_t* B_col, const double* B_val, int wb, const double* R_sqrtm) {
+    if (!h) return fail(-1, "null handle");
+    if (h->have_op) return fail(-1, "operator already set (create a new handle)");
+    if (!L_col || !L_val || !E_diag || wl <= 0) return fail(-1, "null operator arrays");
+    Problem& P = h->P;
+    if (P.nb > 0 && (!B_col || !B_val || !R_sqrtm || wb <= 0)) return fail(-1, "null boundary arrays");
+    CU(cudaSetDevice(h->device));
+    for (size_t k = 0; k < (size_t)P.d * wl; ++k)
+        if (L_col[k] >= P.d) return fail(-1, "L_col out of range");
+    for (size_t k = 0; k < (size_t)P.nb * wb; ++k)
+        if (B_col[k] >= P.d) return fail(-1, "B_col out of range");
+    P.wl = wl;
+    P.wb = P.nb > 0 ? wb : 0;
+    P.wh = std::max(wl + (P.semilinear ? P.ncomp : 0) + 1 + (P.latent ? 1 : 0), P.wb);
+    int rc;
+    if ((rc = dev_upload(h, &P.Lcol, L_col, (size_t)P.d * wl))) return rc;
+    if ((rc = dev_upload(h, &P.Lval, L_val, (size_t)P.d * wl))) return rc;
+    if ((rc = dev_upload(h, &P.Ediag, E_diag, (size_t)P.d))) return rc;
+    if (P.nb > 0) {
+        if ((rc = dev_upload(h, &P.Bcol, B_col, (size_t)P.nb * wb))) return rc;
+        if ((rc = dev_upload(h, &P.Bval, B_val, (size_t)P.nb * wb))) return rc;
+        if ((rc = dev_upload(h, &P.Rsq, R_sqrtm, (size_t)P.nb * P.nb))) return rc;
+    }
+    std::vector<int32_t> te_p(P.D), be_p(P.D), te_pd(P.D), te_u(P.m + P.D), be_u(P.m + P.D);
+    compute_structure(P.latent, P.semilinear, P.d, P.n, P.nb, P.ncomp, L_col, wl, B_col, P.wb, 0, te_p.data(), be_p.data(),
+                      te_u.data(), be_u.data());
+    for (int i = 0; i < P.D; ++i) te_pd[i] = P.D - 1;
+    if ((rc = dev_upload(h, &P.te_p, te_p.data(), te_p.size()))) return rc;
+    if ((rc = dev_upload(h, &P.be_p, be_p.data(), be_p.size()))) return rc;
+    if ((rc = dev_upload(h, &P.te_pd, te_pd.data(), te_pd.size()))) return rc;
+    if ((rc = dev_upload(h, &P.te_u, te_u.data(), te_u.size()))) return rc;
+    if ((rc = dev_upload(h, &P.be_u, be_u.data(), be_u.size()))) return rc;
+    // launch geometry + per-CTA scratch
+    CU(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    CU(cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run, kThreads, h->smem_bytes));
+    int want = 2;
+    if (const char* e = std::getenv("PNMOL_B200_CTAS_PER_SM")) want = std::max(1, std::atoi(e));
+    occ = std::max(1, std::min(occ, want));
+    h->grid = std::min(P.batch, occ * h->num_sms);
+    const size_t wsz = (size_t)P.ld * (P.m + P.D);
+    if ((rc = dev_alloc(h, &P.W, wsz * h->grid))) return rc;
+    if ((rc = dev_alloc(h, &P.Hcol, (size_t)h->grid * P.m * P.wh))) return rc;
+    if ((rc = dev_alloc(h, &P.Hval, (size_t)h->grid * P.m * P.wh))) return rc;
+    if ((rc = dev_alloc(h, &P.F, (size_t)h->grid * P.m * P.d))) return rc;
+    if ((rc = dev_alloc(h, &P.S, (size_t)h->grid * P.m * P.m))) return rc;
+    CU(cudaMemset(P.W, 0, wsz * h->grid * sizeof(double)));
+    h->have_op = true;
+    return 0;
+}
+
+int pnmol_b200_set_prior(pnmol_b200_handle* h, const double* A1d, const double* LQ1d, const double* Lk) {
+    if (!h || !A1d || !LQ1d || !Lk) return fail(-1, "null argument");
+    if (h->have_prior) return fail(-1, "prior already set (create a new handle)");
+    Problem& P = h->P;
+    CU(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = dev_upload(h, &P.A1d, A1d, (size_t)P.n * P.n))) return rc;
+    if ((rc = dev_upload(h, &P.LQ1d, LQ1d, (size_t)P.n * P.n))) return rc;
+    if ((rc = dev_upload(h, &P.Lk, Lk, (size_t)P.d * P.d))) return rc;
+    double* Kg = nullptr;
+    if ((rc = dev_alloc(h, &Kg, (size_t)P.d * P.d))) return rc;
+    k_gram<<<P.d, 128>>>(P.Lk, Kg, P.d);
+    ++g_launches;
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    P.Kg = Kg;
+    h->have_prior = true;
+    return 0;
+}
+
+int pnmol_b200_set_members(pnmol_b200_handle* h, const double* diff_scale, const double* prior_scale,
+                           const double* reaction_params, int nparams) {
+    if (!h) return fail(-1, "null handle");
+    Problem& P = h->P;
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    int rc;
+    if (diff_scale && (rc = dev_upload(h, &P.diffscale, diff_scale, (size_t)P.batch * P.ncomp))) return rc;
+    if (prior_scale && (rc = dev_upload(h, &P.priorscale, prior_scale, (size_t)P.batch))) return rc;
+    if (reaction_params) {
+        const int need = P.reaction == 1 ? 1 : P.reaction == 2 ? 2 : P.reaction == 3 ? 4 : 0;
+        if (nparams < need || nparams > PNMOL_B200_MAX_REACTION_PARAMS) return fail(-1, "wrong number of reaction parameters");
+        if ((rc = dev_upload(h, &P.rparams, reaction_params, (size_t)P.batch * nparams))) return rc;
+        P.nparams = nparams;
+    }
+    return 0;
+}
+
+int pnmol_b200_initialize(pnmol_b200_handle* h, const double* y0, double t0, double diffuse_prior_scale, double* mean_out,
+                          double* chol_out, int32_t* status, void* stream) {
+    int rc = ensure_ready(h);
+    if (rc) return rc;
+    if (!y0 || !mean_out || !chol_out) return fail(-1, "null state pointer");
+    InitArgs a;
+    a.y0 = y0; a.t0 = t0; a.prior_scale0 = diffuse_prior_scale;
+    a.nugget = h->P.latent ? 1e-6 : 1e-10;  // latent.py:71,98 / white.py:33,51
+    a.mean_out = mean_out; a.chol_out = chol_out; a.status = status;
+    k_init<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pnmol_b200_step(pnmol_b200_handle* h, double t_new, double dt, const double* precond, const double* precond_inv,
+                    const double* mean_in, const double* chol_in, double* mean_out, double* chol_out, double* err_out,
+                    double* ref_out, double* diff_out, int32_t* status, int flags, void* stream) {
+    int rc = ensure_ready(h);
+    if (rc) return rc;
+    if (!precond || !precond_inv || !mean_in || !chol_in || !mean_out || !chol_out) return fail(-1, "null argument");
+    if (mean_in == mean_out || chol_in == chol_out) return fail(-1, "pnmol_b200_step is out of place");
+    RunArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.nsteps = 1; a.flags = flags; a.final_in_b = 1;
+    for (int i = 0; i < h->P.n; ++i) { a.pv0[i] = precond[i]; a.pinv0[i] = precond_inv[i]; }
+    a.dt0 = dt; a.tnew0 = t_new;
+    a.mean_a = const_cast<double*>(mean_in); a.chol_a = const_cast<double*>(chol_in);
+    a.mean_b = mean_out; a.chol_b = chol_out;
+    a.err_out = err_out; a.ref_out = ref_out; a.diff_last = diff_out; a.status = status;
+    k_run<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pnmol_b200_run(pnmol_b200_handle* h, double t0, const double* dts, const double* precond, const double* precond_inv,
+                   int nsteps, double* mean, double* chol, double* mean_tmp, double* chol_tmp, double* err_out,
+                   double* ref_out, double* diff_last, double* diff_sum, double* mean_traj, double* chol_traj,
+                   int32_t* status, int flags, void* stream) {
+    int rc = ensure_ready(h);
+    if (rc) return rc;
+    if (nsteps <= 0) return fail(-1, "nsteps must be positive");
+    if (!dts || !precond || !precond_inv || !mean || !chol || !mean_tmp || !chol_tmp) return fail(-1, "null argument");
+    RunArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.nsteps = nsteps; a.flags = flags; a.final_in_b = 0;
+    if ((rc = upload_steps(h, nsteps, t0, dts, precond, precond_inv, (cudaStream_t)stream, &a))) return rc;
+    a.mean_a = mean; a.chol_a = chol; a.mean_b = mean_tmp; a.chol_b = chol_tmp;
+    a.err_out = err_out; a.ref_out = ref_out; a.diff_last = diff_last; a.diff_sum = diff_sum;
+    a.mean_traj = mean_traj; a.chol_traj = chol_traj; a.status = status;
+    k_run<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pnmol_b200_rescale(pnmol_b200_handle* h, double* chol, const double* diff_sum, int nsteps, double* diff_cal_out,
+                       void* stream) {
+    int rc = ensure_ready(h);
+    if (rc) return rc;
+    if (!chol || !diff_sum || nsteps <= 0) return fail(-1, "invalid argument");
+    const Problem& P = h->P;
+    dim3 g(std::max(1, std::min(64, (int)((size_t)P.D * P.D / 1024))), P.batch);
+    k_rescale<<<g, 256, 0, (cudaStream_t)stream>>>(chol, diff_sum, diff_cal_out, nsteps, (size_t)P.D * P.D, P.batch);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pnmol_b200_simulate_final_state_host(pnmol_b200_handle* h, const double* y0_host, double t0, double diffuse_prior_scale,
+                                         const double* dts, const double* precond, const double* precond_inv, int nsteps,
+                                         double* mean_host, double* chol_host, double* diff_cal_host, int32_t* status_host,
+                                         int flags, void* stream) {
+    int rc = ensure_ready(h);
+    if (rc) return rc;
+    if (!y0_host || !mean_host || !chol_host) return fail(-1, "null host buffer");
+    const Problem& P = h->P;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t msz = (size_t)P.batch * P.D, csz = (size_t)P.batch * P.D * P.D;
+    if (!h->hs_y0) {
+        CU(cudaMalloc((void**)&h->hs_y0, sizeof(double) * P.batch * P.d));
+        CU(cudaMalloc((void**)&h->hs_mean_a, sizeof(double) * msz));
+        CU(cudaMalloc((void**)&h->hs_mean_b, sizeof(double) * msz));
+        CU(cudaMalloc((void**)&h->hs_chol_a, sizeof(double) * csz));
+        CU(cudaMalloc((void**)&h->hs_chol_b, sizeof(double) * csz));
+        CU(cudaMalloc((void**)&h->hs_diffsum, sizeof(double) * P.batch));
+        CU(cudaMalloc((void**)&h->hs_diffcal, sizeof(double) * P.batch));
+        CU(cudaMalloc((void**)&h->hs_status, sizeof(int32_t) * P.batch));
+    }
+    CU(cudaMemcpyAsync(h->hs_y0, y0_host, sizeof(double) * P.batch * P.d, cudaMemcpyHostToDevice, st));
+    if ((rc = pnmol_b200_initialize(h, h->hs_y0, t0, diffuse_prior_scale, h->hs_mean_a, h->hs_chol_a, h->hs_status, stream))) return rc;
+    if ((rc = pnmol_b200_run(h, t0, dts, precond, precond_inv, nsteps, h->hs_mean_a, h->hs_chol_a, h->hs_mean_b, h->hs_chol_b,
+                             nullptr, nullptr, nullptr, h->hs_diffsum, nullptr, nullptr, h->hs_status, flags, stream)))
+        return rc;
+    if ((rc = pnmol_b200_rescale(h, h->hs_chol_a, h->hs_diffsum, nsteps, h->hs_diffcal, stream))) return rc;
+    CU(cudaMemcpyAsync(mean_host, h->hs_mean_a, sizeof(double) * msz, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(chol_host, h->hs_chol_a, sizeof(double) * csz, cudaMemcpyDeviceToHost, st));
+    if (diff_cal_host) CU(cudaMemcpyAsync(diff_cal_host, h->hs_diffcal, sizeof(double) * P.batch, cudaMemcpyDeviceToHost, st));
+    if (status_host) CU(cudaMemcpyAsync(status_host, h->hs_status, sizeof(int32_t) * P.batch, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ------------------------------------------------------------------ dense sqrt functions
+namespace {
+struct Scratch { double* p = nullptr; size_t cap = 0; int device = -1; };
+Scratch g_scratch;
+int get_scratch(int device, size_t count, double** out) {
+    if (g_scratch.device != device || g_scratch.cap < count) {
+        CU(cudaDeviceSynchronize());
+        if (g_scratch.p) { cudaSetDevice(g_scratch.device); cudaFree(g_scratch.p); cudaSetDevice(device); }
+        CU(cudaMalloc((void**)&g_scratch.p, count * sizeof(double)));
+        g_scratch.cap = count;
+        g_scratch.device = device;
+    }
+    *out = g_scratch.p;
+    return 0;
+}
+}  // namespace
+
+int pnmol_b200_sqrt_propagate(const double* S1, const double* S2, double* out, int r, int c1, int c2, int batch, int device,
+                              void* stream) {
+    if (!S1 || !out || r <= 0 || c1 <= 0 || c2 < 0 || batch <= 0 || (c2 > 0 && !S2)) return fail(-1, "invalid argument");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(-3, "no such CUDA device (libpnmol_b200 has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const int rows = c1 + c2;
+    const int grid = std::min(batch, 296);
+    double* W;
+    int rc = get_scratch(device, (size_t)grid * rows * r, &W);
+    if (rc) return rc;
+    const size_t smem = sizeof(double) * (rows + 4 + 2 * kWarps);
+    CU(cudaFuncSetAttribute(k_sqrt_propagate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    k_sqrt_propagate<<<grid, kThreads, smem, (cudaStream_t)stream>>>(S1, S2, out, r, c1, c2, batch, W);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pnmol_b200_sqrt_update(const double* H, const double* C, const double* meascov, double* C_out, double* K_out, double* S_out,
+                           int m, int D, int batch, int device, void* stream) {
+    if (!H || !C || !C_out || !K_out || !S_out || m <= 0 || D <= 0 || batch <= 0) return fail(-1, "invalid argument");
+    if (meascov && D < m) return fail(-1, "update_sqrt needs D >= m (src/pnmol/base/sqrt.py:55-57)");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(-3, "no such CUDA device (libpnmol_b200 has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const int grid = std::min(batch, 296);
+    double* W;
+    int rc = get_scratch(device, (size_t)grid * (D + m) * (m + D), &W);
+    if (rc) return rc;
+    const size_t smem = sizeof(double) * (D + m + 4 + 2 * kWarps);
+    CU(cudaFuncSetAttribute(k_sqrt_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    k_sqrt_update<<<grid, kThreads, smem, (cudaStream_t)stream>>>(H, C, meascov, C_out, K_out, S_out, m, D, batch, W);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

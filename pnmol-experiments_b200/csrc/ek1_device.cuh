@@ -1,0 +1,558 @@
+// Device code of the EK1 filter loop (one CTA per ensemble member).
+//
+// Reference path restated here (file:line in schmidtjonathan/pnmol-experiments):
+//   attempt_step      src/pnmol/white.py:96-146, src/pnmol/latent.py:155-225
+//   evaluate_ode      src/pnmol/white.py:169-208, src/pnmol/latent.py:237-292
+//   estimate_error    src/pnmol/white.py:153-162
+//   sqrt propagation  src/pnmol/base/sqrt.py:9-23, update src/pnmol/base/sqrt.py:34-95
+//   initialize        src/pnmol/white.py:12-80, src/pnmol/latent.py:20-134
+//
+// Layout: each CTA owns a column-major workspace W (leading dimension ld = 2D) of
+// m + D columns that stays L2-resident.  Columns m..m+D-1 first hold the predict stack
+// [(A P^-1 Cl)^T ; Ql^T] (2D x D); its R factor (= Clp^T) is then, in place, the top-right
+// block of the update matrix [[Clp^T H^T, Clp^T], [E^T, 0]] whose left m columns live in
+// W's columns 0..m-1.  Householder QR follows LAPACK dlarfg conventions
+// (beta = -sign(alpha) * norm, H = I for a zero sub-column) on the reference's own
+// matrix layout, touching only the rows inside per-column support envelopes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pnmol {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxN = 8;     // num_derivatives + 1
+constexpr int kMaxComp = 4;  // PDE components
+
+enum EMode {
+    E_STEP_WHITE = 0,      // E = blockdiag(E_sqrtm, R_sqrtm)           white.py:184
+    E_NONE = 1,            // no measurement noise                       latent.py:197
+    E_NUGGET_ONLY = 2,     // nugget * I                                 white.py:33-38, latent.py:71-76,98-103
+    E_STEP_PLUS_NUGGET = 3 // blockdiag(E_sqrtm, R_sqrtm) + nugget * I   white.py:51-56
+};
+
+struct Problem {
+    int latent, semilinear, reaction;
+    int d, n, nb, ncomp, npts, dd, D, m;
+    int wl, wb, wh, ld, batch, nparams;
+    const int32_t* Lcol; const double* Lval; const double* Ediag;
+    const int32_t* Bcol; const double* Bval; const double* Rsq;
+    const double* A1d; const double* LQ1d; const double* Lk; const double* Kg;
+    const double* diffscale; const double* priorscale; const double* rparams;
+    const int32_t* te_p; const int32_t* be_p; const int32_t* te_u; const int32_t* be_u;     // triangular input factor
+    const int32_t* te_pd;                                                                    // dense input factor
+    double* W; int32_t* Hcol; double* Hval; double* F; double* S;
+};
+
+struct Shape {  // QR row structure: rows [0,nt) top, [nt, nt+nbot) bottom
+    int nt, nbot, ncols;
+    const int32_t* te;  // nullptr = dense
+    const int32_t* be;
+};
+
+struct Smem {
+    double *vbuf, *mp, *z, *y, *xw, *xat, *red, *pv, *pinv;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) s += red[i];
+    return s;
+}
+
+__host__ __device__ __forceinline__ size_t smem_doubles(int D, int m, int dd) {
+    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 2 * kWarps + 2 * kMaxN + 8;
+}
+
+__device__ __forceinline__ Smem carve(double* base, int D, int m, int dd) {
+    Smem s;
+    s.vbuf = base;              base += 2 * D + 4;
+    s.mp = base;                base += D;
+    s.z = base;                 base += m;
+    s.y = base;                 base += m;
+    s.xw = base;                base += m;
+    s.xat = base;               base += dd;
+    s.red = base;               base += 2 * kWarps;
+    s.pv = base;                base += kMaxN;
+    s.pinv = base;
+    return s;
+}
+
+// ---------------------------------------------------------------- Householder QR
+// Unblocked, structure-aware, on the global (L2-resident) workspace.  After return the
+// upper triangle holds R and every entry below the diagonal inside the support envelope
+// is exactly zero.
+__device__ void householder_qr(double* __restrict__ W, int ld, const Shape s, double* vbuf, double* red) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nrows = s.nt + s.nbot;
+    const int nref = nrows < s.ncols ? nrows : s.ncols;
+    for (int j = 0; j < nref; ++j) {
+        int a1 = j, e1, a2, e2;
+        if (j < s.nt) {
+            e1 = s.te ? s.te[j] : s.nt - 1;
+            if (e1 > s.nt - 1) e1 = s.nt - 1;
+            if (e1 < j) e1 = j;
+            a2 = s.nt;
+            e2 = s.be ? s.be[j] : nrows - 1;
+            if (e2 > nrows - 1) e2 = nrows - 1;
+        } else {
+            e1 = s.be ? s.be[j] : nrows - 1;
+            if (e1 > nrows - 1) e1 = nrows - 1;
+            if (e1 < j) e1 = j;
+            a2 = 0;
+            e2 = -1;
+        }
+        const int len1 = e1 - a1 + 1;
+        const int len2 = e2 >= a2 ? e2 - a2 + 1 : 0;
+        const int len = len1 + len2;
+        double* col = W + (size_t)j * ld;
+        double ss = 0.0;
+        for (int c = tid; c < len; c += kThreads) {
+            const int r = c < len1 ? a1 + c : a2 + (c - len1);
+            const double x = col[r];
+            vbuf[c] = x;
+            if (c > 0) ss += x * x;
+        }
+        ss = block_sum(ss, red);
+        const double alpha = vbuf[0];
+        double tau = 0.0, beta = alpha, scale = 0.0;
+        if (ss != 0.0) {  // dlarfg: xnorm == 0 -> H = I
+            const double nrm = sqrt(alpha * alpha + ss);
+            beta = alpha >= 0.0 ? -nrm : nrm;
+            tau = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+        }
+        __syncthreads();
+        if (tau != 0.0) {
+            for (int c = tid; c < len; c += kThreads) {
+                const int r = c < len1 ? a1 + c : a2 + (c - len1);
+                vbuf[c] = c == 0 ? 1.0 : vbuf[c] * scale;
+                col[r] = c == 0 ? beta : 0.0;
+            }
+        }
+        __syncthreads();
+        if (tau != 0.0) {
+            for (int k = j + 1 + warp; k < s.ncols; k += kWarps) {
+                double* ck = W + (size_t)k * ld;
+                double dot = 0.0;
+                for (int c = lane; c < len; c += 32) {
+                    const int r = c < len1 ? a1 + c : a2 + (c - len1);
+                    dot = fma(vbuf[c], ck[r], dot);
+                }
+                dot = warp_sum(dot);
+                const double w = tau * dot;
+                if (w != 0.0) {
+                    for (int c = lane; c < len; c += 32) {
+                        const int r = c < len1 ? a1 + c : a2 + (c - len1);
+                        ck[r] = fma(-w, vbuf[c], ck[r]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- reaction terms
+// f and df of src/pnmol/pde/examples.py:151-165 (SIR), :228-235 (Lotka-Volterra),
+// :311-315 (spruce budworm); all point-wise, so df is ncomp x ncomp per mesh point.
+__device__ __forceinline__ void reaction_point(int id, const double* prm, const double* x, double* f, double* J) {
+    if (id == 1) {
+        const double g = prm[0];
+        f[0] = g * x[0] * (1.0 - x[0]);
+        J[0] = g * (1.0 - 2.0 * x[0]);
+    } else if (id == 2) {
+        const double beta = prm[0], gamma = prm[1];
+        const double s = x[0], i = x[1], r = x[2];
+        const double tot = s + i + r;
+        const double g = beta * s * i / tot;
+        const double gs = beta * i / tot - g / tot;
+        const double gi = beta * s / tot - g / tot;
+        const double gr = -g / tot;
+        f[0] = -g; f[1] = g - gamma * i; f[2] = gamma * i;
+        J[0] = -gs; J[1] = -gi; J[2] = -gr;
+        J[3] = gs;  J[4] = gi - gamma; J[5] = gr;
+        J[6] = 0.0; J[7] = gamma; J[8] = 0.0;
+    } else if (id == 3) {
+        const double a = prm[0], b = prm[1], c = prm[2], dd = prm[3];
+        const double u = x[0], v = x[1];
+        f[0] = a * u - b * u * v;
+        f[1] = c * u * v - dd * v;
+        J[0] = a - b * v; J[1] = -b * u;
+        J[2] = c * v;     J[3] = c * u - dd;
+    }
+}
+
+// ---------------------------------------------------------------- evaluate_ode
+// Builds z (smem) and the sparse rows of H (global scratch, ELL width wh) from the
+// predicted mean mp (smem), with projections p0 = E0 P, p1 = E1 P reduced to the two
+// scalars p0s, p1s.  white.py:169-208, latent.py:237-292.
+__device__ void evaluate_ode(const Problem& P, int b, const Smem& sm, double p0s, double p1s, int32_t* Hcol,
+                             double* Hval) {
+    const int tid = threadIdx.x;
+    const int n = P.n, d = P.d;
+    for (int j = tid; j < P.dd; j += kThreads) sm.xat[j] = p0s * sm.mp[j * n];
+    __syncthreads();
+    const double* prm = P.rparams ? P.rparams + (size_t)b * P.nparams : nullptr;
+    for (int i = tid; i < d; i += kThreads) {
+        const int comp = i / P.npts, pt = i - comp * P.npts;
+        const double ds = P.diffscale ? P.diffscale[(size_t)b * P.ncomp + comp] : 1.0;
+        int32_t* hc = Hcol + (size_t)i * P.wh;
+        double* hv = Hval + (size_t)i * P.wh;
+        double acc = 0.0;
+        int w = 0;
+        for (; w < P.wl; ++w) {
+            const int c = P.Lcol[(size_t)i * P.wl + w];
+            if (c >= 0) {
+                const double lv = ds * P.Lval[(size_t)i * P.wl + w];
+                acc = fma(lv, sm.xat[c], acc);
+                hc[w] = c * n;
+                hv[w] = -p0s * lv;
+            } else {
+                hc[w] = -1;
+                hv[w] = 0.0;
+            }
+        }
+        double shift = 0.0;
+        if (P.semilinear) {
+            double x[kMaxComp], f[kMaxComp], J[kMaxComp * kMaxComp];
+            for (int c = 0; c < P.ncomp; ++c) x[c] = sm.xat[c * P.npts + pt];
+            reaction_point(P.reaction, prm, x, f, J);
+            double jx = 0.0;
+            for (int c = 0; c < P.ncomp; ++c) {
+                const double jv = J[comp * P.ncomp + c];
+                jx = fma(jv, x[c], jx);
+                hc[w] = (c * P.npts + pt) * n;
+                hv[w] = -p0s * jv;
+                ++w;
+            }
+            acc += jx;
+            shift = jx - f[comp];
+        }
+        hc[w] = i * n + 1;
+        hv[w] = p1s;
+        ++w;
+        double hz = p1s * sm.mp[i * n + 1] - acc;
+        if (P.latent) {
+            hc[w] = (d + i) * n;
+            hv[w] = -p0s;
+            ++w;
+            hz -= sm.xat[d + i];
+        }
+        for (; w < P.wh; ++w) { hc[w] = -1; hv[w] = 0.0; }
+        sm.z[i] = hz + shift;
+    }
+    for (int r = tid; r < P.nb; r += kThreads) {
+        int32_t* hc = Hcol + (size_t)(d + r) * P.wh;
+        double* hv = Hval + (size_t)(d + r) * P.wh;
+        double acc = 0.0;
+        int w = 0;
+        for (; w < P.wb; ++w) {
+            const int c = P.Bcol[(size_t)r * P.wb + w];
+            if (c >= 0) {
+                const double bv = P.Bval[(size_t)r * P.wb + w];
+                acc = fma(bv, sm.xat[c], acc);
+                hc[w] = c * n;
+                hv[w] = p0s * bv;
+            } else {
+                hc[w] = -1;
+                hv[w] = 0.0;
+            }
+        }
+        for (; w < P.wh; ++w) { hc[w] = -1; hv[w] = 0.0; }
+        sm.z[d + r] = acc;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- predict stack
+// Columns m..m+D-1 of W: top D rows (A P^-1 Cl)^T, bottom D rows Ql^T.
+// white.py:104,118 / latent.py:179,194 and iwp.py:32-53, stacked_ssm.py:16-26.
+__device__ void build_predict(const Problem& P, int b, const Smem& sm, const double* __restrict__ Cl,
+                              const int32_t* te, double* Wp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = P.n, D = P.D, nd = P.n * P.d;
+    const double ps = P.priorscale ? P.priorscale[b] : 1.0;
+    for (int i = warp; i < D; i += kWarps) {
+        double* col = Wp + (size_t)i * P.ld;
+        const int blk = i / n, ii = i - blk * n;
+        double coef[kMaxN];
+        for (int s = 0; s < n; ++s) coef[s] = P.A1d[ii * n + s];
+        const int tend = te[i];
+        for (int k = lane; k <= tend; k += 32) {
+            double acc = 0.0;
+            for (int s = 0; s < n; ++s) acc = fma(coef[s], sm.pinv[s] * Cl[(size_t)(blk * n + s) * D + k], acc);
+            col[k] = acc;
+        }
+        // Ql^T column i = row i of Ql, entries 0..i
+        if (i < nd) {
+            for (int k = lane; k <= i; k += 32) {
+                const int kb = k / n, kk = k - kb * n;
+                col[D + k] = (ps * P.Lk[(size_t)blk * P.d + kb]) * P.LQ1d[ii * n + kk];
+            }
+        } else {
+            const int comp = (blk - P.d) / P.npts;
+            const double ds = P.diffscale ? P.diffscale[(size_t)b * P.ncomp + comp] : 1.0;
+            const double eb = ds * P.Ediag[blk - P.d];
+            for (int k = lane; k <= i; k += 32) {
+                const int kb = k / n, kk = k - kb * n;
+                col[D + k] = kb == blk ? eb * P.LQ1d[ii * n + kk] : 0.0;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- error estimate
+// white.py:153-162 in closed form: with H = At E0 + p1 It E1 (At = order-0 entries of H,
+// It = [I_d; 0]) and Ql Ql^T = K (x) q,  H Q H^T = q00 At K At^T + q01 p1 (At K It^T + It K At^T)
+// + q11 p1^2 It K It^T.  sigma^2 = z^T S^-1 z / m through a Cholesky factorisation of S.
+__device__ void error_estimate(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode,
+                               double nugget, const int32_t* Hcol, const double* Hval, double* F, double* S,
+                               double* err_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = P.n, d = P.d, m = P.m;
+    const double ps = P.priorscale ? P.priorscale[b] : 1.0;
+    const double ps2 = ps * ps;
+    double q00 = 0, q01 = 0, q11 = 0;
+    for (int s = 0; s < n; ++s) {
+        q00 = fma(P.LQ1d[s], P.LQ1d[s], q00);
+        q01 = fma(P.LQ1d[s], P.LQ1d[n + s], q01);
+        q11 = fma(P.LQ1d[n + s], P.LQ1d[n + s], q11);
+    }
+    // F = At K  (m x d)
+    for (int r = warp; r < m; r += kWarps) {
+        for (int k = lane; k < d; k += 32) {
+            double acc = 0.0;
+            for (int w = 0; w < P.wh; ++w) {
+                const int c = Hcol[(size_t)r * P.wh + w];
+                if (c >= 0 && (c % n) == 0 && c < n * d) acc = fma(Hval[(size_t)r * P.wh + w], ps2 * P.Kg[(size_t)(c / n) * d + k], acc);
+            }
+            F[(size_t)r * d + k] = acc;
+        }
+    }
+    __syncthreads();
+    // S (m x m), row-major, full
+    for (int r = warp; r < m; r += kWarps) {
+        for (int rp = lane; rp < m; rp += 32) {
+            double acc = 0.0;
+            for (int w = 0; w < P.wh; ++w) {
+                const int c = Hcol[(size_t)rp * P.wh + w];
+                if (c >= 0 && (c % n) == 0 && c < n * d) acc = fma(F[(size_t)r * d + c / n], Hval[(size_t)rp * P.wh + w], acc);
+            }
+            double val = q00 * acc;
+            double cross = 0.0;
+            if (rp < d) cross += F[(size_t)r * d + rp];
+            if (r < d) cross += F[(size_t)rp * d + r];
+            val += q01 * p1s * cross;
+            if (r < d && rp < d) val += q11 * p1s * p1s * ps2 * P.Kg[(size_t)r * d + rp];
+            // E E^T
+            double ee = 0.0;
+            if (emode == E_STEP_WHITE) {
+                if (r < d && rp == r) {
+                    const int comp = r / P.npts;
+                    const double ds = P.diffscale ? P.diffscale[(size_t)b * P.ncomp + comp] : 1.0;
+                    const double e = ds * P.Ediag[r];
+                    ee = e * e;
+                } else if (r >= d && rp >= d) {
+                    for (int k = 0; k < P.nb; ++k) ee = fma(P.Rsq[(size_t)(r - d) * P.nb + k], P.Rsq[(size_t)(rp - d) * P.nb + k], ee);
+                }
+            }
+            S[(size_t)r * m + rp] = val + ee;
+        }
+    }
+    __syncthreads();
+    for (int r = tid; r < m; r += kThreads) sm.y[r] = S[(size_t)r * m + r];  // diag(S) before factorisation
+    __syncthreads();
+    // right-looking Cholesky on the lower triangle (row-major)
+    for (int k = 0; k < m; ++k) {
+        const double piv = sqrt(S[(size_t)k * m + k]);
+        __syncthreads();
+        for (int r = k + tid; r < m; r += kThreads) S[(size_t)r * m + k] = r == k ? piv : S[(size_t)r * m + k] / piv;
+        __syncthreads();
+        for (int r = k + 1 + warp; r < m; r += kWarps) {
+            const double lrk = S[(size_t)r * m + k];
+            for (int c = k + 1 + lane; c <= r; c += 32) S[(size_t)r * m + c] = fma(-lrk, S[(size_t)c * m + k], S[(size_t)r * m + c]);
+        }
+        __syncthreads();
+    }
+    // forward solve L u = z  (xw <- u), row-oriented dot form
+    for (int r = tid; r < m; r += kThreads) sm.xw[r] = sm.z[r];
+    __syncthreads();
+    for (int k = 0; k < m; ++k) {
+        if (warp == 0) {
+            double acc = 0.0;
+            for (int c = lane; c < k; c += 32) acc = fma(S[(size_t)k * m + c], sm.xw[c], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) sm.xw[k] = (sm.xw[k] - acc) / S[(size_t)k * m + k];
+        }
+        __syncthreads();
+    }
+    double part = 0.0;
+    for (int r = tid; r < m; r += kThreads) part = fma(sm.xw[r], sm.xw[r], part);
+    const double sigma = sqrt(block_sum(part, sm.red) / m);
+    if (err_out)
+        for (int i = tid; i < d; i += kThreads) err_out[i] = dt * (sqrt(sm.y[i]) * sigma);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- update stage
+// E^T entry (row rp of column r of the bottom-left block), see EMode.
+__device__ __forceinline__ double meas_sqrtm_entry(const Problem& P, int b, EMode emode, double nugget, int r,
+                                                   int rp) {
+    double v = 0.0;
+    if (emode == E_STEP_WHITE || emode == E_STEP_PLUS_NUGGET) {
+        if (r < P.d) {
+            if (rp == r) {
+                const int comp = r / P.npts;
+                const double ds = P.diffscale ? P.diffscale[(size_t)b * P.ncomp + comp] : 1.0;
+                v = ds * P.Ediag[r];
+            }
+        } else if (rp >= P.d) {
+            v = P.Rsq[(size_t)(r - P.d) * P.nb + (rp - P.d)];
+        }
+    }
+    if ((emode == E_NUGGET_ONLY || emode == E_STEP_PLUS_NUGGET) && rp == r) v += nugget;
+    return v;
+}
+
+// Assemble the update block matrix of sqrt.py:60-65 / 82-87 in W (compact form: the
+// D - m structurally zero rows of the reference's 2D x (m+D) matrix are dropped), factor
+// it, and apply the result to the predicted mean.  On entry the top-right block holds
+// R = Clp^T in place (Rsrc == nullptr) or is read from the row-major lower-triangular
+// factor Rsrc (D x D).  mcur = number of measurement rows of this update.
+struct UpdateOut {
+    double* mean_out;  // (n, dd) or nullptr (then the new flat mean is left in sm.mp)
+    double* chol_out;  // (D, D) row-major
+    double* diff_out;  // scalar or nullptr
+    double* ref_out;   // (d) or nullptr
+    bool scale_by_p;   // multiply by the Nordsieck preconditioner on output
+};
+
+__device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, EMode emode, double nugget,
+                             const double* __restrict__ Rsrc, const int32_t* te, const int32_t* be,
+                             const int32_t* Hcol, const double* Hval, double* W, const UpdateOut out,
+                             int* nonfinite) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = P.D, ld = P.ld, n = P.n;
+    const int nbot = emode == E_NONE ? 0 : mcur;
+    const int nrows = D + nbot;
+    // The right block always starts at column P.m of the workspace (where the predict QR
+    // left R); an update with fewer measurement rows (initialisation on y0) uses the
+    // columns P.m - mcur .. P.m - 1 for its left block.
+    double* Wl = W + (size_t)(P.m - mcur) * ld;
+    double* Wr = W + (size_t)P.m * ld;
+    const int ncols = mcur + D;
+
+    // right block: rows 0..k hold R (copied from Rsrc if given), the rest of the envelope is zero
+    for (int k = warp; k < D; k += kWarps) {
+        double* col = Wr + (size_t)k * ld;
+        int tend = te ? te[mcur + k] : D - 1;
+        if (tend > D - 1) tend = D - 1;
+        if (Rsrc) {
+            for (int i = lane; i <= k; i += 32) col[i] = Rsrc[(size_t)k * D + i];
+        }
+        for (int i = k + 1 + lane; i <= tend; i += 32) col[i] = 0.0;
+        int bend = be ? be[mcur + k] : nrows - 1;
+        if (bend > nrows - 1) bend = nrows - 1;
+        for (int i = D + lane; i <= bend; i += 32) col[i] = 0.0;
+    }
+    __syncthreads();
+    // left block: top = R H^T (column r = sum over the sparse row r of H), bottom = E^T
+    for (int r = warp; r < mcur; r += kWarps) {
+        double* col = Wl + (size_t)r * ld;
+        int tend = te ? te[r] : D - 1;
+        if (tend > D - 1) tend = D - 1;
+        for (int i = lane; i <= tend; i += 32) {
+            double acc = 0.0;
+            for (int w = 0; w < P.wh; ++w) {
+                const int c = Hcol[(size_t)r * P.wh + w];
+                if (c >= i) acc = fma(Hval[(size_t)r * P.wh + w], Wr[(size_t)c * ld + i], acc);  // R[i][c], zero for i > c
+            }
+            col[i] = acc;
+        }
+        int bend = be ? be[r] : nrows - 1;
+        if (bend > nrows - 1) bend = nrows - 1;
+        for (int i = D + lane; i <= bend; i += 32) col[i] = meas_sqrtm_entry(P, b, emode, nugget, r, i - D);
+    }
+    __syncthreads();
+
+    Shape sh;
+    sh.nt = D; sh.nbot = nbot; sh.ncols = ncols; sh.te = te; sh.be = be;
+    householder_qr(Wl, ld, sh, sm.vbuf, sm.red);
+
+    // R1 = Wl[0:m, 0:m] (upper, column-major).  y = R1^-T z (for the mean),  x = R1^-1 z (quirk Q1,
+    // white.py:125 / latent.py:204).
+    for (int r = tid; r < mcur; r += kThreads) { sm.y[r] = sm.z[r]; sm.xw[r] = sm.z[r]; }
+    __syncthreads();
+    for (int k = 0; k < mcur; ++k) {  // forward: dot form over contiguous column k of R1
+        if (warp == 0) {
+            const double* ck = Wl + (size_t)k * ld;
+            double acc = 0.0;
+            for (int c = lane; c < k; c += 32) acc = fma(ck[c], sm.y[c], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) sm.y[k] = (sm.y[k] - acc) / ck[k];
+        }
+        __syncthreads();
+    }
+    for (int k = mcur - 1; k >= 0; --k) {  // backward: axpy form over contiguous column k of R1
+        const double* ck = Wl + (size_t)k * ld;
+        const double xk = sm.xw[k] / ck[k];
+        __syncthreads();
+        for (int c = tid; c < k; c += kThreads) sm.xw[c] = fma(-xk, ck[c], sm.xw[c]);
+        if (tid == 0) sm.xw[k] = xk;
+        __syncthreads();
+    }
+    double part = 0.0;
+    for (int r = tid; r < mcur; r += kThreads) part = fma(sm.xw[r], sm.xw[r], part);
+    const double diff = block_sum(part, sm.red) / mcur;
+    if (out.diff_out && tid == 0) *out.diff_out = diff;
+
+    // m_new = mp - R2^T y   (white.py:123, sqrt.py:72)
+    for (int k = warp; k < D; k += kWarps) {
+        const double* col = Wr + (size_t)k * ld;
+        double acc = 0.0;
+        for (int i = lane; i < mcur; i += 32) acc = fma(col[i], sm.y[i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) sm.mp[k] -= acc;
+    }
+    __syncthreads();
+    int bad = 0;
+    if (!(diff == diff) || isinf(diff)) bad = 1;
+    // outputs: mean (n, dd) = P m_new reshaped (white.py:132-135); factor = P R3^T (white.py:132)
+    for (int k = tid; k < D; k += kThreads) {
+        const int j = k / n, i = k - j * n;
+        const double v = out.scale_by_p ? sm.pv[i] * sm.mp[k] : sm.mp[k];
+        if (out.mean_out) out.mean_out[(size_t)i * P.dd + j] = v;
+        if (out.ref_out && i == 0 && j < P.d) out.ref_out[j] = fabs(v);
+        if (!isfinite(v)) bad = 1;
+    }
+    for (int r = warp; r < D; r += kWarps) {
+        // row r of the factor = column m + r of R, rows m.. (R3[c][r] = W[(m + r) ld + m + c])
+        const double* col = Wr + (size_t)r * ld + mcur;
+        const double pr = out.scale_by_p ? sm.pv[r % n] : 1.0;
+        double* orow = out.chol_out + (size_t)r * D;
+        for (int c = lane; c < D; c += 32) {
+            double v = 0.0;
+            if (c <= r && mcur + c < nrows) v = pr * col[c];
+            orow[c] = v;
+            if (!isfinite(v)) bad = 1;
+        }
+    }
+    if (bad) atomicOr(nonfinite, 1);
+    __syncthreads();
+}
+
+}  // namespace pnmol

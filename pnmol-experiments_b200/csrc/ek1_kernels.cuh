@@ -1,0 +1,279 @@
+// __global__ entry points built from the device phases in ek1_device.cuh.
+#pragma once
+#include "ek1_device.cuh"
+
+namespace pnmol {
+
+struct RunArgs {
+    int nsteps, flags, final_in_b;
+    double pv0[kMaxN], pinv0[kMaxN], dt0, tnew0;              // single-step parameters (nsteps == 1, by value)
+    const double *dts, *tnew, *pv, *pinv;                     // multi-step parameters (device arrays)
+    double *mean_a, *chol_a, *mean_b, *chol_b;                // ping-pong state; step 0 reads a
+    double *err_out, *ref_out, *diff_last, *diff_sum, *mean_traj, *chol_traj;
+    int32_t* status;
+};
+
+struct InitArgs {
+    const double* y0;
+    double t0, prior_scale0, nugget;
+    double *mean_out, *chol_out;
+    int32_t* status;
+};
+
+// One EK1 step for member b: state (mean_in, chol_in) -> (mean_out, chol_out).
+__device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, double dt, double tnew,
+                         const double* mean_in, const double* chol_in, double* mean_out, double* chol_out,
+                         double* err_out, double* ref_out, double* diff_out, int flags, int* nonfinite) {
+    const int tid = threadIdx.x;
+    const int n = P.n, D = P.D;
+    double* W = P.W + (size_t)slot * P.ld * (P.m + P.D);
+    int32_t* Hcol = P.Hcol + (size_t)slot * P.m * P.wh;
+    double* Hval = P.Hval + (size_t)slot * P.m * P.wh;
+    // [setup + predict]  m = P^-1 mean (flattened column-major, index j n + i), mp = A m   white.py:104-107
+    for (int k = tid; k < D; k += kThreads) {
+        const int j = k / n, i = k - j * n;
+        double acc = 0.0;
+        for (int s = 0; s < n; ++s) acc = fma(P.A1d[i * n + s], sm.pinv[s] * mean_in[(size_t)s * P.dd + j], acc);
+        sm.mp[k] = acc;
+    }
+    __syncthreads();
+    evaluate_ode(P, b, sm, sm.pv[0], sm.pv[1], Hcol, Hval);
+    const bool dense = flags & 1;
+    build_predict(P, b, sm, chol_in, dense ? P.te_pd : P.te_p, W + (size_t)P.m * P.ld);
+    Shape sp;
+    sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p;
+    householder_qr(W + (size_t)P.m * P.ld, P.ld, sp, sm.vbuf, sm.red);
+    if (!P.latent && !(flags & 2)) {
+        error_estimate(P, b, sm, sm.pv[1], dt, E_STEP_WHITE, 0.0, Hcol, Hval, P.F + (size_t)slot * P.m * P.d,
+                       P.S + (size_t)slot * P.m * P.m, err_out);
+    }
+    UpdateOut out;
+    out.mean_out = mean_out; out.chol_out = chol_out; out.diff_out = diff_out;
+    out.ref_out = P.latent ? nullptr : ref_out; out.scale_by_p = true;
+    update_stage(P, b, sm, P.m, P.latent ? E_NONE : E_STEP_WHITE, 0.0, nullptr, P.te_u, P.be_u, Hcol, Hval, W, out,
+                 nonfinite);
+}
+
+__global__ void __launch_bounds__(kThreads) k_run(const Problem P, const RunArgs a) {
+    extern __shared__ double smem_raw[];
+    const Smem sm = carve(smem_raw, P.D, P.m, P.dd);
+    __shared__ int nonfinite;
+    __shared__ double diff_s;
+    const int tid = threadIdx.x;
+    const size_t msz = (size_t)P.D, csz = (size_t)P.D * P.D;
+    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+        if (tid == 0) nonfinite = 0;
+        double diffsum = 0.0;
+        __syncthreads();
+        for (int s = 0; s < a.nsteps; ++s) {
+            double dt, tnew;
+            if (a.nsteps == 1 && a.pv == nullptr) {
+                if (tid < P.n) { sm.pv[tid] = a.pv0[tid]; sm.pinv[tid] = a.pinv0[tid]; }
+                dt = a.dt0; tnew = a.tnew0;
+            } else {
+                if (tid < P.n) { sm.pv[tid] = a.pv[(size_t)s * P.n + tid]; sm.pinv[tid] = a.pinv[(size_t)s * P.n + tid]; }
+                dt = a.dts[s]; tnew = a.tnew[s];
+            }
+            __syncthreads();
+            const bool even = (s & 1) == 0;
+            const double* min_ = (even ? a.mean_a : a.mean_b) + b * msz;
+            const double* cin_ = (even ? a.chol_a : a.chol_b) + b * csz;
+            double* mout = (even ? a.mean_b : a.mean_a) + b * msz;
+            double* cout = (even ? a.chol_b : a.chol_a) + b * csz;
+            // only the first step may see a user-supplied (possibly dense) factor
+            const int flags = s == 0 ? a.flags : (a.flags & ~1);
+            ek1_step(P, b, blockIdx.x, sm, dt, tnew, min_, cin_, mout, cout,
+                     a.err_out ? a.err_out + (size_t)b * P.d : nullptr,
+                     a.ref_out ? a.ref_out + (size_t)b * P.d : nullptr, &diff_s, flags, &nonfinite);
+            __syncthreads();
+            diffsum += diff_s;
+            if (a.mean_traj) {
+                double* mt = a.mean_traj + ((size_t)s * P.batch + b) * msz;
+                for (size_t k = tid; k < msz; k += kThreads) mt[k] = mout[k];
+            }
+            if (a.chol_traj) {
+                double* ct = a.chol_traj + ((size_t)s * P.batch + b) * csz;
+                for (size_t k = tid; k < csz; k += kThreads) ct[k] = cout[k];
+            }
+            __syncthreads();
+        }
+        if ((a.nsteps & 1) && !a.final_in_b) {  // result sits in b: bring it home
+            const double* ms = a.mean_b + b * msz; const double* cs = a.chol_b + b * csz;
+            double* md = a.mean_a + b * msz; double* cd = a.chol_a + b * csz;
+            for (size_t k = tid; k < msz; k += kThreads) md[k] = ms[k];
+            for (size_t k = tid; k < csz; k += kThreads) cd[k] = cs[k];
+        }
+        if (tid == 0) {
+            if (a.diff_last) a.diff_last[b] = diff_s;
+            if (a.diff_sum) a.diff_sum[b] = diffsum;
+            if (a.status) a.status[b] = nonfinite;
+        }
+        __syncthreads();
+    }
+}
+
+// initialize(): two square-root updates on a Kronecker-structured prior factor.
+__global__ void __launch_bounds__(kThreads) k_init(const Problem P, const InitArgs a) {
+    extern __shared__ double smem_raw[];
+    const Smem sm = carve(smem_raw, P.D, P.m, P.dd);
+    __shared__ int nonfinite;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = P.n, d = P.d, D = P.D, nd = P.n * P.d;
+    const int slot = blockIdx.x;
+    double* W = P.W + (size_t)slot * P.ld * (P.m + P.D);
+    int32_t* Hcol = P.Hcol + (size_t)slot * P.m * P.wh;
+    double* Hval = P.Hval + (size_t)slot * P.m * P.wh;
+    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+        if (tid == 0) nonfinite = 0;
+        double* chol = a.chol_out + (size_t)b * D * D;
+        double* mean = a.mean_out + (size_t)b * D;
+        const double ps = P.priorscale ? P.priorscale[b] : 1.0;
+        // C0 = kron(Lk, c0 I_n) (white.py:23-24); latent: blockdiag(., kron(E_sqrtm, c0 I_n)) (latent.py:60-62,81-83)
+        for (int r = warp; r < D; r += kWarps) {
+            const int rb = r / n, ri = r - rb * n;
+            for (int c = lane; c < D; c += 32) {
+                const int cb = c / n, ci = c - cb * n;
+                double v = 0.0;
+                if (ri == ci && c <= r) {
+                    if (r < nd) {
+                        v = a.prior_scale0 * (ps * P.Lk[(size_t)rb * d + cb]);
+                    } else if (rb == cb) {
+                        const int comp = (rb - d) / P.npts;
+                        const double ds = P.diffscale ? P.diffscale[(size_t)b * P.ncomp + comp] : 1.0;
+                        v = a.prior_scale0 * (ds * P.Ediag[rb - d]);
+                    }
+                }
+                chol[(size_t)r * D + c] = v;
+            }
+        }
+        // update on the initial condition: H = E0, z = 0 - y0 so that m = K y0 (white.py:32-39)
+        for (int k = tid; k < D; k += kThreads) sm.mp[k] = 0.0;
+        for (int i = tid; i < d; i += kThreads) {
+            sm.z[i] = -a.y0[(size_t)b * d + i];
+            for (int w = 0; w < P.wh; ++w) { Hcol[(size_t)i * P.wh + w] = w == 0 ? i * n : -1; Hval[(size_t)i * P.wh + w] = w == 0 ? 1.0 : 0.0; }
+        }
+        if (tid < n) { sm.pv[tid] = 1.0; sm.pinv[tid] = 1.0; }
+        __syncthreads();
+        UpdateOut o1;
+        o1.mean_out = nullptr; o1.chol_out = chol; o1.diff_out = nullptr; o1.ref_out = nullptr; o1.scale_by_p = false;
+        update_stage(P, b, sm, d, E_NUGGET_ONLY, a.nugget, chol, nullptr, nullptr, Hcol, Hval, W, o1, &nonfinite);
+        // linearise the PDE at t0 without preconditioning (white.py:42-48, latent.py:86-95)
+        evaluate_ode(P, b, sm, 1.0, 1.0, Hcol, Hval);
+        UpdateOut o2;
+        o2.mean_out = mean; o2.chol_out = chol; o2.diff_out = nullptr; o2.ref_out = nullptr; o2.scale_by_p = false;
+        update_stage(P, b, sm, P.m, P.latent ? E_NUGGET_ONLY : E_STEP_PLUS_NUGGET, a.nugget, chol, nullptr, nullptr, Hcol,
+                     Hval, W, o2, &nonfinite);
+        if (tid == 0 && a.status) a.status[b] = nonfinite;
+        __syncthreads();
+    }
+}
+
+// cov_sqrtm *= sqrt(mean local diffusion)   pdefilter.py:113-116
+__global__ void k_rescale(double* chol, const double* diff_sum, double* diff_cal, int nsteps, size_t csz, int batch) {
+    const int b = blockIdx.y;
+    const double cal = diff_sum[b] / nsteps;
+    const double s = sqrt(cal);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && diff_cal) diff_cal[b] = cal;
+    double* c = chol + (size_t)b * csz;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < csz; k += (size_t)gridDim.x * blockDim.x) c[k] *= s;
+}
+
+// K = Lk Lk^T (spatial Gram matrix), once per set_prior.
+__global__ void k_gram(const double* Lk, double* Kg, int d) {
+    const int r = blockIdx.x;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        double acc = 0.0;
+        const int kmax = r < c ? r : c;
+        for (int k = 0; k <= kmax; ++k) acc = fma(Lk[(size_t)r * d + k], Lk[(size_t)c * d + k], acc);
+        Kg[(size_t)r * d + c] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- dense sqrt entry points
+// propagate_cholesky_factor for dense S1 (r x c1), S2 (r x c2): QR of the (c1+c2) x r stack.
+__global__ void __launch_bounds__(kThreads) k_sqrt_propagate(const double* S1, const double* S2, double* out, int r,
+                                                            int c1, int c2, int batch, double* Wall) {
+    extern __shared__ double smem_raw[];
+    double* vbuf = smem_raw;
+    double* red = smem_raw + (c1 + c2) + 4;
+    const int tid = threadIdx.x;
+    const int rows = c1 + c2, ld = rows;
+    const int k = rows < r ? rows : r;
+    double* W = Wall + (size_t)blockIdx.x * ld * r;
+    for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+        for (int idx = tid; idx < rows * r; idx += kThreads) {
+            const int col = idx / rows, row = idx - col * rows;
+            W[(size_t)col * ld + row] = row < c1 ? S1[((size_t)b * r + col) * c1 + row] : S2[((size_t)b * r + col) * c2 + (row - c1)];
+        }
+        __syncthreads();
+        Shape sh; sh.nt = rows; sh.nbot = 0; sh.ncols = r; sh.te = nullptr; sh.be = nullptr;
+        householder_qr(W, ld, sh, vbuf, red);
+        for (int idx = tid; idx < r * k; idx += kThreads) {  // out[i][j] = R[j][i], i < r, j < k
+            const int i = idx / k, j = idx - i * k;
+            out[(size_t)b * r * k + idx] = j <= i ? W[(size_t)i * ld + j] : 0.0;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_sqrt_update(const double* H, const double* C, const double* E, double* C_out,
+                                                         double* K_out, double* S_out, int m, int D, int batch,
+                                                         double* Wall) {
+    extern __shared__ double smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nbot = E ? m : 0;
+    const int rows = D + nbot, ld = D + m, ncols = m + D;
+    double* vbuf = smem_raw;
+    double* red = smem_raw + ld + 4;
+    double* W = Wall + (size_t)blockIdx.x * ld * ncols;
+    for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+        const double* Hb = H + (size_t)b * m * D;
+        const double* Cb = C + (size_t)b * D * D;
+        // right block: C^T (column k = row k of C), bottom zero
+        for (int k = warp; k < D; k += kWarps) {
+            double* col = W + (size_t)(m + k) * ld;
+            for (int i = lane; i < D; i += 32) col[i] = Cb[(size_t)k * D + i];
+            for (int i = D + lane; i < rows; i += 32) col[i] = 0.0;
+        }
+        // left block: C^T H^T on top, E^T below
+        for (int r = warp; r < m; r += kWarps) {
+            double* col = W + (size_t)r * ld;
+            for (int i = lane; i < D; i += 32) {
+                double acc = 0.0;
+                for (int k = 0; k < D; ++k) acc = fma(Cb[(size_t)k * D + i], Hb[(size_t)r * D + k], acc);
+                col[i] = acc;
+            }
+            if (E) for (int i = lane; i < m; i += 32) col[D + i] = E[((size_t)b * m + r) * m + i];
+        }
+        __syncthreads();
+        Shape sh; sh.nt = D; sh.nbot = nbot; sh.ncols = ncols; sh.te = nullptr; sh.be = nullptr;
+        householder_qr(W, ld, sh, vbuf, red);
+        // S_out = R1^T, C_out = R3^T
+        for (int idx = tid; idx < m * m; idx += kThreads) {
+            const int i = idx / m, j = idx - i * m;
+            S_out[(size_t)b * m * m + idx] = j <= i ? W[(size_t)i * ld + j] : 0.0;
+        }
+        for (int idx = tid; idx < D * D; idx += kThreads) {
+            const int i = idx / D, j = idx - i * D;
+            double v = 0.0;
+            if (j <= i && m + j < rows) v = W[(size_t)(m + i) * ld + m + j];
+            C_out[(size_t)b * D * D + idx] = v;
+        }
+        __syncthreads();
+        // gain K = (R1^-1 R2)^T, one warp per column of R2 (back substitution, axpy form)
+        for (int k = warp; k < D; k += kWarps) {
+            double* col = W + (size_t)(m + k) * ld;
+            for (int i = m - 1; i >= 0; --i) {
+                const double* ri = W + (size_t)i * ld;
+                const double xi = col[i] / ri[i];
+                __syncwarp();
+                for (int c = lane; c < i; c += 32) col[c] = fma(-xi, ri[c], col[c]);
+                if (lane == 0) K_out[((size_t)b * D + k) * m + i] = xi;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pnmol

@@ -1,0 +1,288 @@
+"""GPU parity tests: the CUDA path (through the Python solver API -> ctypes -> C ABI)
+against the NumPy oracle on identical inputs.  Tolerances are the north-star ones: means
+to rtol 1e-9, covariances as L L^T to rtol 1e-8, in the per-derivative-block norm."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ek1_np, sqrt_np
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+KIND_CASES = [("heat", "white_linear", "dirichlet", 6), ("heat", "white_linear", "neumann", 6),
+              ("heat", "latent_linear", "dirichlet", 6), ("heat", "latent_linear", "neumann", 6),
+              ("spruce", "white_semilinear", "dirichlet", 6), ("spruce", "white_semilinear", "neumann", 6),
+              ("spruce", "latent_semilinear", "dirichlet", 6), ("spruce", "latent_semilinear", "neumann", 6),
+              ("sir", "white_semilinear", "neumann", 5), ("lv", "white_semilinear", "neumann", 6),
+              ("sir", "latent_semilinear", "neumann", 4), ("heat", "white_linear", "dirichlet", 50),
+              ("sir", "white_semilinear", "neumann", 17)]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__
+
+    __graft_entry__.ensure_built()
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------- sqrt primitives
+@pytest.mark.parametrize("shape", [(2, 2, 2), (1, 2, 1), (5, 9, 5), (12, 12, 4), (40, 64, 17)])
+def test_propagate_cholesky_factor(shape):
+    from pnmol_b200.base import sqrt
+
+    r, c1, c2 = shape
+    rng = np.random.default_rng(0)
+    S1, S2 = rng.standard_normal((r, c1)), rng.standard_normal((r, c2))
+    out = _np(sqrt.propagate_cholesky_factor(S1, S2))
+    ref = sqrt_np.chol_of_sum(S1, S2)
+    assert out.shape == ref.shape
+    assert np.allclose(out, np.tril(out))
+    assert np.allclose(out @ out.T, S1 @ S1.T + S2 @ S2.T, rtol=1e-12, atol=1e-12)
+    assert np.allclose(out, ref, rtol=1e-9, atol=1e-12)  # same signs as LAPACK (dlarfg convention)
+    outb = _np(sqrt.batched_propagate_cholesky_factor(np.stack([S1, 2 * S1]), np.stack([S2, 2 * S2])))
+    assert np.allclose(outb[0], out) and np.allclose(outb[1], 2 * out)
+    St = np.vstack((S1.T, S2.T))
+    assert np.allclose(_np(sqrt.sqrtm_to_cholesky(St)), ref, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("m,D", [(2, 2), (1, 2), (3, 9), (8, 18), (20, 33)])
+@pytest.mark.parametrize("noise", [True, False])
+def test_update_sqrt(m, D, noise):
+    """tests/test_base/test_sqrt.py:49-109 of the reference + equality with the oracle."""
+    from pnmol_b200.base import sqrt
+
+    rng = np.random.default_rng(m * 100 + D)
+    H = rng.standard_normal((m, D))
+    C = np.tril(rng.standard_normal((D, D))) + 2 * np.eye(D)
+    E = np.tril(rng.standard_normal((m, m))) * 0.3
+    if noise:
+        Cn, K, Sl = map(_np, sqrt.update_sqrt(H, C, E))
+    else:
+        Cn, K, Sl = map(_np, sqrt.update_sqrt_no_meascov(H, C))
+    Cr, Kr, Sr = sqrt_np.measurement_update(H, C, E if noise else None)
+    S = H @ C @ C.T @ H.T + (E @ E.T if noise else 0)
+    Kx = C @ C.T @ H.T @ np.linalg.inv(S)
+    assert Cn.shape == (D, D) and K.shape == (D, m) and Sl.shape == (m, m)
+    assert np.allclose(Cn @ Cn.T, C @ C.T - Kx @ S @ Kx.T, atol=1e-10)
+    assert np.allclose(Cn, np.tril(Cn)) and np.allclose(Sl, np.tril(Sl))
+    assert np.allclose(K, Kx, rtol=1e-8, atol=1e-10) and np.allclose(K, Kr, rtol=1e-8, atol=1e-10)
+    assert np.allclose(Sl @ Sl.T, S, rtol=1e-10) and np.allclose(Sl, Sr, rtol=1e-9, atol=1e-12)
+    assert np.allclose(Cn @ Cn.T, Cr @ Cr.T, atol=1e-10)
+
+
+# ------------------------------------------------------------------------- EK1 steps
+@pytest.mark.parametrize("name,kind,bcond,num", KIND_CASES)
+def test_initialize_and_steps_from_oracle_state(name, kind, bcond, num):
+    """Every step starts from the oracle's state: pure per-step parity (no error accumulation)."""
+    from pnmol_b200 import pdefilter
+    from pnmol_b200.base import rv
+
+    case = cases.make_case(name, num=num, bcond=bcond)
+    n = case["nu"] + 1
+    solver = cases.make_solver(kind, case)
+    init, stepf, semil = ek1_np.KINDS[kind]
+    st = init(case["opde"], case["nu"], case["gram_sqrtm"], 1.0, semil)
+    s0 = solver.initialize(case["pde"])
+    assert s0.t == case["pde"].t0 and s0.error_estimate is None and s0.diffusion_squared_local == []
+    assert cases.cov_excess(_np(s0.y.cov_sqrtm), st.cov_sqrtm, n) < 1
+    if not (kind.startswith("latent") and bcond == "neumann"):
+        # latent + Neumann + an initial condition that violates the BC is conditioned ~1e5..1e6:
+        # the reference's own result is only reproducible to ~1e-5 there ("conditioning floor")
+        assert cases.mean_excess(_np(s0.y.mean), st.mean) < 1
+    dev = s0.y.mean.device
+    for _ in range(3):
+        gstate = pdefilter.PDEFilterState(t=st.t, y=rv.MultivariateNormal(torch.tensor(st.mean, device=dev),
+                                                                         torch.tensor(st.cov_sqrtm, device=dev)),
+                                          error_estimate=None, reference_state=None, diffusion_squared_local=None)
+        new, info = solver.attempt_step(gstate, case["dt"], case["pde"])
+        st = stepf(case["opde"], st, case["dt"], case["nu"], case["gram_sqrtm"], semil)
+        assert info == dict(num_f_evaluations=1, num_df_evaluations=1)
+        assert new.t == st.t
+        L = _np(new.y.cov_sqrtm)
+        assert np.array_equal(np.triu(L, 1), np.zeros_like(L))
+        assert cases.mean_excess(_np(new.y.mean), st.mean) < 1
+        assert cases.cov_excess(L, st.cov_sqrtm, n) < 1
+        # same inputs + LAPACK's dlarfg sign convention => the quirk-Q1 diffusion agrees too
+        assert float(new.diffusion_squared_local) == pytest.approx(float(st.diffusion_squared_local), rel=1e-7)
+        if kind.startswith("white"):
+            assert np.allclose(_np(new.error_estimate), st.error_estimate, rtol=1e-7)
+            assert np.allclose(_np(new.reference_state), st.reference_state, rtol=1e-9, atol=1e-300)
+        else:
+            assert new.error_estimate is None and new.reference_state is None
+
+
+@pytest.mark.parametrize("name,kind,bcond,num", [c for c in KIND_CASES if not (c[1].startswith("latent") and c[2] == "neumann")])
+def test_solve_trajectory(name, kind, bcond, num):
+    """Free-running trajectory (exactly representable dt): solve() against the oracle's solve()."""
+    case = cases.make_case(name, num=num, bcond=bcond, tmax=0.75)
+    n = case["nu"] + 1
+    sol = cases.make_solver(kind, case).solve(case["pde"])
+    ref = ek1_np.solve(kind, case["opde"], case["dt"], case["nu"], case["gram_sqrtm"])
+    assert np.array_equal(np.asarray(sol.t), ref.t)
+    assert sol.info == ref.info
+    mean, chol = _np(sol.mean), _np(sol.cov_sqrtm)
+    assert mean.shape == ref.mean.shape and chol.shape == ref.cov_sqrtm.shape
+    for k in range(len(ref.t)):
+        assert cases.mean_excess(mean[k], ref.mean[k]) < 1, k
+        assert cases.cov_excess(chol[k], ref.cov_sqrtm[k], n) < 1, k
+    if kind == "white_linear" and bcond == "neumann":  # full-rank updates: QR signs are well determined
+        assert float(sol.diffusion_squared_calibrated) == pytest.approx(float(ref.diffusion_squared_calibrated), rel=1e-6)
+
+
+def test_generator_path_equals_persistent_path_and_reference_time_grid():
+    """dt = 0.1, tmax = 1 (the reference's own test config): 11 steps including the rounding sliver step;
+    NaN-free like tests/test_pdefilter.py:141-146, and the step-by-step route equals the one-launch route."""
+    case = cases.make_case("heat", num=6, dt=0.1)
+    solver = cases.make_solver("white_linear", case)
+    sol = solver.solve(case["pde"])
+    ref_t, ref_dts = ek1_np.constant_step_schedule(0.0, 1.0, 0.1)
+    assert np.array_equal(np.asarray(sol.t), ref_t) and sol.info["num_steps"] == 11
+    assert not torch.isnan(sol.mean).any() and not torch.isnan(sol.cov_sqrtm).any()
+    states = [s for s, _ in solver.solution_generator(case["pde"])]
+    assert len(states) == 12
+    for k, s in enumerate(states[:-1]):  # the sliver step itself is ill-conditioned
+        assert torch.equal(s.y.mean, sol.mean[k]) and torch.equal(s.y.cov_sqrtm, sol.cov_sqrtm[k])
+    ref = ek1_np.solve("white_linear", case["opde"], 0.1, 2, case["gram_sqrtm"])
+    for k in range(11):
+        assert cases.mean_excess(_np(sol.mean[k]), ref.mean[k]) < 1
+
+
+@pytest.mark.parametrize("kind,name,bcond", [("white_linear", "heat", "neumann"), ("latent_semilinear", "spruce", "dirichlet")])
+def test_simulate_final_state(kind, name, bcond):
+    case = cases.make_case(name, num=7, bcond=bcond, tmax=0.5)
+    state, info = cases.make_solver(kind, case).simulate_final_state(case["pde"])
+    ref, cal = ek1_np.simulate_final_state(kind, case["opde"], case["dt"], case["nu"], case["gram_sqrtm"])
+    assert state.t == ref.t and info["num_steps"] == 8
+    assert cases.mean_excess(_np(state.y.mean), ref.mean) < 1
+    # the rescaling factor is the QR-sign dependent quirk-Q1 quantity: compare the unscaled covariance
+    sol = cases.make_solver(kind, case).solve(case["pde"])
+    unscaled = cases.cov(_np(sol.cov_sqrtm[-1]))
+    got = cases.cov(_np(state.y.cov_sqrtm))
+    assert np.allclose(got, unscaled * float(sol.diffusion_squared_calibrated), rtol=1e-12, atol=1e-300)
+    if bcond == "neumann" and kind.startswith("white"):
+        assert cases.block_rel(got, cases.cov(ref.cov_sqrtm), 3) < 1e-6
+
+
+def test_dense_input_factor_and_adaptive_steps():
+    from pnmol_b200 import pdefilter, white
+    from pnmol_b200.base import rv
+    from pnmol_b200.odetools import step
+
+    case = cases.make_case("heat", num=7, bcond="neumann")
+    solver = cases.make_solver("white_linear", case)
+    st = ek1_np.white_initialize(case["opde"], 2, case["gram_sqrtm"])
+    Q, _ = np.linalg.qr(np.random.default_rng(3).standard_normal(st.cov_sqrtm.shape))
+    dense = st.cov_sqrtm @ Q
+    ref = ek1_np.white_step(case["opde"], st._replace(cov_sqrtm=dense), case["dt"], 2, case["gram_sqrtm"])
+    solver.initialize(case["pde"])
+    g = pdefilter.PDEFilterState(t=st.t, y=rv.MultivariateNormal(torch.tensor(st.mean).cuda(), torch.tensor(dense).cuda()),
+                                 error_estimate=None, reference_state=None, diffusion_squared_local=None)
+    new, _ = solver.attempt_step(g, case["dt"], case["pde"])
+    assert cases.mean_excess(_np(new.y.mean), ref.mean) < 1
+    assert cases.cov_excess(_np(new.y.cov_sqrtm), ref.cov_sqrtm, 3) < 1
+    # Adaptive rule drives the same attempt_step through accept/reject (host-side logic of step.py:58-119)
+    ada = white.LinearWhiteNoiseEK1(num_derivatives=2, steprule=step.Adaptive(abstol=1e-2, reltol=1e-2),
+                                    spatial_kernel=case["kernel"])
+    sol = ada.solve(case["pde"])
+    assert sol.t[-1] == pytest.approx(case["pde"].tmax) and sol.info["num_attempted_steps"] >= sol.info["num_steps"] >= 2
+    assert not torch.isnan(sol.mean).any()
+
+
+# ------------------------------------------------------------------------- ensembles
+def test_ensemble_members_match_individual_oracle_solves():
+    from oracle import setup_np
+    from pnmol_b200 import ensemble
+
+    case = cases.make_case("heat", num=9, tmax=0.5)
+    pde, o = case["pde"], case["opde"]
+    rng = np.random.default_rng(20261018)
+    B = 5
+    x = pde.mesh_spatial.points[:, 0]
+    y0 = np.stack([a * np.exp(-((x - c) ** 2)) * np.sin(np.pi * x) for a, c in zip(rng.uniform(0.05, 0.2, B), rng.uniform(0.3, 0.7, B))])
+    ds = np.exp(rng.uniform(np.log(0.5), np.log(2.0), B))
+    ps = np.exp(rng.uniform(np.log(0.1), np.log(10.0), B))
+    solver = cases.make_solver("white_linear", case)
+    es = ensemble.EnsembleSolver(solver, pde, y0=y0, diff_scale=ds, prior_scale=ps)
+    res = es.simulate_final_state(rescale=False)
+    host = es.simulate_final_state_host()
+    assert res.num_steps == 8 and int(res.status.max()) == 0
+    for b in range(B):
+        member = setup_np.with_member(o, diff_scale=ds[b], y0=y0[b])
+        ref = ek1_np.solve("white_linear", member, case["dt"], 2, ps[b] * case["gram_sqrtm"])
+        assert cases.mean_excess(_np(res.mean[b]), ref.mean[-1]) < 1
+        assert cases.cov_excess(_np(res.cov_sqrtm[b]), ref.cov_sqrtm[-1], 3) < 1
+    # host-buffer route = device route, plus the final rescaling of pdefilter.py:113-116
+    assert torch.equal(host.mean, res.mean.cpu())
+    scale = torch.sqrt(host.diffusion_squared_calibrated)[:, None, None]
+    assert torch.allclose(host.cov_sqrtm, res.cov_sqrtm.cpu() * scale, rtol=1e-13, atol=0)
+    assert torch.allclose(host.diffusion_squared_calibrated, res.diffusion_squared_calibrated.cpu(), rtol=1e-13)
+
+
+def test_ensemble_semilinear_sir_with_member_parameters():
+    from oracle import setup_np
+    from pnmol_b200 import ensemble
+
+    case = cases.make_case("sir", num=6, tmax=0.25)
+    rng = np.random.default_rng(7)
+    B = 3
+    params = np.stack([rng.uniform(0.2, 0.4, B), rng.uniform(0.05, 0.1, B)], axis=1)
+    ds = rng.uniform(0.5, 2.0, (B, 3))
+    solver = cases.make_solver("white_semilinear", case)
+    y0 = np.tile(case["pde"].y0, (B, 1))
+    res = ensemble.EnsembleSolver(solver, case["pde"], y0=y0, diff_scale=ds, reaction_params=params).simulate_final_state(rescale=False)
+    for b in range(B):
+        o = setup_np.sir_1d(num=6, tmax=0.25, beta=params[b, 0], gamma=params[b, 1], diffusion_rates=tuple(0.035 * ds[b]),
+                            n_bnd=5)
+        ref = ek1_np.solve("white_semilinear", o, case["dt"], 2, case["gram_sqrtm"])
+        assert cases.mean_excess(_np(res.mean[b]), ref.mean[-1]) < 1
+        assert cases.cov_excess(_np(res.cov_sqrtm[b]), ref.cov_sqrtm[-1], 3) < 1
+
+
+def test_ensemble_properties_at_full_size():
+    """Size-independent checks at a BASELINE-sized member (N = 50, D = 150): identical members give identical
+    results, and the linear filter mean is linear in the initial condition (same covariance recursion)."""
+    from pnmol_b200 import ensemble
+
+    case = cases.make_case("heat", num=50, tmax=0.25)
+    pde = case["pde"]
+    B = 24
+    y0 = np.tile(pde.y0, (B, 1))
+    y0[1] *= 2.0
+    y0[2] = 0.0
+    res = ensemble.EnsembleSolver(cases.make_solver("white_linear", case), pde, y0=y0).simulate_final_state(rescale=False)
+    assert int(res.status.max()) == 0
+    assert torch.equal(res.mean[0], res.mean[5]) and torch.equal(res.cov_sqrtm[0], res.cov_sqrtm[B - 1])
+    assert torch.allclose(res.mean[1], 2.0 * res.mean[0], rtol=1e-9, atol=1e-14)
+    assert float(res.mean[2].abs().max()) < 1e-12
+    P0, P1 = (cases.cov(_np(res.cov_sqrtm[i])) for i in (0, 1))
+    assert cases.block_rel(P1, P0, 3) < 1e-9
+    ref = ek1_np.solve("white_linear", case["opde"], case["dt"], 2, case["gram_sqrtm"])
+    assert cases.mean_excess(_np(res.mean[0]), ref.mean[-1]) < 1
+    assert cases.cov_excess(_np(res.cov_sqrtm[0]), ref.cov_sqrtm[-1], 3) < 1
+
+
+# ------------------------------------------------------------------------- golden fixtures
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_path_reproduces_golden(path):
+    g = np.load(path, allow_pickle=False)
+    prob, kind = str(g["problem"]), str(g["kind"])
+    num = g["L"].shape[0] // {"sir": 3, "lv": 2}.get(prob, 1)
+    case = cases.make_case(prob, num=num, bcond="neumann" if "neumann" in path else "dirichlet", tmax=0.5)
+    sol = cases.make_solver(kind, case).solve(case["pde"])
+    n = int(g["nu"]) + 1
+    assert np.array_equal(np.asarray(sol.t), g["t"])
+    for k in range(len(g["t"])):
+        assert cases.mean_excess(_np(sol.mean[k]), g["mean"][k]) < 1
+        assert cases.cov_excess(_np(sol.cov_sqrtm[k]), g["cov_sqrtm"][k], n) < 1
