@@ -115,7 +115,7 @@ def test_initialize_and_steps_from_oracle_state(name, kind, bcond, num):
         assert float(new.diffusion_squared_local) == pytest.approx(float(st.diffusion_squared_local), rel=1e-7)
         if kind.startswith("white"):
             assert np.allclose(_np(new.error_estimate), st.error_estimate, rtol=1e-7)
-            assert np.allclose(_np(new.reference_state), st.reference_state, rtol=1e-9, atol=1e-300)
+            assert np.allclose(_np(new.reference_state), st.reference_state, rtol=1e-9, atol=1e-15)
         else:
             assert new.error_estimate is None and new.reference_state is None
 
