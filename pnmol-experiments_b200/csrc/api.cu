@@ -67,13 +67,34 @@ void compute_structure(int latent, int semilinear, int d, int n, int nb, int nco
     }
 }
 
+// Largest compact row list of any kNB-wide panel (mirrors panel_rows in qr_blocked.cuh).
+int max_panel_len(int nt, int nbot, int ncols, const int32_t* te, const int32_t* be) {
+    const int nrows = nt + nbot, nref = std::min(nrows, ncols);
+    int best = 1;
+    for (int j0 = 0; j0 < nref; j0 += kNB) {
+        const int jl = std::min(j0 + kNB, nref) - 1;
+        auto top = [&](int j) { return std::min(te ? te[j] : nt - 1, nt - 1); };
+        auto bot = [&](int j) { return std::min(be ? be[j] : nrows - 1, nrows - 1); };
+        int len;
+        if (j0 < nt) {
+            const int jt = std::min(jl, nt - 1);
+            const int e1 = std::max(top(jt), jt), e2 = bot(jl);
+            len = e1 - j0 + 1 + (e2 >= nt ? e2 - nt + 1 : 0);
+        } else {
+            len = std::max(bot(jl), jl) - j0 + 1;
+        }
+        best = std::max(best, len);
+    }
+    return best;
+}
+
 }  // namespace
 
 struct pnmol_b200_handle {
     int kind, device, grid, num_sms;
     Problem P;
     std::vector<void*> allocs;
-    size_t smem_bytes;
+    size_t smem_bytes, smem_optin;
     bool have_op = false, have_prior = false;
     double* steparr = nullptr;  // device: dts | tnew | pv | pinv
     int steparr_cap = 0;
@@ -193,8 +214,7 @@ int pnmol_b200_create(pnmol_b200_handle** out, int kind, int d, int num_derivati
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
-    h->smem_bytes = smem_doubles(P.D, P.m, P.dd) * sizeof(double);
-    if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { delete h; return fail(-1, "state dimension too large for the single-CTA path"); }
+    h->smem_optin = prop.sharedMemPerBlockOptin;
     *out = h;
     return 0;
 }
@@ -244,6 +264,19 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
     if ((rc = dev_upload(h, &P.te_pd, te_pd.data(), te_pd.size()))) return rc;
     if ((rc = dev_upload(h, &P.te_u, te_u.data(), te_u.size()))) return rc;
     if ((rc = dev_upload(h, &P.be_u, be_u.data(), be_u.size()))) return rc;
+    // panel geometry of the blocked QR: V buffer rows = 16 G for the largest row list (<= 512, else fallback)
+    {
+        int maxlen = max_panel_len(P.D, P.D, P.D, te_p.data(), be_p.data());
+        maxlen = std::max(maxlen, max_panel_len(P.D, P.D, P.D, te_pd.data(), be_p.data()));
+        maxlen = std::max(maxlen, max_panel_len(P.D, P.latent ? 0 : P.m, P.m + P.D, te_u.data(), be_u.data()));
+        maxlen = std::max(maxlen, max_panel_len(P.D, P.d, P.d + P.D, nullptr, nullptr));   // initialisation updates
+        maxlen = std::max(maxlen, max_panel_len(P.D, P.m, P.m + P.D, nullptr, nullptr));
+        const int G = maxlen <= 64 ? 4 : maxlen <= 128 ? 8 : maxlen <= 256 ? 16 : 32;
+        P.vld = 16 * G;
+        P.ldm = P.m <= 96 ? (P.m | 1) : 0;  // odd leading dimension: conflict-free rows and columns
+        h->smem_bytes = smem_doubles(P.D, P.m, P.dd, P.vld, P.ldm) * sizeof(double);
+        if (h->smem_bytes > h->smem_optin) return fail(-1, "state dimension too large for the single-CTA path");
+    }
     // launch geometry + per-CTA scratch
     CU(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     CU(cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -356,6 +389,20 @@ int pnmol_b200_run(pnmol_b200_handle* h, double t0, const double* dts, const dou
     k_run<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
     ++g_launches;
     CU(cudaGetLastError());
+    return 0;
+}
+
+int pnmol_b200_profile(pnmol_b200_handle* h, int enable, uint64_t* cycles_out) {
+    if (!h) return fail(-1, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    if (cycles_out && h->P.prof) CU(cudaMemcpy(cycles_out, h->P.prof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (enable && !h->P.prof) {
+        int rc = dev_alloc(h, &h->P.prof, 16);
+        if (rc) return rc;
+    }
+    if (h->P.prof) CU(cudaMemset(h->P.prof, 0, 16 * sizeof(uint64_t)));
+    if (!enable) h->P.prof = nullptr;
     return 0;
 }
 

@@ -35,7 +35,7 @@ enum EMode {
 struct Problem {
     int latent, semilinear, reaction;
     int d, n, nb, ncomp, npts, dd, D, m;
-    int wl, wb, wh, ld, batch, nparams;
+    int wl, wb, wh, ld, batch, nparams, vld, ldm;  // ldm > 0: an m x ldm shared-memory scratch exists (small m)
     const int32_t* Lcol; const double* Lval; const double* Ediag;
     const int32_t* Bcol; const double* Bval; const double* Rsq;
     const double* A1d; const double* LQ1d; const double* Lk; const double* Kg;
@@ -43,6 +43,21 @@ struct Problem {
     const int32_t* te_p; const int32_t* be_p; const int32_t* te_u; const int32_t* be_u;     // triangular input factor
     const int32_t* te_pd;                                                                    // dense input factor
     double* W; int32_t* Hcol; double* Hval; double* F; double* S;
+    unsigned long long* prof;  // optional clock64 phase accumulators (diagnostics)
+};
+
+// Phase timer: thread 0 of every CTA adds the cycles since the previous mark to prof[idx].
+struct PhaseClock {
+    unsigned long long* prof;
+    long long last;
+    __device__ __forceinline__ void start(unsigned long long* p) { prof = p; if (prof && threadIdx.x == 0) last = clock64(); }
+    __device__ __forceinline__ void mark(int idx) {
+        if (prof && threadIdx.x == 0) {
+            const long long now = clock64();
+            atomicAdd(&prof[idx], (unsigned long long)(now - last));
+            last = now;
+        }
+    }
 };
 
 struct Shape {  // QR row structure: rows [0,nt) top, [nt, nt+nbot) bottom
@@ -52,7 +67,7 @@ struct Shape {  // QR row structure: rows [0,nt) top, [nt, nt+nbot) bottom
 };
 
 struct Smem {
-    double *vbuf, *mp, *z, *y, *xw, *xat, *red, *pv, *pinv;
+    double *vbuf, *mp, *z, *y, *xw, *xat, *red, *pv, *pinv, *Vs, *xraw, *sc, *msq;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -72,11 +87,11 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;
 }
 
-__host__ __device__ __forceinline__ size_t smem_doubles(int D, int m, int dd) {
-    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 2 * kWarps + 2 * kMaxN + 8;
+__host__ __device__ __forceinline__ size_t smem_doubles(int D, int m, int dd, int vld, int ldm) {
+    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 48 + 18 * (size_t)vld + (size_t)m * ldm + 8;
 }
 
-__device__ __forceinline__ Smem carve(double* base, int D, int m, int dd) {
+__device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vld, int ldm) {
     Smem s;
     s.vbuf = base;              base += 2 * D + 4;
     s.mp = base;                base += D;
@@ -84,9 +99,13 @@ __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd) {
     s.y = base;                 base += m;
     s.xw = base;                base += m;
     s.xat = base;               base += dd;
-    s.red = base;               base += 2 * kWarps;
+    s.red = base;               base += 16;
     s.pv = base;                base += kMaxN;
-    s.pinv = base;
+    s.pinv = base;              base += kMaxN;
+    s.sc = base;                base += 48;
+    s.xraw = base;              base += 2 * vld;
+    s.Vs = base;                base += 16 * vld;
+    s.msq = ldm > 0 ? base : nullptr;
     return s;
 }
 
@@ -94,11 +113,11 @@ __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd) {
 // Unblocked, structure-aware, on the global (L2-resident) workspace.  After return the
 // upper triangle holds R and every entry below the diagonal inside the support envelope
 // is exactly zero.
-__device__ void householder_qr(double* __restrict__ W, int ld, const Shape s, double* vbuf, double* red) {
+__device__ void householder_columns(double* __restrict__ W, int ld, const Shape& s, int jbeg, int jend, double* vbuf,
+                                    double* red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nrows = s.nt + s.nbot;
-    const int nref = nrows < s.ncols ? nrows : s.ncols;
-    for (int j = 0; j < nref; ++j) {
+    for (int j = jbeg; j < jend; ++j) {
         int a1 = j, e1, a2, e2;
         if (j < s.nt) {
             e1 = s.te ? s.te[j] : s.nt - 1;
@@ -130,7 +149,7 @@ __device__ void householder_qr(double* __restrict__ W, int ld, const Shape s, do
         double tau = 0.0, beta = alpha, scale = 0.0;
         if (ss != 0.0) {  // dlarfg: xnorm == 0 -> H = I
             const double nrm = sqrt(alpha * alpha + ss);
-            beta = alpha >= 0.0 ? -nrm : nrm;
+            beta = -copysign(nrm, alpha);  // Fortran SIGN semantics of dlarfg
             tau = (beta - alpha) / beta;
             scale = 1.0 / (alpha - beta);
         }
@@ -164,6 +183,17 @@ __device__ void householder_qr(double* __restrict__ W, int ld, const Shape s, do
         __syncthreads();
     }
 }
+
+__device__ void householder_qr(double* __restrict__ W, int ld, const Shape s, double* vbuf, double* red) {
+    const int nrows = s.nt + s.nbot;
+    householder_columns(W, ld, s, 0, nrows < s.ncols ? nrows : s.ncols, vbuf, red);
+}
+
+}  // namespace pnmol
+
+#include "qr_blocked.cuh"
+
+namespace pnmol {
 
 // ---------------------------------------------------------------- reaction terms
 // f and df of src/pnmol/pde/examples.py:151-165 (SIR), :228-235 (Lotka-Volterra),
@@ -293,7 +323,7 @@ __device__ void build_predict(const Problem& P, int b, const Smem& sm, const dou
         const int tend = te[i];
         for (int k = lane; k <= tend; k += 32) {
             double acc = 0.0;
-            for (int s = 0; s < n; ++s) acc = fma(coef[s], sm.pinv[s] * Cl[(size_t)(blk * n + s) * D + k], acc);
+            for (int s = 0; s < n; ++s) acc = fma(coef[s], sm.pinv[s] * __ldcs(Cl + (size_t)(blk * n + s) * D + k), acc);
             col[k] = acc;
         }
         // Ql^T column i = row i of Ql, entries 0..i
@@ -319,9 +349,27 @@ __device__ void build_predict(const Problem& P, int b, const Smem& sm, const dou
 // white.py:153-162 in closed form: with H = At E0 + p1 It E1 (At = order-0 entries of H,
 // It = [I_d; 0]) and Ql Ql^T = K (x) q,  H Q H^T = q00 At K At^T + q01 p1 (At K It^T + It K At^T)
 // + q11 p1^2 It K It^T.  sigma^2 = z^T S^-1 z / m through a Cholesky factorisation of S.
-__device__ void error_estimate(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode,
-                               double nugget, const int32_t* Hcol, const double* Hval, double* F, double* S,
-                               double* err_out) {
+// (E E^T)[r][rp] for the step's measurement noise E = blockdiag(E_sqrtm, R_sqrtm)   white.py:157,184
+__device__ __forceinline__ double meas_cov_entry(const Problem& P, int b, EMode emode, int r, int rp) {
+    double ee = 0.0;
+    if (emode == E_STEP_WHITE) {
+        if (r < P.d) {
+            if (rp == r) {
+                const int comp = r / P.npts;
+                const double ds = P.diffscale ? P.diffscale[(size_t)b * P.ncomp + comp] : 1.0;
+                const double e = ds * P.Ediag[r];
+                ee = e * e;
+            }
+        } else if (rp >= P.d) {
+            for (int k = 0; k < P.nb; ++k) ee = fma(P.Rsq[(size_t)(r - P.d) * P.nb + k], P.Rsq[(size_t)(rp - P.d) * P.nb + k], ee);
+        }
+    }
+    return ee;
+}
+
+__device__ void error_estimate_global(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode,
+                                      double nugget, const int32_t* Hcol, const double* Hval, double* F, double* S,
+                                      double* err_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = P.n, d = P.d, m = P.m;
     const double ps = P.priorscale ? P.priorscale[b] : 1.0;
@@ -358,19 +406,7 @@ __device__ void error_estimate(const Problem& P, int b, const Smem& sm, double p
             if (r < d) cross += F[(size_t)rp * d + r];
             val += q01 * p1s * cross;
             if (r < d && rp < d) val += q11 * p1s * p1s * ps2 * P.Kg[(size_t)r * d + rp];
-            // E E^T
-            double ee = 0.0;
-            if (emode == E_STEP_WHITE) {
-                if (r < d && rp == r) {
-                    const int comp = r / P.npts;
-                    const double ds = P.diffscale ? P.diffscale[(size_t)b * P.ncomp + comp] : 1.0;
-                    const double e = ds * P.Ediag[r];
-                    ee = e * e;
-                } else if (r >= d && rp >= d) {
-                    for (int k = 0; k < P.nb; ++k) ee = fma(P.Rsq[(size_t)(r - d) * P.nb + k], P.Rsq[(size_t)(rp - d) * P.nb + k], ee);
-                }
-            }
-            S[(size_t)r * m + rp] = val + ee;
+            S[(size_t)r * m + rp] = val + meas_cov_entry(P, b, emode, r, rp);
         }
     }
     __syncthreads();
@@ -406,6 +442,113 @@ __device__ void error_estimate(const Problem& P, int b, const Smem& sm, double p
     if (err_out)
         for (int i = tid; i < d; i += kThreads) err_out[i] = dt * (sqrt(sm.y[i]) * sigma);
     __syncthreads();
+}
+
+// Shared-memory variant for small m (P.ldm > 0): S is assembled entry by entry straight from the sparse rows of
+// At and the L2-resident Gram matrix (all loads independent), factorised and solved in sm.msq.
+__device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode,
+                                    const int32_t* Hcol, const double* Hval, double* err_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = P.n, d = P.d, m = P.m, ldm = P.ldm;
+    const double ps = P.priorscale ? P.priorscale[b] : 1.0;
+    const double ps2 = ps * ps;
+    double q00 = 0, q01 = 0, q11 = 0;
+    for (int s = 0; s < n; ++s) {
+        q00 = fma(P.LQ1d[s], P.LQ1d[s], q00);
+        q01 = fma(P.LQ1d[s], P.LQ1d[n + s], q01);
+        q11 = fma(P.LQ1d[n + s], P.LQ1d[n + s], q11);
+    }
+    double* S = sm.msq;
+    const int na_ode = P.wl + (P.semilinear ? P.ncomp : 0);  // order-0 entries come first in a row of H
+    const int ntri = m * (m + 1) / 2;
+    for (int idx = tid; idx < ntri; idx += kThreads) {
+        int r = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+        while (r * (r + 1) / 2 > idx) --r;
+        while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+        const int rp = idx - r * (r + 1) / 2;  // rp <= r
+        const int32_t* hr = Hcol + (size_t)r * P.wh;
+        const int32_t* hp = Hcol + (size_t)rp * P.wh;
+        const double* vr = Hval + (size_t)r * P.wh;
+        const double* vp = Hval + (size_t)rp * P.wh;
+        const int nar = r < d ? na_ode : P.wb, nap = rp < d ? na_ode : P.wb;
+        double acc = 0.0, cross = 0.0;
+        for (int u = 0; u < nar; ++u) {
+            const int cu = hr[u];
+            if (cu < 0) continue;
+            const double* krow = P.Kg + (size_t)(cu / n) * d;
+            double inner = 0.0;
+            for (int w = 0; w < nap; ++w) {
+                const int cw = hp[w];
+                if (cw >= 0) inner = fma(vp[w], krow[cw / n], inner);
+            }
+            acc = fma(vr[u], inner, acc);
+            if (rp < d) cross = fma(vr[u], krow[rp], cross);
+        }
+        if (r < d) {
+            for (int w = 0; w < nap; ++w) {
+                const int cw = hp[w];
+                if (cw >= 0) cross = fma(vp[w], P.Kg[(size_t)(cw / n) * d + r], cross);
+            }
+        }
+        double val = q00 * acc + q01 * p1s * cross;
+        if (r < d && rp < d) val = fma(q11 * p1s * p1s, P.Kg[(size_t)r * d + rp], val);
+        val = ps2 * val + meas_cov_entry(P, b, emode, r, rp);
+        S[r * ldm + rp] = val;
+        if (r == rp) sm.y[r] = val;  // diag(S) before factorisation
+    }
+    __syncthreads();
+    // right-looking Cholesky of the lower triangle, two barriers per column; the diagonal of L goes to sm.xw so
+    // that S[k][k] is never written while other threads may still read it
+    for (int k = 0; k < m; ++k) {
+        __syncthreads();
+        const double skk = S[k * ldm + k];
+        const double rinv = rsqrt(skk);
+        for (int r = k + 1 + tid; r < m; r += kThreads) S[r * ldm + k] *= rinv;
+        if (tid == 0) sm.xw[k] = skk * rinv;
+        __syncthreads();
+        const int rem = m - k - 1;
+        for (int idx = tid; idx < rem * rem; idx += kThreads) {
+            const int r = k + 1 + idx / rem, c = k + 1 + idx % rem;
+            if (c <= r) S[r * ldm + c] = fma(-S[r * ldm + k], S[c * ldm + k], S[r * ldm + c]);
+        }
+    }
+    __syncthreads();
+    // forward solve L u = z by warp 0 (column oriented: each lane owns rows lane, lane + 32, lane + 64)
+    if (warp == 0) {
+        double u[3], acc[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { const int r = lane + 32 * q; u[q] = r < m ? sm.z[r] : 0.0; acc[q] = 0.0; }
+        for (int k = 0; k < m; ++k) {
+            const int q = k >> 5;
+            double cand = q == 0 ? u[0] - acc[0] : q == 1 ? u[1] - acc[1] : u[2] - acc[2];
+            cand /= sm.xw[k];
+            const double uk = __shfl_sync(0xffffffffu, cand, k & 31);
+#pragma unroll
+            for (int qq = 0; qq < 3; ++qq) {
+                const int r = lane + 32 * qq;
+                if (r > k && r < m) acc[qq] = fma(S[r * ldm + k], uk, acc[qq]);
+                if (r == k) u[qq] = uk;
+            }
+        }
+        double part = 0.0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { const int r = lane + 32 * q; if (r < m) part = fma(u[q], u[q], part); }
+        part = warp_sum(part);
+        if (lane == 0) sm.red[15] = sqrt(part / m);
+    }
+    __syncthreads();
+    const double sigma = sm.red[15];
+    if (err_out)
+        for (int i = tid; i < d; i += kThreads) err_out[i] = dt * (sqrt(sm.y[i]) * sigma);
+    __syncthreads();
+}
+
+__device__ void error_estimate(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode, double nugget,
+                               const int32_t* Hcol, const double* Hval, double* F, double* S, double* err_out) {
+    if (P.ldm > 0 && P.m <= 96)
+        error_estimate_smem(P, b, sm, p1s, dt, emode, Hcol, Hval, err_out);
+    else
+        error_estimate_global(P, b, sm, p1s, dt, emode, nugget, Hcol, Hval, F, S, err_out);
 }
 
 // ---------------------------------------------------------------- update stage
@@ -444,7 +587,7 @@ struct UpdateOut {
 __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, EMode emode, double nugget,
                              const double* __restrict__ Rsrc, const int32_t* te, const int32_t* be,
                              const int32_t* Hcol, const double* Hval, double* W, const UpdateOut out,
-                             int* nonfinite) {
+                             int* nonfinite, PhaseClock& pc) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = P.D, ld = P.ld, n = P.n;
     const int nbot = emode == E_NONE ? 0 : mcur;
@@ -489,35 +632,87 @@ __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, 
     }
     __syncthreads();
 
+    pc.mark(4);
     Shape sh;
     sh.nt = D; sh.nbot = nbot; sh.ncols = ncols; sh.te = te; sh.be = be;
-    householder_qr(Wl, ld, sh, sm.vbuf, sm.red);
+    householder_qr_blocked(Wl, ld, sh, sm.Vs, P.vld, sm.xraw, sm.sc, sm.vbuf, sm.red, pc);
+    pc.mark(5);
 
     // R1 = Wl[0:m, 0:m] (upper, column-major).  y = R1^-T z (for the mean),  x = R1^-1 z (quirk Q1,
     // white.py:125 / latent.py:204).
-    for (int r = tid; r < mcur; r += kThreads) { sm.y[r] = sm.z[r]; sm.xw[r] = sm.z[r]; }
-    __syncthreads();
-    for (int k = 0; k < mcur; ++k) {  // forward: dot form over contiguous column k of R1
-        if (warp == 0) {
-            const double* ck = Wl + (size_t)k * ld;
-            double acc = 0.0;
-            for (int c = lane; c < k; c += 32) acc = fma(ck[c], sm.y[c], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) sm.y[k] = (sm.y[k] - acc) / ck[k];
+    double diff;
+    if (P.ldm > 0 && mcur <= 96) {
+        // stage R1 row-major in shared memory (odd leading dimension: conflict-free rows and columns), then
+        // warp 0 solves R1^T y = z and warp 1 solves R1 x = z concurrently, column oriented
+        const int ldm = P.ldm;
+        double* Rs = sm.msq;
+        for (int idx = tid; idx < mcur * mcur; idx += kThreads) {
+            const int k = idx / mcur, c = idx - k * mcur;  // column k, row c
+            if (c <= k) Rs[c * ldm + k] = Wl[(size_t)k * ld + c];
         }
         __syncthreads();
-    }
-    for (int k = mcur - 1; k >= 0; --k) {  // backward: axpy form over contiguous column k of R1
-        const double* ck = Wl + (size_t)k * ld;
-        const double xk = sm.xw[k] / ck[k];
+        if (warp == 0) {  // forward: y_k = (z_k - sum_{c<k} R1[c][k] y_c) / R1[k][k]
+            double zz[3], acc[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { const int j = lane + 32 * q; zz[q] = j < mcur ? sm.z[j] : 0.0; acc[q] = 0.0; }
+            for (int k = 0; k < mcur; ++k) {
+                const int q = k >> 5;
+                double cand = q == 0 ? zz[0] - acc[0] : q == 1 ? zz[1] - acc[1] : zz[2] - acc[2];
+                cand /= Rs[k * ldm + k];
+                const double yk = __shfl_sync(0xffffffffu, cand, k & 31);
+#pragma unroll
+                for (int qq = 0; qq < 3; ++qq) {
+                    const int j = lane + 32 * qq;
+                    if (j > k && j < mcur) acc[qq] = fma(Rs[k * ldm + j], yk, acc[qq]);
+                    if (j == k) sm.y[j] = yk;
+                }
+            }
+        } else if (warp == 1) {  // backward: x_k = (z_k - sum_{c>k} R1[k][c] x_c) / R1[k][k]
+            double zz[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { const int j = lane + 32 * q; zz[q] = j < mcur ? sm.z[j] : 0.0; }
+            double part = 0.0;
+            for (int k = mcur - 1; k >= 0; --k) {
+                const int q = k >> 5;
+                double cand = q == 0 ? zz[0] : q == 1 ? zz[1] : zz[2];
+                cand /= Rs[k * ldm + k];
+                const double xk = __shfl_sync(0xffffffffu, cand, k & 31);
+                if (lane == 0) part = fma(xk, xk, part);
+#pragma unroll
+                for (int qq = 0; qq < 3; ++qq) {
+                    const int c = lane + 32 * qq;
+                    if (c < k) zz[qq] = fma(-Rs[c * ldm + k], xk, zz[qq]);
+                }
+            }
+            if (lane == 0) sm.red[14] = part / mcur;
+        }
         __syncthreads();
-        for (int c = tid; c < k; c += kThreads) sm.xw[c] = fma(-xk, ck[c], sm.xw[c]);
-        if (tid == 0) sm.xw[k] = xk;
+        diff = sm.red[14];
+    } else {
+        for (int r = tid; r < mcur; r += kThreads) { sm.y[r] = sm.z[r]; sm.xw[r] = sm.z[r]; }
         __syncthreads();
+        for (int k = 0; k < mcur; ++k) {  // forward: dot form over contiguous column k of R1
+            if (warp == 0) {
+                const double* ck = Wl + (size_t)k * ld;
+                double acc = 0.0;
+                for (int c = lane; c < k; c += 32) acc = fma(ck[c], sm.y[c], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) sm.y[k] = (sm.y[k] - acc) / ck[k];
+            }
+            __syncthreads();
+        }
+        for (int k = mcur - 1; k >= 0; --k) {  // backward: axpy form over contiguous column k of R1
+            const double* ck = Wl + (size_t)k * ld;
+            const double xk = sm.xw[k] / ck[k];
+            __syncthreads();
+            for (int c = tid; c < k; c += kThreads) sm.xw[c] = fma(-xk, ck[c], sm.xw[c]);
+            if (tid == 0) sm.xw[k] = xk;
+            __syncthreads();
+        }
+        double part = 0.0;
+        for (int r = tid; r < mcur; r += kThreads) part = fma(sm.xw[r], sm.xw[r], part);
+        diff = block_sum(part, sm.red) / mcur;
     }
-    double part = 0.0;
-    for (int r = tid; r < mcur; r += kThreads) part = fma(sm.xw[r], sm.xw[r], part);
-    const double diff = block_sum(part, sm.red) / mcur;
     if (out.diff_out && tid == 0) *out.diff_out = diff;
 
     // m_new = mp - R2^T y   (white.py:123, sqrt.py:72)
@@ -529,6 +724,7 @@ __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, 
         if (lane == 0) sm.mp[k] -= acc;
     }
     __syncthreads();
+    pc.mark(6);
     int bad = 0;
     if (!(diff == diff) || isinf(diff)) bad = 1;
     // outputs: mean (n, dd) = P m_new reshaped (white.py:132-135); factor = P R3^T (white.py:132)
@@ -547,12 +743,13 @@ __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, 
         for (int c = lane; c < D; c += 32) {
             double v = 0.0;
             if (c <= r && mcur + c < nrows) v = pr * col[c];
-            orow[c] = v;
+            __stcs(orow + c, v);  // streaming: keep the workspaces, not the state, resident in L2
             if (!isfinite(v)) bad = 1;
         }
     }
     if (bad) atomicOr(nonfinite, 1);
     __syncthreads();
+    pc.mark(7);
 }
 
 }  // namespace pnmol

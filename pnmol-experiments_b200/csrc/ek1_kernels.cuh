@@ -25,6 +25,8 @@ __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, doub
                          const double* mean_in, const double* chol_in, double* mean_out, double* chol_out,
                          double* err_out, double* ref_out, double* diff_out, int flags, int* nonfinite) {
     const int tid = threadIdx.x;
+    PhaseClock pc;
+    pc.start(P.prof);
     const int n = P.n, D = P.D;
     double* W = P.W + (size_t)slot * P.ld * (P.m + P.D);
     int32_t* Hcol = P.Hcol + (size_t)slot * P.m * P.wh;
@@ -38,25 +40,29 @@ __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, doub
     }
     __syncthreads();
     evaluate_ode(P, b, sm, sm.pv[0], sm.pv[1], Hcol, Hval);
+    pc.mark(0);
     const bool dense = flags & 1;
     build_predict(P, b, sm, chol_in, dense ? P.te_pd : P.te_p, W + (size_t)P.m * P.ld);
+    pc.mark(1);
     Shape sp;
     sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p;
-    householder_qr(W + (size_t)P.m * P.ld, P.ld, sp, sm.vbuf, sm.red);
+    householder_qr_blocked(W + (size_t)P.m * P.ld, P.ld, sp, sm.Vs, P.vld, sm.xraw, sm.sc, sm.vbuf, sm.red, pc);
+    pc.mark(2);
     if (!P.latent && !(flags & 2)) {
         error_estimate(P, b, sm, sm.pv[1], dt, E_STEP_WHITE, 0.0, Hcol, Hval, P.F + (size_t)slot * P.m * P.d,
                        P.S + (size_t)slot * P.m * P.m, err_out);
     }
+    pc.mark(3);
     UpdateOut out;
     out.mean_out = mean_out; out.chol_out = chol_out; out.diff_out = diff_out;
     out.ref_out = P.latent ? nullptr : ref_out; out.scale_by_p = true;
     update_stage(P, b, sm, P.m, P.latent ? E_NONE : E_STEP_WHITE, 0.0, nullptr, P.te_u, P.be_u, Hcol, Hval, W, out,
-                 nonfinite);
+                 nonfinite, pc);
 }
 
-__global__ void __launch_bounds__(kThreads) k_run(const Problem P, const RunArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_run(const Problem P, const RunArgs a) {
     extern __shared__ double smem_raw[];
-    const Smem sm = carve(smem_raw, P.D, P.m, P.dd);
+    const Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm);
     __shared__ int nonfinite;
     __shared__ double diff_s;
     const int tid = threadIdx.x;
@@ -113,9 +119,9 @@ __global__ void __launch_bounds__(kThreads) k_run(const Problem P, const RunArgs
 }
 
 // initialize(): two square-root updates on a Kronecker-structured prior factor.
-__global__ void __launch_bounds__(kThreads) k_init(const Problem P, const InitArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_init(const Problem P, const InitArgs a) {
     extern __shared__ double smem_raw[];
-    const Smem sm = carve(smem_raw, P.D, P.m, P.dd);
+    const Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm);
     __shared__ int nonfinite;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = P.n, d = P.d, D = P.D, nd = P.n * P.d;
@@ -156,13 +162,15 @@ __global__ void __launch_bounds__(kThreads) k_init(const Problem P, const InitAr
         __syncthreads();
         UpdateOut o1;
         o1.mean_out = nullptr; o1.chol_out = chol; o1.diff_out = nullptr; o1.ref_out = nullptr; o1.scale_by_p = false;
-        update_stage(P, b, sm, d, E_NUGGET_ONLY, a.nugget, chol, nullptr, nullptr, Hcol, Hval, W, o1, &nonfinite);
+        PhaseClock pc;
+        pc.start(nullptr);
+        update_stage(P, b, sm, d, E_NUGGET_ONLY, a.nugget, chol, nullptr, nullptr, Hcol, Hval, W, o1, &nonfinite, pc);
         // linearise the PDE at t0 without preconditioning (white.py:42-48, latent.py:86-95)
         evaluate_ode(P, b, sm, 1.0, 1.0, Hcol, Hval);
         UpdateOut o2;
         o2.mean_out = mean; o2.chol_out = chol; o2.diff_out = nullptr; o2.ref_out = nullptr; o2.scale_by_p = false;
         update_stage(P, b, sm, P.m, P.latent ? E_NUGGET_ONLY : E_STEP_PLUS_NUGGET, a.nugget, chol, nullptr, nullptr, Hcol,
-                     Hval, W, o2, &nonfinite);
+                     Hval, W, o2, &nonfinite, pc);
         if (tid == 0 && a.status) a.status[b] = nonfinite;
         __syncthreads();
     }
@@ -195,7 +203,7 @@ __global__ void __launch_bounds__(kThreads) k_sqrt_propagate(const double* S1, c
                                                             int c1, int c2, int batch, double* Wall) {
     extern __shared__ double smem_raw[];
     double* vbuf = smem_raw;
-    double* red = smem_raw + (c1 + c2) + 4;
+    double* red = smem_raw + (c1 + c2) + 4;  // 16 doubles
     const int tid = threadIdx.x;
     const int rows = c1 + c2, ld = rows;
     const int k = rows < r ? rows : r;

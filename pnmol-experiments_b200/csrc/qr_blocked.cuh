@@ -1,0 +1,329 @@
+// Blocked, register-resident Householder QR for one CTA (sm_100a).
+//
+// Same mathematics and LAPACK dlarfg conventions as householder_columns (ek1_device.cuh); what
+// changes is where the data lives.  Columns are processed in panels of kNB.  For a panel the
+// union of the reflector supports is a short list of rows (<= 16 G, G in {4, 8, 16, 32}); a
+// column restricted to those rows is held in the registers of a G-lane group (lane s keeps
+// rows s, s + G, ...: up to kRPL = 16 values), two columns per group, 32/G groups per warp.
+// Dot products are reduced inside a group with log2(G) shuffle stages that serve all columns
+// of the warp at once; the panel's reflectors live in shared memory (Vs) and are applied to
+// every trailing column while that column sits in registers, so the trailing matrix is read
+// from and written to the L2-resident workspace exactly once per panel.
+//
+// Panel factorisation uses one reduction round per column: the owner publishes its raw
+// column x_i, every group reduces (x_i . x_k over rows > i, x_k[i]) for its own columns k --
+// for k = i that is the norm -- the owner derives (beta, tau, scale) from it, and all groups
+// then apply  x_k -= tau (x_k[i] + scale x_i.x_k) v  with v = scale x_i below the diagonal.
+#pragma once
+// included from ek1_device.cuh (after householder_columns)
+
+namespace pnmol {
+
+constexpr int kNB = 16;   // panel width
+constexpr int kRPL = 16;  // rows per lane (upper bound; chunks of 4 beyond the row list are skipped)
+
+struct RowMap {  // compact row list of a panel: c < len1 -> j0 + c, else a2 + (c - len1)
+    int j0, len1, a2, len;
+    __device__ __forceinline__ int row(int c) const { return c + (c < len1 ? j0 : a2 - len1); }
+};
+
+__device__ __forceinline__ int env_top(const Shape& s, int j) {
+    int e = s.te ? s.te[j] : s.nt - 1;
+    return e > s.nt - 1 ? s.nt - 1 : e;
+}
+__device__ __forceinline__ int env_bot(const Shape& s, int j) {
+    const int last = s.nt + s.nbot - 1;
+    int e = s.be ? s.be[j] : last;
+    return e > last ? last : e;
+}
+
+__device__ __forceinline__ RowMap panel_rows(const Shape& s, int j0, int jl) {
+    RowMap rm;
+    rm.j0 = j0;
+    if (j0 < s.nt) {
+        const int jt = jl < s.nt ? jl : s.nt - 1;
+        int e1 = env_top(s, jt);
+        if (e1 < jt) e1 = jt;
+        rm.len1 = e1 - j0 + 1;
+        rm.a2 = s.nt;
+        const int e2 = env_bot(s, jl);
+        rm.len = rm.len1 + (e2 >= s.nt ? e2 - s.nt + 1 : 0);
+    } else {
+        rm.len1 = 0;
+        rm.a2 = j0;
+        int e2 = env_bot(s, jl);
+        if (e2 < jl) e2 = jl;
+        rm.len = e2 - j0 + 1;
+    }
+    return rm;
+}
+
+// Interleaved butterfly reductions inside a G-lane group.
+template <int G>
+__device__ __forceinline__ void group_sum2(double& a, double& b) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const double ta = __shfl_xor_sync(0xffffffffu, a, o);
+        const double tb = __shfl_xor_sync(0xffffffffu, b, o);
+        a += ta;
+        b += tb;
+    }
+}
+template <int G>
+__device__ __forceinline__ void group_sum3(double& a, double& b, double& c) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const double ta = __shfl_xor_sync(0xffffffffu, a, o);
+        const double tb = __shfl_xor_sync(0xffffffffu, b, o);
+        const double tc = __shfl_xor_sync(0xffffffffu, c, o);
+        a += ta; b += tb; c += tc;
+    }
+}
+template <int G>
+__device__ __forceinline__ void group_sum4(double& a, double& b, double& c, double& d) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const double ta = __shfl_xor_sync(0xffffffffu, a, o);
+        const double tb = __shfl_xor_sync(0xffffffffu, b, o);
+        const double tc = __shfl_xor_sync(0xffffffffu, c, o);
+        const double td = __shfl_xor_sync(0xffffffffu, d, o);
+        a += ta; b += tb; c += tc; d += td;
+    }
+}
+
+// Apply one reflector to the two register-resident columns of a lane group.
+template <int G>
+__device__ __forceinline__ void apply_reflector(const double (&v)[kRPL], double (&x0)[kRPL], double (&x1)[kRPL], int nq,
+                                                double tau) {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (q < nq) {
+#pragma unroll
+            for (int rr = 0; rr < 4; rr += 2) {
+                const int r = 4 * q + rr;
+                a0 = fma(v[r], x0[r], a0);
+                a1 = fma(v[r], x1[r], a1);
+                b0 = fma(v[r + 1], x0[r + 1], b0);
+                b1 = fma(v[r + 1], x1[r + 1], b1);
+            }
+        }
+    }
+    double d0 = a0 + b0, d1 = a1 + b1;
+    group_sum2<G>(d0, d1);
+    const double w0 = -tau * d0, w1 = -tau * d1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (q < nq) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int r = 4 * q + rr;
+                x0[r] = fma(w0, v[r], x0[r]);
+                x1[r] = fma(w1, v[r], x1[r]);
+            }
+        }
+    }
+}
+
+// One panel: factor columns j0 .. j0+nbk-1 and apply their reflectors to all later columns.
+// Shared memory: Vs[kNB][vld] reflectors, xraw[2][vld] raw column of the current reflector (double
+// buffered), sc[3 * i] = tau of reflector i.
+template <int G>
+__device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const Shape& s, int j0, int nbk, const RowMap rm,
+                                           double* __restrict__ Vs, int vld, double* __restrict__ xraw,
+                                           double* __restrict__ sc, PhaseClock& pc) {
+    constexpr int CPW = (32 / G) * 2;  // trailing columns per warp (two per lane group)
+    constexpr int PPW = 32 / G;        // panel columns per warp (one per lane group)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / G, sl = lane % G;
+    const int nt = s.nt;
+    const int nq = (rm.len + 4 * G - 1) / (4 * G);  // row chunks (of 4 per lane) that hold data
+    double x0[kRPL], x1[kRPL];
+
+    // ---- load this group's panel column (entries outside the column's own envelope are zero)
+    const int p0 = warp * PPW + g;
+    const bool hp = p0 < nbk;
+    const int jp = j0 + (hp ? p0 : 0);
+    const int etp = hp ? env_top(s, jp) : -1, ebp = hp ? env_bot(s, jp) : -1;
+    {
+        const double* c0 = W + (size_t)jp * ld;
+#pragma unroll
+        for (int r = 0; r < kRPL; ++r) {
+            const int c = sl + G * r;
+            const int row = rm.row(c);
+            const bool ok = c < rm.len && (row < nt ? row <= etp : row <= ebp);
+            x0[r] = ok ? c0[row] : 0.0;
+        }
+    }
+    pc.mark(8);
+
+    // ---- factor the panel: one barrier and one reduction round per column.  The owner publishes its column with
+    // the rows c <= i zeroed (so nobody else needs per-element masks) and the diagonal entry alpha; every group
+    // that still holds a live column reduces x_i . x_k and derives the reflector scalars (dlarfg) redundantly.
+    const int wfirst = warp * PPW, wlast = warp * PPW + PPW - 1;  // panel columns of this warp
+    for (int i = 0; i < nbk; ++i) {
+        const bool own = p0 == i;
+        const int ri = i / G, si = i % G;  // register slot and lane that hold row i  (ri < 16 / G <= 4)
+        double* xr = xraw + (i & 1) * vld;  // double buffered: the next owner may publish while others still read
+        if (own) {
+#pragma unroll
+            for (int r = 0; r < kRPL; ++r) {
+                const bool gt = r > ri || (r == ri && sl > si);
+                xr[sl + G * r] = gt ? x0[r] : 0.0;
+                if (r == ri && sl == si) sc[3 * i + 1] = x0[r];
+            }
+        }
+        __syncthreads();
+        if (wfirst >= nbk || wlast < i) continue;  // no live panel column in this warp: only keep the barrier
+        const double al = sc[3 * i + 1];
+        double d0 = 0.0, ss = 0.0, d0b = 0.0, ssb = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q < nq) {
+#pragma unroll
+                for (int rr = 0; rr < 4; rr += 2) {
+                    const int r = 4 * q + rr;
+                    const double t = xr[sl + G * r], u = xr[sl + G * (r + 1)];
+                    d0 = fma(t, x0[r], d0);
+                    ss = fma(t, t, ss);
+                    d0b = fma(u, x0[r + 1], d0b);
+                    ssb = fma(u, u, ssb);
+                }
+            }
+        }
+        d0 += d0b; ss += ssb;
+        // entry of this group's column at row i: slot ri of lane si
+        double e0 = x0[0];
+        if (G < 16 && ri == 1) e0 = x0[1];
+        if (G < 8 && ri == 2) e0 = x0[2];
+        if (G < 8 && ri == 3) e0 = x0[3];
+        e0 = __shfl_sync(0xffffffffu, e0, (lane & ~(G - 1)) | si);
+        group_sum2<G>(d0, ss);
+        // dlarfg on (alpha, ||x||^2): beta = -sign(alpha) ||(alpha, x)||, tau = (beta - alpha) / beta, v = x / (alpha - beta)
+        double tau = 0.0, beta = al, scale = 0.0;
+        if (ss != 0.0) {  // zero sub-column -> H = I
+            const double s2 = fma(al, al, ss);
+            const double rn = rsqrt(s2);
+            const double nrm = s2 * rn;
+            beta = -copysign(nrm, al);  // Fortran SIGN semantics of dlarfg (IEEE copysign, -0.0 counts as negative)
+            tau = (beta - al) * -copysign(rn, al);
+            scale = __drcp_rn(al - beta);
+        }
+        if (own && sl == 0) sc[3 * i] = tau;
+        if (tau != 0.0) {
+            const double f0 = p0 > i && hp ? -tau * fma(scale, d0, e0) : 0.0;
+            const double g0 = f0 * scale;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (q < nq) {
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int r = 4 * q + rr;
+                        x0[r] = fma(g0, xr[sl + G * r], x0[r]);
+                    }
+                }
+            }
+            if (sl == si) {  // v = 1 at row i
+                x0[0] += ri == 0 ? f0 : 0.0;
+                if (G < 16) x0[1] += ri == 1 ? f0 : 0.0;
+                if (G < 8) { x0[2] += ri == 2 ? f0 : 0.0; x0[3] += ri == 3 ? f0 : 0.0; }
+            }
+            if (own) {  // reflector into Vs; the column itself becomes (R entries, beta, zeros)
+#pragma unroll
+                for (int r = 0; r < kRPL; ++r) {
+                    const bool eq = r == ri && sl == si;
+                    const bool ge = r > ri || (r == ri && sl >= si);
+                    Vs[i * vld + sl + G * r] = eq ? 1.0 : scale * xr[sl + G * r];
+                    if (ge) x0[r] = eq ? beta : 0.0;
+                }
+            }
+        }
+    }
+    pc.mark(9);
+
+    // ---- write the factored panel column back
+    if (hp) {
+        double* c0 = W + (size_t)jp * ld;
+#pragma unroll
+        for (int r = 0; r < kRPL; ++r) {
+            const int c = sl + G * r;
+            const int row = rm.row(c);
+            if (c < rm.len && (row < nt ? row <= etp : row <= ebp)) c0[row] = x0[r];
+        }
+    }
+    __syncthreads();  // all of Vs / sc written
+    pc.mark(10);
+
+    // ---- trailing columns: load once, apply the nbk reflectors from registers, store once
+    const double* vbase = Vs + sl;
+    for (int kb = j0 + nbk + warp * CPW; kb < s.ncols; kb += kWarps * CPW) {
+        const int k0 = kb + g * 2, k1 = k0 + 1;
+        const bool h0 = k0 < s.ncols, h1 = k1 < s.ncols;
+        double* c0 = W + (size_t)(h0 ? k0 : kb) * ld;
+        double* c1 = W + (size_t)(h1 ? k1 : kb) * ld;
+#pragma unroll
+        for (int r = 0; r < kRPL; ++r) {
+            const int c = sl + G * r;
+            const int row = rm.row(c);
+            const bool in = c < rm.len;
+            x0[r] = (in && h0) ? c0[row] : 0.0;
+            x1[r] = (in && h1) ? c1[row] : 0.0;
+        }
+        for (int i = 0; i < nbk; ++i) {
+            const double tau = sc[3 * i];
+            if (tau == 0.0) continue;
+            double v[kRPL];
+            const double* vp = vbase + i * vld;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) v[4 * q + rr] = q < nq ? vp[G * (4 * q + rr)] : 0.0;
+            }
+            apply_reflector<G>(v, x0, x1, nq, tau);
+        }
+#pragma unroll
+        for (int r = 0; r < kRPL; ++r) {
+            const int c = sl + G * r;
+            const int row = rm.row(c);
+            const bool in = c < rm.len;
+            if (in && h0) c0[row] = x0[r];
+            if (in && h1) c1[row] = x1[r];
+        }
+    }
+    pc.mark(11);
+    __syncthreads();  // Vs / sc are rewritten by the next panel; workspace writes are visible
+    pc.mark(12);
+}
+
+// Blocked QR driver.  Panels whose row list exceeds 512 rows (or the smem V buffer) fall
+// back to the unblocked column-by-column routine.
+__device__ void householder_qr_blocked(double* __restrict__ W, int ld, const Shape s, double* Vs, int vld, double* xraw,
+                                       double* sc, double* vbuf, double* red, PhaseClock& pc) {
+    const int nrows = s.nt + s.nbot;
+    const int nref = nrows < s.ncols ? nrows : s.ncols;
+    int j0 = 0;
+    while (j0 < nref) {
+        int nbk = nref - j0 < kNB ? nref - j0 : kNB;
+        RowMap rm = panel_rows(s, j0, j0 + nbk - 1);
+        const int G = rm.len <= 4 * kRPL ? 4 : rm.len <= 8 * kRPL ? 8 : rm.len <= 16 * kRPL ? 16 : 32;
+        const int cap = kWarps * (32 / G);  // panel columns the CTA can hold in registers (one per lane group)
+        if (nbk > cap) {
+            nbk = cap;
+            rm = panel_rows(s, j0, j0 + nbk - 1);
+        }
+        if (rm.len > 32 * kRPL || 16 * G > vld) {
+            householder_columns(W, ld, s, j0, j0 + nbk, vbuf, red);
+        } else if (G == 4) {
+            qr_panel_step<4>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, pc);
+        } else if (G == 8) {
+            qr_panel_step<8>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, pc);
+        } else if (G == 16) {
+            qr_panel_step<16>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, pc);
+        } else {
+            qr_panel_step<32>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, pc);
+        }
+        j0 += nbk;
+    }
+}
+
+}  // namespace pnmol

@@ -91,14 +91,49 @@ def cov_excess(La, Lb, n, rtol=None):
     return float(np.max(np.abs(Pa - Pb) / np.maximum(tol + floor, 1e-300)))
 
 
-def mean_excess(a, b, rtol=None):
+import contextlib
+
+
+@contextlib.contextmanager
+def perturbed_oracle(seed=0):
+    """Run the oracle with eps * max|A| * N(0,1) added to every QR input A (the normwise backward error of any
+    Householder QR, LAPACK's included): the spread between this and the exact oracle measures how reproducible
+    the reference's own result is (its conditioning floor)."""
+    from oracle import sqrt_np
+
+    orig = sqrt_np.triu_factor
+    rng = np.random.default_rng(seed)
+
+    def noisy(stack):
+        stack = np.asarray(stack, dtype=np.float64)
+        return orig(stack + np.finfo(np.float64).eps * np.max(np.abs(stack)) * rng.standard_normal(stack.shape))
+
+    sqrt_np.triu_factor = noisy
+    try:
+        yield
+    finally:
+        sqrt_np.triu_factor = orig
+
+
+def oracle_pair(fn):
+    """(exact oracle result, result under eps-level normwise perturbations of every QR input)."""
+    ref = fn()
+    with perturbed_oracle():
+        ref_eps = fn()
+    return ref, ref_eps
+
+
+def mean_excess(a, b, rtol=None, spread=None):
     """Mean parity: max over derivative rows of |dm| / (rtol * max|row| + 10 D eps max|m|) (holds iff < 1).  The
     second term only matters for rows that are pure rounding noise (e.g. the second-derivative row of the initial
     mean, ~1e-18 next to O(0.1) rows)."""
     rtol = MEAN_RTOL if rtol is None else rtol
     a, b = np.asarray(a), np.asarray(b)
     floor = 10.0 * b.size * np.finfo(np.float64).eps * np.max(np.abs(b))
-    return float(max(np.max(np.abs(a[i] - b[i])) / max(rtol * np.max(np.abs(b[i])) + floor, 1e-300) for i in range(b.shape[0])))
+    # spread: a second oracle result from eps-perturbed inputs; 10 x its distance is the reproducibility floor
+    extra = [0.0] * b.shape[0] if spread is None else [10.0 * np.max(np.abs(np.asarray(spread)[i] - b[i])) for i in range(b.shape[0])]
+    return float(max(np.max(np.abs(a[i] - b[i])) / max(rtol * np.max(np.abs(b[i])) + floor + extra[i], 1e-300)
+                     for i in range(b.shape[0])))
 
 
 MEAN_RTOL = 1e-9  # BASELINE.json north_star: filter means to rtol 1e-9

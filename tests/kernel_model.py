@@ -47,7 +47,7 @@ def householder_qr(W, nt, nbot, ncols, te, be):
         if ss == 0.0 or np.isnan(ss) and False:
             continue
         nrm = np.sqrt(alpha * alpha + ss)
-        beta = -nrm if alpha >= 0 else nrm
+        beta = -np.copysign(nrm, alpha)
         tau = (beta - alpha) / beta
         v = v / (alpha - beta)
         v[0] = 1.0
@@ -57,6 +57,79 @@ def householder_qr(W, nt, nbot, ncols, te, be):
             blk = W[np.ix_(rows, np.arange(j + 1, ncols))]
             w = tau * (v @ blk)
             W[np.ix_(rows, np.arange(j + 1, ncols))] = blk - np.outer(v, w)
+    return W
+
+
+NB, RPL, WARPS = 16, 16, 8
+
+
+def _env(te, be, nt, nbot, j):
+    nrows = nt + nbot
+    et = min(te[j] if te is not None else nt - 1, nt - 1)
+    eb = min(be[j] if be is not None else nrows - 1, nrows - 1)
+    return et, eb
+
+
+def panel_rows(nt, nbot, te, be, j0, jl):
+    """Mirror of panel_rows in csrc/qr_blocked.cuh: compact row list of a panel."""
+    if j0 < nt:
+        jt = min(jl, nt - 1)
+        e1 = max(_env(te, be, nt, nbot, jt)[0], jt)
+        e2 = _env(te, be, nt, nbot, jl)[1]
+        rows = list(range(j0, e1 + 1)) + list(range(nt, e2 + 1))
+    else:
+        e2 = max(_env(te, be, nt, nbot, jl)[1], jl)
+        rows = list(range(j0, e2 + 1))
+    return np.asarray(rows)
+
+
+def householder_qr_blocked(W, nt, nbot, ncols, te, be, vld=512):
+    """Mirror of householder_qr_blocked / qr_panel_step (csrc/qr_blocked.cuh): panels of NB columns, panel
+    columns loaded with their own-envelope mask, trailing columns loaded unmasked on the panel's row list."""
+    nrows = nt + nbot
+    nref = min(nrows, ncols)
+    j0 = 0
+    while j0 < nref:
+        nbk = min(NB, nref - j0)
+        rows = panel_rows(nt, nbot, te, be, j0, j0 + nbk - 1)
+        G = 4 if len(rows) <= 4 * RPL else 8 if len(rows) <= 8 * RPL else 16 if len(rows) <= 16 * RPL else 32
+        cap = WARPS * (32 // G)
+        if nbk > cap:
+            nbk = cap
+            rows = panel_rows(nt, nbot, te, be, j0, j0 + nbk - 1)
+        assert len(rows) <= 32 * RPL and len(rows) <= vld, "fallback path not modelled"
+        X = np.zeros((len(rows), nbk))
+        masks = []
+        for p in range(nbk):
+            et, eb = _env(te, be, nt, nbot, j0 + p)
+            mask = np.where(rows < nt, rows <= et, rows <= eb)
+            masks.append(mask)
+            X[mask, p] = W[rows[mask], j0 + p]
+        V = np.zeros((len(rows), nbk))
+        taus = np.zeros(nbk)
+        for i in range(nbk):
+            ss = float(np.sum(X[i + 1:, i] ** 2))
+            al = X[i, i]
+            if ss != 0.0:
+                nrm = np.sqrt(al * al + ss)
+                beta = -np.copysign(nrm, al)
+                taus[i] = (beta - al) / beta
+                V[i + 1:, i] = X[i + 1:, i] / (al - beta)
+                V[i, i] = 1.0
+                X[i:, i] = 0.0
+                X[i, i] = beta
+                w = taus[i] * (V[:, i] @ X[:, i + 1:])
+                X[:, i + 1:] -= np.outer(V[:, i], w)
+        for p in range(nbk):
+            W[rows[masks[p]], j0 + p] = X[masks[p], p]
+        if j0 + nbk < ncols:
+            cols = np.arange(j0 + nbk, ncols)
+            C = W[np.ix_(rows, cols)]
+            for i in range(nbk):
+                if taus[i] != 0.0:
+                    C -= np.outer(V[:, i], taus[i] * (V[:, i] @ C))
+            W[np.ix_(rows, cols)] = C
+        j0 += nbk
     return W
 
 
@@ -81,7 +154,8 @@ def reaction_point(rid, prm, x):
 
 
 class Model:
-    def __init__(self, pde, family, nu, gram_sqrtm, diff_scale=None, prior_scale=1.0, rparams=None):
+    def __init__(self, pde, family, nu, gram_sqrtm, diff_scale=None, prior_scale=1.0, rparams=None, blocked=True):
+        self.blocked = blocked
         self.latent = family == "latent"
         self.semil = bool(getattr(pde, "is_semilinear", False))
         self.kind = _engine.KINDS[(family, self.semil)]
@@ -236,7 +310,7 @@ class Model:
             for i in range(D, bend + 1):
                 W[i, off + r] = self.meas_entry(emode, nugget, r, i - D)
         sub = W[:, off:]
-        householder_qr(sub, D, nbot, mcur + D, te, be)
+        (householder_qr_blocked if self.blocked else householder_qr)(sub, D, nbot, mcur + D, te, be)
         R1 = np.triu(sub[:mcur, :mcur])
         y = np.linalg.solve(R1.T, z[:mcur])
         x = np.linalg.solve(R1, z[:mcur])
@@ -294,7 +368,7 @@ class Model:
         z, Hc, Hv = self.evaluate_ode(mp, pv[0], pv[1])
         te = self.te_pd if dense else self.te_p
         self.build_predict(chol, pinv, te)
-        householder_qr(self.W[:, self.m:], D, D, D, te, self.be_p)
+        (householder_qr_blocked if self.blocked else householder_qr)(self.W[:, self.m:], D, D, D, te, self.be_p)
         err = None
         if not self.latent:
             err = self.error_estimate(z, Hc, Hv, pv[1], dt)

@@ -22,19 +22,21 @@ CASES = [("heat", "white_linear", "dirichlet", 8), ("heat", "white_linear", "neu
          ("sir", "latent_semilinear", "neumann", 4), ("lv", "white_semilinear", "neumann", 6)]
 
 
-@pytest.mark.parametrize("name,kind,bcond,num", CASES)
-def test_model_matches_oracle(name, kind, bcond, num):
+@pytest.mark.parametrize("blocked", [True, False], ids=["blocked", "unblocked"])
+@pytest.mark.parametrize("name,kind,bcond,num", CASES + [("heat", "white_linear", "dirichlet", 23), ("heat", "latent_linear", "neumann", 12)])
+def test_model_matches_oracle(name, kind, bcond, num, blocked):
     case = cases.make_case(name, num=num, bcond=bcond)
     family = kind.split("_")[0]
-    mdl = kernel_model.Model(case["pde"], family, case["nu"], case["gram_sqrtm"])
+    mdl = kernel_model.Model(case["pde"], family, case["nu"], case["gram_sqrtm"], blocked=blocked)
     init, stepf, semil = ek1_np.KINDS[kind]
     st = init(case["opde"], case["nu"], case["gram_sqrtm"], 1.0, semil)
     m0, C0 = mdl.initialize(case["pde"].y0)
     n = case["nu"] + 1
     assert not np.isnan(m0).any() and not np.isnan(C0).any()  # no read outside the envelopes
     assert cases.cov_excess(C0, st.cov_sqrtm, n) < 1
-    if not (family == "latent" and bcond == "neumann"):  # conditioning floor, see DESIGN.md
-        assert cases.mean_excess(m0, st.mean) < 1
+    with cases.perturbed_oracle():  # reproducibility floor of the reference's own initial mean, see DESIGN.md
+        st_eps = init(case["opde"], case["nu"], case["gram_sqrtm"], 1.0, semil)
+    assert cases.mean_excess(m0, st.mean, spread=st_eps.mean) < 1
     mean, chol = st.mean, st.cov_sqrtm
     for _ in range(3):
         st = stepf(case["opde"], st, case["dt"], case["nu"], case["gram_sqrtm"], semil)
