@@ -282,7 +282,7 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
     CU(cudaFuncSetAttribute(k_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run, kThreads, h->smem_bytes));
-    int want = 2;
+    int want = PNMOL_MIN_CTAS;
     if (const char* e = std::getenv("PNMOL_B200_CTAS_PER_SM")) want = std::max(1, std::atoi(e));
     occ = std::max(1, std::min(occ, want));
     h->grid = std::min(P.batch, occ * h->num_sms);

@@ -20,7 +20,13 @@
 
 namespace pnmol {
 
-constexpr int kThreads = 256;
+#ifndef PNMOL_THREADS
+#define PNMOL_THREADS 256
+#endif
+#ifndef PNMOL_MIN_CTAS
+#define PNMOL_MIN_CTAS 2
+#endif
+constexpr int kThreads = PNMOL_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxN = 8;     // num_derivatives + 1
 constexpr int kMaxComp = 4;  // PDE components

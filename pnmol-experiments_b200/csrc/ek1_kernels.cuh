@@ -60,7 +60,7 @@ __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, doub
                  nonfinite, pc);
 }
 
-__global__ void __launch_bounds__(kThreads, 2) k_run(const Problem P, const RunArgs a) {
+__global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem P, const RunArgs a) {
     extern __shared__ double smem_raw[];
     const Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm);
     __shared__ int nonfinite;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_run(const Problem P, const RunA
 }
 
 // initialize(): two square-root updates on a Kronecker-structured prior factor.
-__global__ void __launch_bounds__(kThreads, 2) k_init(const Problem P, const InitArgs a) {
+__global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_init(const Problem P, const InitArgs a) {
     extern __shared__ double smem_raw[];
     const Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm);
     __shared__ int nonfinite;

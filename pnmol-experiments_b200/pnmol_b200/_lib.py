@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpnmol_b200.so")
+LIB_PATH = os.environ.get("PNMOL_B200_LIB") or os.path.join(_HERE, "libpnmol_b200.so")  # env override: tuning builds
 
 c_int, c_double, c_void_p, c_int64 = ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int64
 
