@@ -141,8 +141,10 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
     double x0[kRPL], x1[kRPL];
 
     // ---- load this group's panel column (entries outside the column's own envelope are zero)
-    const int p0 = warp * PPW + g;
-    const bool hp = p0 < nbk;
+    // round-robin ownership (column p -> warp p % kWarps, group p / kWarps): consecutive reflectors are owned by
+    // different warps, so the owner's post-work overlaps with the next owner's critical chain
+    const int p0 = warp + kWarps * g;
+    const bool hp = p0 < nbk && g < PPW;
     const int jp = j0 + (hp ? p0 : 0);
     const int etp = hp ? env_top(s, jp) : -1, ebp = hp ? env_bot(s, jp) : -1;
     {
@@ -160,9 +162,12 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
     // ---- factor the panel: one barrier and one reduction round per column.  The owner publishes its column with
     // the rows c <= i zeroed (so nobody else needs per-element masks) and the diagonal entry alpha; every group
     // that still holds a live column reduces x_i . x_k and derives the reflector scalars (dlarfg) redundantly.
-    const int wfirst = warp * PPW, wlast = warp * PPW + PPW - 1;  // panel columns of this warp
+    int wlast = -1;  // last panel column held by this warp
+#pragma unroll
+    for (int gg = 0; gg < PPW; ++gg)
+        if (warp + kWarps * gg < nbk) wlast = warp + kWarps * gg;
     for (int i = 0; i < nbk; ++i) {
-        const bool own = p0 == i;
+        const bool own = hp && p0 == i;
         const int ri = i / G, si = i % G;  // register slot and lane that hold row i  (ri < 16 / G <= 4)
         double* xr = xraw + (i & 1) * vld;  // double buffered: the next owner may publish while others still read
         if (own) {
@@ -174,7 +179,7 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
             }
         }
         __syncthreads();
-        if (wfirst >= nbk || wlast < i) continue;  // no live panel column in this warp: only keep the barrier
+        if (wlast < i) continue;  // no live panel column in this warp: only keep the barrier
         const double al = sc[3 * i + 1];
         double d0 = 0.0, ss = 0.0, d0b = 0.0, ssb = 0.0;
 #pragma unroll
