@@ -94,7 +94,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 
 __host__ __device__ __forceinline__ size_t smem_doubles(int D, int m, int dd, int vld, int ldm) {
-    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 48 + 18 * (size_t)vld + (size_t)m * ldm + 8;
+    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 80 + 18 * (size_t)vld + (size_t)m * ldm + 8;
 }
 
 __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vld, int ldm) {
@@ -108,7 +108,7 @@ __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vl
     s.red = base;               base += 16;
     s.pv = base;                base += kMaxN;
     s.pinv = base;              base += kMaxN;
-    s.sc = base;                base += 48;
+    s.sc = base;                base += 80;
     s.xraw = base;              base += 2 * vld;
     s.Vs = base;                base += 16 * vld;
     s.msq = ldm > 0 ? base : nullptr;

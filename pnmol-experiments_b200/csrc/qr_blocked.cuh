@@ -20,6 +20,12 @@
 namespace pnmol {
 
 constexpr int kNB = 16;   // panel width
+#ifndef PNMOL_WY_TRAILING
+#define PNMOL_WY_TRAILING 0
+#endif
+// compact-WY (blocks of 4) trailing update; measured slower than the reflector-at-a-time loop at D = 150 on B200
+// (8 rows per lane make the 32-lane butterflies as expensive as the FMAs): profiles/r01_notes.md
+constexpr bool kUseWyTrailing = PNMOL_WY_TRAILING != 0;
 constexpr int kRPL = 16;  // rows per lane (upper bound; chunks of 4 beyond the row list are skipped)
 
 struct RowMap {  // compact row list of a panel: c < len1 -> j0 + c, else a2 + (c - len1)
@@ -125,6 +131,111 @@ __device__ __forceinline__ void apply_reflector(const double (&v)[kRPL], double 
     }
 }
 
+// Gram entries v_k . v_i for the pairs inside each block of 4 reflectors (6 per block): gsm[6 * b + {01,02,03,12,13,23}].
+__device__ __forceinline__ void panel_gram(const double* __restrict__ Vs, int vld, int len, int nbk, double* __restrict__ gsm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int pair = warp; pair < 24; pair += kWarps) {
+        const int b = pair / 6, q = pair - 6 * b;
+        const int k = 4 * b + (q < 3 ? 0 : q < 5 ? 1 : 2);
+        const int i = 4 * b + (q < 3 ? q + 1 : q < 5 ? q - 1 : 3);
+        double acc = 0.0;
+        if (i < nbk) {
+            for (int c = lane; c < len; c += 32) acc = fma(Vs[k * vld + c], Vs[i * vld + c], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) gsm[pair] = acc;
+    }
+}
+
+// Trailing update in compact-WY form, 4 reflectors at a time.  GT lanes hold a column (8 rows per lane), two columns
+// per lane group.  Per block: 8 independent dot products (4 reflectors x 2 columns) reduced together, the 4 x 4
+// triangular recurrence  w_i = -tau_i (v_i.x + sum_{k<i} w_k v_k.v_i)  on scalars, then one fused update.
+template <int GT>
+__device__ __noinline__ void trailing_wy(double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
+                                         const double* __restrict__ Vs, int vld, const double* __restrict__ sc,
+                                         const double* __restrict__ gsm) {
+    constexpr int CPW = (32 / GT) * 2;
+    constexpr int R = 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / GT, sl = lane % GT;
+    const double* vbase = Vs + sl;
+    for (int kb = j0 + nbk + warp * CPW; kb < ncols; kb += kWarps * CPW) {
+        const int k0 = kb + g * 2, k1 = k0 + 1;
+        const bool h0 = k0 < ncols, h1 = k1 < ncols;
+        double* c0 = W + (size_t)(h0 ? k0 : kb) * ld;
+        double* c1 = W + (size_t)(h1 ? k1 : kb) * ld;
+        double x0[R], x1[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int c = sl + GT * r;
+            const int row = rm.row(c);
+            const bool in = c < rm.len;
+            x0[r] = (in && h0) ? c0[row] : 0.0;
+            x1[r] = (in && h1) ? c1[row] : 0.0;
+        }
+        for (int b = 0; 4 * b < nbk; ++b) {
+            const int i0 = 4 * b;
+            double v[4][R];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool have = i0 + q < nbk;
+                const double* vp = vbase + (i0 + q) * vld;
+#pragma unroll
+                for (int r = 0; r < R; ++r) v[q][r] = have ? vp[GT * r] : 0.0;
+            }
+            double y[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { y[q][0] = 0.0; y[q][1] = 0.0; }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    y[q][0] = fma(v[q][r], x0[r], y[q][0]);
+                    y[q][1] = fma(v[q][r], x1[r], y[q][1]);
+                }
+            }
+#pragma unroll
+            for (int o = GT / 2; o > 0; o >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double ta = __shfl_xor_sync(0xffffffffu, y[q][0], o);
+                    const double tb = __shfl_xor_sync(0xffffffffu, y[q][1], o);
+                    y[q][0] += ta;
+                    y[q][1] += tb;
+                }
+            }
+            const double t0 = sc[3 * i0], t1 = i0 + 1 < nbk ? sc[3 * (i0 + 1)] : 0.0;
+            const double t2 = i0 + 2 < nbk ? sc[3 * (i0 + 2)] : 0.0, t3 = i0 + 3 < nbk ? sc[3 * (i0 + 3)] : 0.0;
+            const double g01 = gsm[6 * b], g02 = gsm[6 * b + 1], g03 = gsm[6 * b + 2];
+            const double g12 = gsm[6 * b + 3], g13 = gsm[6 * b + 4], g23 = gsm[6 * b + 5];
+            double w[4][2];
+#pragma unroll
+            for (int cw = 0; cw < 2; ++cw) {
+                w[0][cw] = -t0 * y[0][cw];
+                w[1][cw] = -t1 * fma(w[0][cw], g01, y[1][cw]);
+                w[2][cw] = -t2 * fma(w[1][cw], g12, fma(w[0][cw], g02, y[2][cw]));
+                w[3][cw] = -t3 * fma(w[2][cw], g23, fma(w[1][cw], g13, fma(w[0][cw], g03, y[3][cw])));
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    x0[r] = fma(w[q][0], v[q][r], x0[r]);
+                    x1[r] = fma(w[q][1], v[q][r], x1[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int c = sl + GT * r;
+            const int row = rm.row(c);
+            const bool in = c < rm.len;
+            if (in && h0) c0[row] = x0[r];
+            if (in && h1) c1[row] = x1[r];
+        }
+    }
+}
+
 // One panel: factor columns j0 .. j0+nbk-1 and apply their reflectors to all later columns.
 // Shared memory: Vs[kNB][vld] reflectors, xraw[2][vld] raw column of the current reflector (double
 // buffered), sc[3 * i] = tau of reflector i.
@@ -132,6 +243,7 @@ template <int G>
 __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const Shape& s, int j0, int nbk, const RowMap rm,
                                            double* __restrict__ Vs, int vld, double* __restrict__ xraw,
                                            double* __restrict__ sc, PhaseClock& pc) {
+    double* gsm = sc + 48;  // 24 Gram entries of the compact-WY blocks
     constexpr int CPW = (32 / G) * 2;  // trailing columns per warp (two per lane group)
     constexpr int PPW = 32 / G;        // panel columns per warp (one per lane group)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -215,6 +327,10 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
             scale = __drcp_rn(al - beta);
         }
         if (own && sl == 0) sc[3 * i] = tau;
+        if (own && tau == 0.0) {
+#pragma unroll
+            for (int r = 0; r < kRPL; ++r) Vs[i * vld + sl + G * r] = 0.0;
+        }
         if (tau != 0.0) {
             const double f0 = p0 > i && hp ? -tau * fma(scale, d0, e0) : 0.0;
             const double g0 = f0 * scale;
@@ -259,40 +375,49 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
     __syncthreads();  // all of Vs / sc written
     pc.mark(10);
 
-    // ---- trailing columns: load once, apply the nbk reflectors from registers, store once
-    const double* vbase = Vs + sl;
-    for (int kb = j0 + nbk + warp * CPW; kb < s.ncols; kb += kWarps * CPW) {
-        const int k0 = kb + g * 2, k1 = k0 + 1;
-        const bool h0 = k0 < s.ncols, h1 = k1 < s.ncols;
-        double* c0 = W + (size_t)(h0 ? k0 : kb) * ld;
-        double* c1 = W + (size_t)(h1 ? k1 : kb) * ld;
+    // ---- trailing columns: compact-WY update in blocks of 4 reflectors (row lists up to 256), else one at a time
+    if (kUseWyTrailing && rm.len <= 256) {
+        panel_gram(Vs, vld, rm.len, nbk, gsm);
+        __syncthreads();
+        if (rm.len <= 32) trailing_wy<4>(W, ld, s.ncols, j0, nbk, rm, Vs, vld, sc, gsm);
+        else if (rm.len <= 64) trailing_wy<8>(W, ld, s.ncols, j0, nbk, rm, Vs, vld, sc, gsm);
+        else if (rm.len <= 128) trailing_wy<16>(W, ld, s.ncols, j0, nbk, rm, Vs, vld, sc, gsm);
+        else trailing_wy<32>(W, ld, s.ncols, j0, nbk, rm, Vs, vld, sc, gsm);
+    } else {
+        const double* vbase = Vs + sl;
+        for (int kb = j0 + nbk + warp * CPW; kb < s.ncols; kb += kWarps * CPW) {
+            const int k0 = kb + g * 2, k1 = k0 + 1;
+            const bool h0 = k0 < s.ncols, h1 = k1 < s.ncols;
+            double* c0 = W + (size_t)(h0 ? k0 : kb) * ld;
+            double* c1 = W + (size_t)(h1 ? k1 : kb) * ld;
 #pragma unroll
-        for (int r = 0; r < kRPL; ++r) {
-            const int c = sl + G * r;
-            const int row = rm.row(c);
-            const bool in = c < rm.len;
-            x0[r] = (in && h0) ? c0[row] : 0.0;
-            x1[r] = (in && h1) ? c1[row] : 0.0;
-        }
-        for (int i = 0; i < nbk; ++i) {
-            const double tau = sc[3 * i];
-            if (tau == 0.0) continue;
-            double v[kRPL];
-            const double* vp = vbase + i * vld;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr) v[4 * q + rr] = q < nq ? vp[G * (4 * q + rr)] : 0.0;
+            for (int r = 0; r < kRPL; ++r) {
+                const int c = sl + G * r;
+                const int row = rm.row(c);
+                const bool in = c < rm.len;
+                x0[r] = (in && h0) ? c0[row] : 0.0;
+                x1[r] = (in && h1) ? c1[row] : 0.0;
             }
-            apply_reflector<G>(v, x0, x1, nq, tau);
-        }
+            for (int i = 0; i < nbk; ++i) {
+                const double tau = sc[3 * i];
+                if (tau == 0.0) continue;
+                double v[kRPL];
+                const double* vp = vbase + i * vld;
 #pragma unroll
-        for (int r = 0; r < kRPL; ++r) {
-            const int c = sl + G * r;
-            const int row = rm.row(c);
-            const bool in = c < rm.len;
-            if (in && h0) c0[row] = x0[r];
-            if (in && h1) c1[row] = x1[r];
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) v[4 * q + rr] = q < nq ? vp[G * (4 * q + rr)] : 0.0;
+                }
+                apply_reflector<G>(v, x0, x1, nq, tau);
+            }
+#pragma unroll
+            for (int r = 0; r < kRPL; ++r) {
+                const int c = sl + G * r;
+                const int row = rm.row(c);
+                const bool in = c < rm.len;
+                if (in && h0) c0[row] = x0[r];
+                if (in && h1) c1[row] = x1[r];
+            }
         }
     }
     pc.mark(11);

@@ -207,6 +207,43 @@ def test_dense_input_factor_and_adaptive_steps():
     assert not torch.isnan(sol.mean).any()
 
 
+@pytest.mark.parametrize("name,kind,bcond,num,dt", [("sir", "white_semilinear", "neumann", 100, 2.0 ** -3),
+                                                    ("spruce", "latent_semilinear", "dirichlet", 200, 2.0 ** -4)])
+def test_baseline_configs_c2_c3_full_size(name, kind, bcond, num, dt):
+    """BASELINE.json configs 2 and 3 at full size (SIR N=100: D=900, m=306; spruce N=200 latent: D=1200, m=202),
+    with the prior kernels of SURVEY section 8(d): initialisation and two steps, each from the oracle's state.  These
+    sizes exceed the register-resident panels (row lists > 512), so they also cover the column-by-column fallback."""
+    import time
+
+    from pnmol_b200 import pdefilter
+    from pnmol_b200.base import rv
+
+    case = cases.make_case(name, num=num, bcond=bcond, dt=dt, prior="matern" if name == "sir" else "se")
+    n = case["nu"] + 1
+    solver = cases.make_solver(kind, case)
+    init, stepf, semil = ek1_np.KINDS[kind]
+    st, st_eps = cases.oracle_pair(lambda: init(case["opde"], case["nu"], case["gram_sqrtm"], 1.0, semil))
+    t0 = time.perf_counter()
+    s0 = solver.initialize(case["pde"])
+    torch.cuda.synchronize()
+    t_init = time.perf_counter() - t0
+    assert cases.cov_excess(_np(s0.y.cov_sqrtm), st.cov_sqrtm, n) < 1
+    assert cases.mean_excess(_np(s0.y.mean), st.mean, spread=st_eps.mean) < 1
+    dev = s0.y.mean.device
+    for _ in range(2):
+        g = pdefilter.PDEFilterState(t=st.t, y=rv.MultivariateNormal(torch.tensor(st.mean, device=dev),
+                                                                    torch.tensor(st.cov_sqrtm, device=dev)),
+                                     error_estimate=None, reference_state=None, diffusion_squared_local=None)
+        t0 = time.perf_counter()
+        new, _ = solver.attempt_step(g, dt, case["pde"])
+        torch.cuda.synchronize()
+        t_step = time.perf_counter() - t0
+        st = stepf(case["opde"], st, dt, case["nu"], case["gram_sqrtm"], semil)
+        assert cases.mean_excess(_np(new.y.mean), st.mean) < 1
+        assert cases.cov_excess(_np(new.y.cov_sqrtm), st.cov_sqrtm, n) < 1
+    print(f"[{name} N={num} D={st.cov_sqrtm.shape[0]}] initialize {t_init:.2f} s, step {t_step:.2f} s (single CTA path)")
+
+
 # ------------------------------------------------------------------------- ensembles
 def test_ensemble_members_match_individual_oracle_solves():
     from oracle import setup_np
