@@ -286,6 +286,7 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
     if (const char* e = std::getenv("PNMOL_B200_CTAS_PER_SM")) want = std::max(1, std::atoi(e));
     occ = std::max(1, std::min(occ, want));
     h->grid = std::min(P.batch, occ * h->num_sms);
+    if (const char* e = std::getenv("PNMOL_B200_GRID")) h->grid = std::max(1, std::min(h->grid, std::atoi(e)));  // tuning
     const size_t wsz = (size_t)P.ld * (P.m + P.D);
     if ((rc = dev_alloc(h, &P.W, wsz * h->grid))) return rc;
     if ((rc = dev_alloc(h, &P.Hcol, (size_t)h->grid * P.m * P.wh))) return rc;
@@ -396,12 +397,12 @@ int pnmol_b200_profile(pnmol_b200_handle* h, int enable, uint64_t* cycles_out) {
     if (!h) return fail(-1, "null handle");
     CU(cudaSetDevice(h->device));
     CU(cudaDeviceSynchronize());
-    if (cycles_out && h->P.prof) CU(cudaMemcpy(cycles_out, h->P.prof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (cycles_out && h->P.prof) CU(cudaMemcpy(cycles_out, h->P.prof, 24 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     if (enable && !h->P.prof) {
-        int rc = dev_alloc(h, &h->P.prof, 16);
+        int rc = dev_alloc(h, &h->P.prof, 24);
         if (rc) return rc;
     }
-    if (h->P.prof) CU(cudaMemset(h->P.prof, 0, 16 * sizeof(uint64_t)));
+    if (h->P.prof) CU(cudaMemset(h->P.prof, 0, 24 * sizeof(uint64_t)));
     if (!enable) h->P.prof = nullptr;
     return 0;
 }

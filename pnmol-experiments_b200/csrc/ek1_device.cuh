@@ -73,7 +73,7 @@ struct Shape {  // QR row structure: rows [0,nt) top, [nt, nt+nbot) bottom
 };
 
 struct Smem {
-    double *vbuf, *mp, *z, *y, *xw, *xat, *red, *pv, *pinv, *Vs, *xraw, *sc, *msq;
+    double *vbuf, *mp, *z, *y, *xw, *xat, *red, *pv, *pinv, *Vs, *xraw, *sc, *msq, *Vr, *Ts, *Gs;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -94,7 +94,8 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 
 __host__ __device__ __forceinline__ size_t smem_doubles(int D, int m, int dd, int vld, int ldm) {
-    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 80 + 18 * (size_t)vld + (size_t)m * ldm + 8;
+    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 80 + 2 * (size_t)vld + 16 * ((size_t)vld + 2) + 18 * (size_t)vld + 288 + 272 +
+           (size_t)m * ldm + 8;
 }
 
 __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vld, int ldm) {
@@ -110,7 +111,10 @@ __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vl
     s.pinv = base;              base += kMaxN;
     s.sc = base;                base += 80;
     s.xraw = base;              base += 2 * vld;
-    s.Vs = base;                base += 16 * vld;
+    s.Vs = base;                base += 16 * (vld + 2);
+    s.Vr = base;                base += 18 * vld;
+    s.Ts = base;                base += 288;
+    s.Gs = base;                base += 272;
     s.msq = ldm > 0 ? base : nullptr;
     return s;
 }
@@ -193,6 +197,11 @@ __device__ void householder_columns(double* __restrict__ W, int ld, const Shape&
 __device__ void householder_qr(double* __restrict__ W, int ld, const Shape s, double* vbuf, double* red) {
     const int nrows = s.nt + s.nbot;
     householder_columns(W, ld, s, 0, nrows < s.ncols ? nrows : s.ncols, vbuf, red);
+}
+
+// Scratch for the tensor-core trailing update (per-warp partial tiles): the m x ldm buffer is free during a QR.
+__device__ __forceinline__ double* qr_scratch(const Problem& P, const Smem& sm) {
+    return (sm.msq != nullptr && P.m * P.ldm >= 2 * kWarps * 128) ? sm.msq : nullptr;
 }
 
 }  // namespace pnmol
@@ -641,7 +650,7 @@ __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, 
     pc.mark(4);
     Shape sh;
     sh.nt = D; sh.nbot = nbot; sh.ncols = ncols; sh.te = te; sh.be = be;
-    householder_qr_blocked(Wl, ld, sh, sm.Vs, P.vld, sm.xraw, sm.sc, sm.vbuf, sm.red, pc);
+    householder_qr_blocked(Wl, ld, sh, sm.Vs, P.vld, sm.xraw, sm.sc, sm.Vr, sm.Ts, sm.Gs, qr_scratch(P, sm), sm.vbuf, sm.red, pc);
     pc.mark(5);
 
     // R1 = Wl[0:m, 0:m] (upper, column-major).  y = R1^-T z (for the mean),  x = R1^-1 z (quirk Q1,

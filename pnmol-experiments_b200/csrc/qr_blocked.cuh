@@ -26,6 +26,14 @@ constexpr int kNB = 16;   // panel width
 // compact-WY (blocks of 4) trailing update; measured slower than the reflector-at-a-time loop at D = 150 on B200
 // (8 rows per lane make the 32-lane butterflies as expensive as the FMAs): profiles/r01_notes.md
 constexpr bool kUseWyTrailing = PNMOL_WY_TRAILING != 0;
+#ifndef PNMOL_DMMA_TRAILING
+#define PNMOL_DMMA_TRAILING 1
+#endif
+constexpr bool kUseDmmaTrailing = PNMOL_DMMA_TRAILING != 0;
+#ifndef PNMOL_DMMA_PAIR
+#define PNMOL_DMMA_PAIR 0
+#endif
+constexpr bool kUseDmmaPair = PNMOL_DMMA_PAIR != 0;  // warp-pair single-pass variant (measured slower: L2 access efficiency)
 constexpr int kRPL = 16;  // rows per lane (upper bound; chunks of 4 beyond the row list are skipped)
 
 struct RowMap {  // compact row list of a panel: c < len1 -> j0 + c, else a2 + (c - len1)
@@ -236,14 +244,282 @@ __device__ __noinline__ void trailing_wy(double* __restrict__ W, int ld, int nco
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Tensor-core trailing update (FP64 DMMA, mma.sync.m8n8k4.f64).  Fragment layout (verified on B200,
+// tools/dmma_probe.cu): lane = 4 g + t supplies A[g][t] and B[t][g] and owns D[g][2t], D[g][2t+1].
+//
+// Compact WY:  C <- C - V T^T (V^T C)  for the kNB reflectors of a panel.  A warp takes 8 trailing columns; lane
+// (g, t) handles column g and, of every 8-row tile i of the panel's row list, rows 8i + 2t and 8i + 2t + 1.  With
+// that assignment the column data is at once the A operand of  Y^T = C^T V  (k-step (i, e) uses rows 8i + 2t + e)
+// and the accumulator of  C^T -= Y'^T V^T  -- no shuffles, no layout conversion; Y'^T = Y^T T is 8 more DMMAs.
+// Shared memory: Vs[refl][ldt] (ldt = 2 mod 8) feeds the B operand of the second product, Vr[row][kLdr] that of the
+// first, Ts[kNB][kLdr] holds T; the strides make every fragment load bank-conflict free.
+constexpr int kLdr = 18;
+constexpr int kCh = 8;  // 8-row tiles fetched per chunk
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Gs[k][i] = v_k . v_i for k <= i (upper triangle of V^T V) on the tensor pipe: every warp takes a slice of the 8-row
+// tiles and accumulates the three 8 x 8 blocks (0,0), (0,1), (1,1); the per-warp partial blocks go to `scratch`
+// (kWarps x 192 doubles) and are summed in a fixed order (bitwise reproducible; no floating-point atomics).
+// Operands: A[g][t] = V[row][g + 8a], B[t][g] = V[row][g + 8b], row = 8i + 2t + e.  Contains one __syncthreads.
+__device__ __forceinline__ void panel_gram_dmma(const double* __restrict__ Vr, int len, double* __restrict__ Gs,
+                                                double* __restrict__ scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ntile = (len + 7) >> 3;
+    double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+    double d00[2] = {0.0, 0.0}, d01[2] = {0.0, 0.0}, d11[2] = {0.0, 0.0};
+    for (int i = warp; i < ntile; i += kWarps) {
+        const double* v0 = Vr + (8 * i + 2 * t) * kLdr + g;
+        const double a0 = v0[0], a1 = v0[8], b0 = v0[kLdr], b1 = v0[kLdr + 8];
+        dmma884(c00[0], c00[1], a0, a0);
+        dmma884(c01[0], c01[1], a0, a1);
+        dmma884(c11[0], c11[1], a1, a1);
+        dmma884(d00[0], d00[1], b0, b0);
+        dmma884(d01[0], d01[1], b0, b1);
+        dmma884(d11[0], d11[1], b1, b1);
+    }
+    double* mine = scratch + warp * 192;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int e = g * 8 + 2 * t + q;
+        mine[e] = c00[q] + d00[q];
+        mine[64 + e] = c01[q] + d01[q];
+        mine[128 + e] = c11[q] + d11[q];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 192; e += kThreads) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) sum += scratch[w * 192 + e];
+        const int blk = e >> 6, r = (e & 63) >> 3, c = e & 7;
+        Gs[(r + (blk == 2 ? 8 : 0)) * 17 + c + (blk >= 1 ? 8 : 0)] = sum;
+    }
+}
+
+// T of the compact WY representation (upper triangular, LAPACK dlarft forward/columnwise):
+// T[i][i] = tau_i,  T[0:i, i] = -tau_i T[0:i, 0:i] (V^T v_i)[0:i].  One warp, lane k owns row k in registers.
+__device__ __forceinline__ void panel_t_factor(const double* __restrict__ Gs, const double* __restrict__ sc, int nbk,
+                                               double* __restrict__ Ts) {
+    const int k = threadIdx.x & 31;
+    double Trow[kNB];
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) Trow[j] = 0.0;
+#pragma unroll
+    for (int i = 0; i < kNB; ++i) {
+        if (i < nbk) {  // (columns beyond the panel stay zero; their Gram entries were never written)
+            const double tau = sc[3 * i];
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < i; j += 2) {
+                a0 = fma(Trow[j], Gs[j * 17 + i], a0);
+                if (j + 1 < i) a1 = fma(Trow[j + 1], Gs[(j + 1) * 17 + i], a1);
+            }
+            Trow[i] = k < i ? -tau * (a0 + a1) : (k == i ? tau : 0.0);
+        }
+    }
+    if (k < kNB) {
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) Ts[k * kLdr + j] = Trow[j];
+    }
+}
+
+__device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
+                                           const double* __restrict__ Vs, int ldt, const double* __restrict__ Vr,
+                                           const double* __restrict__ Ts) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ntile = (rm.len + 7) >> 3;
+    // B fragments of T: T[8h + 2t + s][g + 8n]
+    double tf[2][2][2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int sx = 0; sx < 2; ++sx)
+#pragma unroll
+            for (int n = 0; n < 2; ++n) tf[h][sx][n] = Ts[(8 * h + 2 * t + sx) * kLdr + g + 8 * n];
+    for (int kb = j0 + nbk + warp * 8; kb < ncols; kb += kWarps * 8) {
+        const int col = kb + g;
+        const bool have = col < ncols;
+        double* cp = W + (size_t)(have ? col : kb) * ld;
+        // ---- Y^T = C^T V : accumulators [row parity e][reflector half n]; rows are fetched in chunks of kCh tiles
+        double y[2][2][2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int n = 0; n < 2; ++n) { y[e][n][0] = 0.0; y[e][n][1] = 0.0; }
+        for (int i0 = 0; i0 < ntile; i0 += kCh) {
+            double xa[kCh][2];
+#pragma unroll
+            for (int a = 0; a < kCh; ++a) {
+                const int c0 = 8 * (i0 + a) + 2 * t, c1 = c0 + 1;
+                xa[a][0] = (have && c0 < rm.len) ? cp[rm.row(c0)] : 0.0;
+                xa[a][1] = (have && c1 < rm.len) ? cp[rm.row(c1)] : 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < kCh; ++a) {
+                if (i0 + a < ntile) {
+                    const double* v0 = Vr + (8 * (i0 + a) + 2 * t) * kLdr + g;
+                    dmma884(y[0][0][0], y[0][0][1], xa[a][0], v0[0]);
+                    dmma884(y[0][1][0], y[0][1][1], xa[a][0], v0[8]);
+                    dmma884(y[1][0][0], y[1][0][1], xa[a][1], v0[kLdr]);
+                    dmma884(y[1][1][0], y[1][1][1], xa[a][1], v0[kLdr + 8]);
+                }
+            }
+        }
+        double yt[2][2];  // Y^T[col g][reflectors 8n + 2t, 8n + 2t + 1]
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) yt[n][q] = y[0][n][q] + y[1][n][q];
+        // ---- Y'^T = Y^T T
+        double z[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int sx = 0; sx < 2; ++sx)
+#pragma unroll
+                for (int n = 0; n < 2; ++n) dmma884(z[n][0], z[n][1], yt[h][sx], tf[h][sx][n]);
+#pragma unroll
+        for (int n = 0; n < 2; ++n) { z[n][0] = -z[n][0]; z[n][1] = -z[n][1]; }
+        // ---- C^T -= Y'^T V^T, again in chunks of kCh tiles
+        for (int i0 = 0; i0 < ntile; i0 += kCh) {
+            double xa[kCh][2];
+#pragma unroll
+            for (int a = 0; a < kCh; ++a) {
+                const int c0 = 8 * (i0 + a) + 2 * t, c1 = c0 + 1;
+                xa[a][0] = (have && c0 < rm.len) ? cp[rm.row(c0)] : 0.0;
+                xa[a][1] = (have && c1 < rm.len) ? cp[rm.row(c1)] : 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < kCh; ++a) {
+                if (i0 + a < ntile) {
+                    const double* vb = Vs + 8 * (i0 + a) + g;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int sx = 0; sx < 2; ++sx) dmma884(xa[a][0], xa[a][1], z[h][sx], vb[(8 * h + 2 * t + sx) * ldt]);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < kCh; ++a) {
+                const int c0 = 8 * (i0 + a) + 2 * t, c1 = c0 + 1;
+                if (have && c0 < rm.len) cp[rm.row(c0)] = xa[a][0];
+                if (have && c1 < rm.len) cp[rm.row(c1)] = xa[a][1];
+            }
+        }
+    }
+}
+
+// Single-pass variant for row lists of at most 8 * 2 * kHalf rows: a warp PAIR shares an 8-column group, each warp
+// keeps its half of the row tiles in registers (all loads issued up front: one L2 round trip), the two partial
+// Y^T are exchanged through `xch` (2 slots x kWarps x 128 doubles, double buffered: one __syncthreads per round),
+// both warps apply T redundantly and update their own rows in place.  Every warp runs the same number of rounds.
+constexpr int kHalf = 16;  // tiles per warp (row lists up to 256)
+
+__device__ __noinline__ void trailing_dmma_pair(double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
+                                                const double* __restrict__ Vs, int ldt, const double* __restrict__ Vr,
+                                                const double* __restrict__ Ts, double* __restrict__ xch, PhaseClock& pc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ntile = (rm.len + 7) >> 3;
+    const int nth = (ntile + 1) >> 1;          // tiles of the first half
+    const int half = warp & 1, pair = warp >> 1;
+    const int tbeg = half ? nth : 0, tcnt = half ? ntile - nth : nth;
+    constexpr int kPairs = kWarps / 2;
+    const int first = j0 + nbk;
+    const int rounds = (ncols - first + 8 * kPairs - 1) / (8 * kPairs);
+    for (int rd = 0; rd < rounds; ++rd) {
+        const int col = first + (rd * kPairs + pair) * 8 + g;
+        const bool have = col < ncols;
+        double* cp = W + (size_t)(have ? col : first) * ld;
+        double xa[kHalf][2];
+#pragma unroll
+        for (int a = 0; a < kHalf; ++a) {
+            const int c0 = 8 * (tbeg + a) + 2 * t, c1 = c0 + 1;
+            const bool live = a < tcnt;
+            xa[a][0] = (have && live && c0 < rm.len) ? cp[rm.row(c0)] : 0.0;
+            xa[a][1] = (have && live && c1 < rm.len) ? cp[rm.row(c1)] : 0.0;
+        }
+        double y[2][2][2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int n = 0; n < 2; ++n) { y[e][n][0] = 0.0; y[e][n][1] = 0.0; }
+#pragma unroll
+        for (int a = 0; a < kHalf; ++a) {
+            if (a < tcnt) {
+                const double* v0 = Vr + (8 * (tbeg + a) + 2 * t) * kLdr + g;
+                dmma884(y[0][0][0], y[0][0][1], xa[a][0], v0[0]);
+                dmma884(y[0][1][0], y[0][1][1], xa[a][0], v0[8]);
+                dmma884(y[1][0][0], y[1][0][1], xa[a][1], v0[kLdr]);
+                dmma884(y[1][1][0], y[1][1][1], xa[a][1], v0[kLdr + 8]);
+            }
+        }
+        pc.mark(16);
+        // exchange the partial Y^T with the partner warp (fixed summation order: first half + second half)
+        double* slot = xch + (rd & 1) * (kWarps * 128);
+        double* mine = slot + warp * 128 + lane;
+        mine[0] = y[0][0][0] + y[1][0][0];
+        mine[32] = y[0][0][1] + y[1][0][1];
+        mine[64] = y[0][1][0] + y[1][1][0];
+        mine[96] = y[0][1][1] + y[1][1][1];
+        __syncthreads();
+        pc.mark(17);
+        const double* lo = slot + (warp & ~1) * 128 + lane;
+        const double* hi = lo + 128;
+        double yt[2][2];
+        yt[0][0] = lo[0] + hi[0];
+        yt[0][1] = lo[32] + hi[32];
+        yt[1][0] = lo[64] + hi[64];
+        yt[1][1] = lo[96] + hi[96];
+        double z[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int sx = 0; sx < 2; ++sx) {
+                const double* tp = Ts + (8 * h + 2 * t + sx) * kLdr + g;
+                dmma884(z[0][0], z[0][1], yt[h][sx], tp[0]);
+                dmma884(z[1][0], z[1][1], yt[h][sx], tp[8]);
+            }
+#pragma unroll
+        for (int n = 0; n < 2; ++n) { z[n][0] = -z[n][0]; z[n][1] = -z[n][1]; }
+#pragma unroll
+        for (int a = 0; a < kHalf; ++a) {
+            if (a < tcnt) {
+                const double* vb = Vs + 8 * (tbeg + a) + g;
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int sx = 0; sx < 2; ++sx) dmma884(xa[a][0], xa[a][1], z[h][sx], vb[(8 * h + 2 * t + sx) * ldt]);
+            }
+        }
+        pc.mark(18);
+#pragma unroll
+        for (int a = 0; a < kHalf; ++a) {
+            const int c0 = 8 * (tbeg + a) + 2 * t, c1 = c0 + 1;
+            const bool live = a < tcnt;
+            if (have && live && c0 < rm.len) cp[rm.row(c0)] = xa[a][0];
+            if (have && live && c1 < rm.len) cp[rm.row(c1)] = xa[a][1];
+        }
+        pc.mark(19);
+    }
+}
+
 // One panel: factor columns j0 .. j0+nbk-1 and apply their reflectors to all later columns.
 // Shared memory: Vs[kNB][vld] reflectors, xraw[2][vld] raw column of the current reflector (double
 // buffered), sc[3 * i] = tau of reflector i.
 template <int G>
 __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const Shape& s, int j0, int nbk, const RowMap rm,
                                            double* __restrict__ Vs, int vld, double* __restrict__ xraw,
-                                           double* __restrict__ sc, PhaseClock& pc) {
+                                           double* __restrict__ sc, double* __restrict__ Vr, double* __restrict__ Ts,
+                                           double* __restrict__ Gs, double* __restrict__ scratch, PhaseClock& pc) {
     double* gsm = sc + 48;  // 24 Gram entries of the compact-WY blocks
+    const int ldt = vld + 2;  // reflector-major stride of Vs (2 mod 8: conflict-free DMMA fragment loads)
     constexpr int CPW = (32 / G) * 2;  // trailing columns per warp (two per lane group)
     constexpr int PPW = 32 / G;        // panel columns per warp (one per lane group)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -329,7 +605,7 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
         if (own && sl == 0) sc[3 * i] = tau;
         if (own && tau == 0.0) {
 #pragma unroll
-            for (int r = 0; r < kRPL; ++r) Vs[i * vld + sl + G * r] = 0.0;
+            for (int r = 0; r < kRPL; ++r) { Vs[i * ldt + sl + G * r] = 0.0; Vr[(sl + G * r) * kLdr + i] = 0.0; }
         }
         if (tau != 0.0) {
             const double f0 = p0 > i && hp ? -tau * fma(scale, d0, e0) : 0.0;
@@ -354,7 +630,9 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
                 for (int r = 0; r < kRPL; ++r) {
                     const bool eq = r == ri && sl == si;
                     const bool ge = r > ri || (r == ri && sl >= si);
-                    Vs[i * vld + sl + G * r] = eq ? 1.0 : scale * xr[sl + G * r];
+                    const double vv = eq ? 1.0 : scale * xr[sl + G * r];
+                    Vs[i * ldt + sl + G * r] = vv;
+                    Vr[(sl + G * r) * kLdr + i] = vv;
                     if (ge) x0[r] = eq ? beta : 0.0;
                 }
             }
@@ -375,14 +653,27 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
     __syncthreads();  // all of Vs / sc written
     pc.mark(10);
 
-    // ---- trailing columns: compact-WY update in blocks of 4 reflectors (row lists up to 256), else one at a time
+    // ---- trailing columns: tensor-core compact-WY update when the row list fits the V buffers, else (or on request)
+    // the DFMA paths
+    if (kUseDmmaTrailing && scratch != nullptr && 8 * ((rm.len + 7) >> 3) <= vld) {
+        if (j0 + nbk < s.ncols) {
+            panel_gram_dmma(Vr, rm.len, Gs, scratch);
+            __syncthreads();
+            pc.mark(13);
+            if (warp == 0) panel_t_factor(Gs, sc, nbk, Ts);
+            __syncthreads();
+            pc.mark(14);
+            if (kUseDmmaPair && rm.len <= 16 * kHalf) trailing_dmma_pair(W, ld, s.ncols, j0, nbk, rm, Vs, ldt, Vr, Ts, scratch, pc);
+            else trailing_dmma(W, ld, s.ncols, j0, nbk, rm, Vs, ldt, Vr, Ts);
+        }
+    } else
     if (kUseWyTrailing && rm.len <= 256) {
-        panel_gram(Vs, vld, rm.len, nbk, gsm);
+        panel_gram(Vs, ldt, rm.len, nbk, gsm);
         __syncthreads();
-        if (rm.len <= 32) trailing_wy<4>(W, ld, s.ncols, j0, nbk, rm, Vs, vld, sc, gsm);
-        else if (rm.len <= 64) trailing_wy<8>(W, ld, s.ncols, j0, nbk, rm, Vs, vld, sc, gsm);
-        else if (rm.len <= 128) trailing_wy<16>(W, ld, s.ncols, j0, nbk, rm, Vs, vld, sc, gsm);
-        else trailing_wy<32>(W, ld, s.ncols, j0, nbk, rm, Vs, vld, sc, gsm);
+        if (rm.len <= 32) trailing_wy<4>(W, ld, s.ncols, j0, nbk, rm, Vs, ldt, sc, gsm);
+        else if (rm.len <= 64) trailing_wy<8>(W, ld, s.ncols, j0, nbk, rm, Vs, ldt, sc, gsm);
+        else if (rm.len <= 128) trailing_wy<16>(W, ld, s.ncols, j0, nbk, rm, Vs, ldt, sc, gsm);
+        else trailing_wy<32>(W, ld, s.ncols, j0, nbk, rm, Vs, ldt, sc, gsm);
     } else {
         const double* vbase = Vs + sl;
         for (int kb = j0 + nbk + warp * CPW; kb < s.ncols; kb += kWarps * CPW) {
@@ -402,7 +693,7 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
                 const double tau = sc[3 * i];
                 if (tau == 0.0) continue;
                 double v[kRPL];
-                const double* vp = vbase + i * vld;
+                const double* vp = vbase + i * ldt;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
 #pragma unroll
@@ -428,7 +719,8 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
 // Blocked QR driver.  Panels whose row list exceeds 512 rows (or the smem V buffer) fall
 // back to the unblocked column-by-column routine.
 __device__ void householder_qr_blocked(double* __restrict__ W, int ld, const Shape s, double* Vs, int vld, double* xraw,
-                                       double* sc, double* vbuf, double* red, PhaseClock& pc) {
+                                       double* sc, double* Vr, double* Ts, double* Gs, double* scratch, double* vbuf,
+                                       double* red, PhaseClock& pc) {
     const int nrows = s.nt + s.nbot;
     const int nref = nrows < s.ncols ? nrows : s.ncols;
     int j0 = 0;
@@ -444,13 +736,13 @@ __device__ void householder_qr_blocked(double* __restrict__ W, int ld, const Sha
         if (rm.len > 32 * kRPL || 16 * G > vld) {
             householder_columns(W, ld, s, j0, j0 + nbk, vbuf, red);
         } else if (G == 4) {
-            qr_panel_step<4>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, pc);
+            qr_panel_step<4>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, Vr, Ts, Gs, scratch, pc);
         } else if (G == 8) {
-            qr_panel_step<8>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, pc);
+            qr_panel_step<8>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, Vr, Ts, Gs, scratch, pc);
         } else if (G == 16) {
-            qr_panel_step<16>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, pc);
+            qr_panel_step<16>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, Vr, Ts, Gs, scratch, pc);
         } else {
-            qr_panel_step<32>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, pc);
+            qr_panel_step<32>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, Vr, Ts, Gs, scratch, pc);
         }
         j0 += nbk;
     }

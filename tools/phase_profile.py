@@ -22,12 +22,13 @@ torch.cuda.synchronize()
 _lib.check(lib.pnmol_b200_profile(es.engine.h, 1, None))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); es.engine.run(pde.t0, es.dts, mean, chol); e1.record(); torch.cuda.synchronize()
-out = np.zeros(16, np.uint64)
+out = np.zeros(24, np.uint64)
 _lib.check(lib.pnmol_b200_profile(es.engine.h, 0, _lib.ptr(out)))
 names = ["mean+evaluate_ode", "build predict", "QR predict (rest)", "error estimate", "build update", "QR update (rest)", "solves+mean", "outputs",
-         "qr: panel load", "qr: panel factor", "qr: panel writeback", "qr: trailing", "qr: end barrier"]
-tot = float(out[:13].sum())
+         "qr: panel load", "qr: panel factor", "qr: panel writeback", "qr: trailing apply", "qr: end barrier",
+         "qr: gram V^T V", "qr: T factor", "-", "pair: loads+gemm1", "pair: barrier", "pair: T+gemm2", "pair: stores"]
+tot = float(out[:20].sum())
 ms = e0.elapsed_time(e1)
 print(f"members {M} steps {len(es.dts)}  kernel {ms:.1f} ms  -> {M*len(es.dts)/ms*1e3:.0f} member-steps/s")
-for n, c in zip(names, out[:13]):
+for n, c in zip(names, out[:20]):
     print(f"  {n:20s} {100.0*float(c)/tot:6.2f} %   {float(c)/(M*len(es.dts)):12.0f} cycles / member-step")
