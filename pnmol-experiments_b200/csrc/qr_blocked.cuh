@@ -567,6 +567,7 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
             }
         }
         __syncthreads();
+        pc.mark(20);
         if (wlast < i) continue;  // no live panel column in this warp: only keep the barrier
         const double al = sc[3 * i + 1];
         double d0 = 0.0, ss = 0.0, d0b = 0.0, ssb = 0.0;
@@ -592,6 +593,7 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
         if (G < 8 && ri == 3) e0 = x0[3];
         e0 = __shfl_sync(0xffffffffu, e0, (lane & ~(G - 1)) | si);
         group_sum2<G>(d0, ss);
+        pc.mark(21);
         // dlarfg on (alpha, ||x||^2): beta = -sign(alpha) ||(alpha, x)||, tau = (beta - alpha) / beta, v = x / (alpha - beta)
         double tau = 0.0, beta = al, scale = 0.0;
         if (ss != 0.0) {  // zero sub-column -> H = I
@@ -602,6 +604,7 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
             tau = (beta - al) * -copysign(rn, al);
             scale = __drcp_rn(al - beta);
         }
+        pc.mark(22);
         if (own && sl == 0) sc[3 * i] = tau;
         if (own && tau == 0.0) {
 #pragma unroll

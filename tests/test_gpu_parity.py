@@ -244,6 +244,31 @@ def test_baseline_configs_c2_c3_full_size(name, kind, bcond, num, dt):
     print(f"[{name} N={num} D={st.cov_sqrtm.shape[0]}] initialize {t_init:.2f} s, step {t_step:.2f} s (single CTA path)")
 
 
+@pytest.mark.skipif(not os.environ.get("PNMOL_B200_SLOW"), reason="minutes on the single-CTA path; set PNMOL_B200_SLOW=1")
+def test_baseline_config_c4_full_size():
+    """BASELINE.json config 4 (heat N=1024: D=3072, m=1026): one step from the oracle's state.  Until the multi-CTA
+    large-D kernel exists this runs on one CTA (column-by-column path) and takes minutes -- opt-in."""
+    import time
+
+    from pnmol_b200 import pdefilter
+    from pnmol_b200.base import rv
+
+    case = cases.make_case("heat", num=1024, bcond="dirichlet")
+    solver = cases.make_solver("white_linear", case)
+    st = ek1_np.white_initialize(case["opde"], 2, case["gram_sqrtm"])
+    solver.initialize(case["pde"])
+    g = pdefilter.PDEFilterState(t=st.t, y=rv.MultivariateNormal(torch.tensor(st.mean).cuda(), torch.tensor(st.cov_sqrtm).cuda()),
+                                 error_estimate=None, reference_state=None, diffusion_squared_local=None)
+    t0 = time.perf_counter()
+    new, _ = solver.attempt_step(g, case["dt"], case["pde"])
+    torch.cuda.synchronize()
+    t_step = time.perf_counter() - t0
+    ref = ek1_np.white_step(case["opde"], st, case["dt"], 2, case["gram_sqrtm"])
+    assert cases.mean_excess(_np(new.y.mean), ref.mean) < 1
+    assert cases.cov_excess(_np(new.y.cov_sqrtm), ref.cov_sqrtm, 3) < 1
+    print(f"[heat N=1024 D=3072] step {t_step:.1f} s (single CTA path)")
+
+
 # ------------------------------------------------------------------------- ensembles
 def test_ensemble_members_match_individual_oracle_solves():
     from oracle import setup_np

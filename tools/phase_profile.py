@@ -26,9 +26,10 @@ out = np.zeros(24, np.uint64)
 _lib.check(lib.pnmol_b200_profile(es.engine.h, 0, _lib.ptr(out)))
 names = ["mean+evaluate_ode", "build predict", "QR predict (rest)", "error estimate", "build update", "QR update (rest)", "solves+mean", "outputs",
          "qr: panel load", "qr: panel factor", "qr: panel writeback", "qr: trailing apply", "qr: end barrier",
-         "qr: gram V^T V", "qr: T factor", "-", "pair: loads+gemm1", "pair: barrier", "pair: T+gemm2", "pair: stores"]
-tot = float(out[:20].sum())
+         "qr: gram V^T V", "qr: T factor", "-", "pair: loads+gemm1", "pair: barrier", "pair: T+gemm2", "pair: stores",
+         "panel: publish+barrier", "panel: dots+reduce", "panel: scalars", "(panel: rest = update+own -> in panel factor)"]
+tot = float(out[:24].sum())
 ms = e0.elapsed_time(e1)
 print(f"members {M} steps {len(es.dts)}  kernel {ms:.1f} ms  -> {M*len(es.dts)/ms*1e3:.0f} member-steps/s")
-for n, c in zip(names, out[:20]):
+for n, c in zip(names, out[:24]):
     print(f"  {n:20s} {100.0*float(c)/tot:6.2f} %   {float(c)/(M*len(es.dts)):12.0f} cycles / member-step")
