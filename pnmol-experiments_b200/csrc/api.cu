@@ -2,6 +2,7 @@
 // argument checking, device-buffer ownership, envelope computation, kernel launches.
 #include "../../include/pnmol_b200.h"
 #include "ek1_kernels.cuh"
+#include "ek1_large.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -102,6 +103,11 @@ struct pnmol_b200_handle {
     double *hs_y0 = nullptr, *hs_mean_a = nullptr, *hs_mean_b = nullptr, *hs_chol_a = nullptr, *hs_chol_b = nullptr,
            *hs_diffsum = nullptr, *hs_diffcal = nullptr;
     int32_t* hs_status = nullptr;
+    // multi-CTA path for large state dimension (ek1_large.cuh): chosen when the single-CTA kernels' shared memory
+    // does not fit (or PNMOL_B200_FORCE_LARGE=1, used by the parity tests to run both paths on the same inputs)
+    bool large = false;
+    LargeQR q{};
+    size_t smem_large = 0;
 };
 
 namespace {
@@ -159,6 +165,17 @@ int upload_steps(pnmol_b200_handle* h, int nsteps, double t0, const double* dts,
     a->tnew = h->steparr + nsteps;
     a->pv = h->steparr + 2 * (size_t)nsteps;
     a->pinv = h->steparr + 2 * (size_t)nsteps + (size_t)nsteps * n;
+    return 0;
+}
+
+int launch_run(pnmol_b200_handle* h, RunArgs& a, cudaStream_t st) {
+    if (h->large) {
+        void* args[] = {(void*)&h->P, (void*)&a, (void*)&h->q};
+        CU(cudaLaunchCooperativeKernel((const void*)k_run_large, dim3(h->grid), dim3(kThreads), args, h->smem_large, st));
+    } else {
+        k_run<<<h->grid, kThreads, h->smem_bytes, st>>>(h->P, a);
+    }
+    ++g_launches;
     return 0;
 }
 
@@ -275,7 +292,46 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
         P.vld = 16 * G;
         P.ldm = P.m <= 96 ? (P.m | 1) : 0;  // odd leading dimension: conflict-free rows and columns
         h->smem_bytes = smem_doubles(P.D, P.m, P.dd, P.vld, P.ldm) * sizeof(double);
-        if (h->smem_bytes > h->smem_optin) return fail(-1, "state dimension too large for the single-CTA path");
+        const char* force = std::getenv("PNMOL_B200_FORCE_LARGE");
+        h->large = h->smem_bytes > h->smem_optin || (force && std::atoi(force) != 0);
+        if (h->large) {
+            // one member at a time on the whole grid: one workspace, vectors in global scratch
+            LargeQR& q = h->q;
+            int cap = (int)(h->smem_optin / sizeof(double)) - kLargeFixed - 64;
+            if (const char* e = std::getenv("PNMOL_B200_LARGE_CAP")) cap = std::max(1280, std::min(cap, std::atoi(e)));  // >= one 64-row V chunk (64 x kLdr)
+            cap &= ~15;
+            const int lp = (maxlen + 7) & ~7;
+            if (lp > cap) return fail(-1, "state dimension too large: one panel column does not fit in shared memory");
+            q.cap = cap;
+            q.lv = lp + 8;
+            q.ycols = P.m + P.D;
+            h->smem_large = (size_t)(kLargeFixed + cap) * sizeof(double);
+            P.ldm = 0;
+            CU(cudaFuncSetAttribute(k_run_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_large));
+            CU(cudaFuncSetAttribute(k_init_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_large));
+            int occ = 0, occ2 = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_large, kThreads, h->smem_large));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_init_large, kThreads, h->smem_large));
+            if (std::min(occ, occ2) < 1) return fail(-1, "multi-CTA kernels do not fit on an SM");
+            h->grid = h->num_sms;
+            if (const char* e = std::getenv("PNMOL_B200_GRID")) h->grid = std::max(1, std::min(h->grid, std::atoi(e)));
+            const size_t wsz = (size_t)P.ld * (P.m + P.D);
+            if ((rc = dev_alloc(h, &P.W, wsz))) return rc;
+            if ((rc = dev_alloc(h, &P.Hcol, (size_t)P.m * P.wh))) return rc;
+            if ((rc = dev_alloc(h, &P.Hval, (size_t)P.m * P.wh))) return rc;
+            if ((rc = dev_alloc(h, &P.F, (size_t)P.m * P.d))) return rc;
+            if ((rc = dev_alloc(h, &P.S, (size_t)P.m * P.m))) return rc;
+            if ((rc = dev_alloc(h, &q.Vg, (size_t)kNB * q.lv))) return rc;
+            if ((rc = dev_alloc(h, &q.Tg, (size_t)kNB * kLdr))) return rc;
+            if ((rc = dev_alloc(h, &q.Yp, (size_t)(maxlen / 64 + 2) * q.ycols * kNB))) return rc;
+            if ((rc = dev_alloc(h, &q.vec, (size_t)P.D + 3 * (size_t)P.m + P.dd + 8))) return rc;
+            if ((rc = dev_alloc(h, &q.Ld, (size_t)P.m))) return rc;
+            if ((rc = dev_alloc(h, &q.nf, 1))) return rc;
+            CU(cudaMemset(P.W, 0, wsz * sizeof(double)));
+            CU(cudaMemset(q.Vg, 0, (size_t)kNB * q.lv * sizeof(double)));
+            h->have_op = true;
+            return 0;
+        }
     }
     // launch geometry + per-CTA scratch
     CU(cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -345,7 +401,12 @@ int pnmol_b200_initialize(pnmol_b200_handle* h, const double* y0, double t0, dou
     a.y0 = y0; a.t0 = t0; a.prior_scale0 = diffuse_prior_scale;
     a.nugget = h->P.latent ? 1e-6 : 1e-10;  // latent.py:71,98 / white.py:33,51
     a.mean_out = mean_out; a.chol_out = chol_out; a.status = status;
-    k_init<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
+    if (h->large) {
+        void* args[] = {(void*)&h->P, (void*)&a, (void*)&h->q};
+        CU(cudaLaunchCooperativeKernel((const void*)k_init_large, dim3(h->grid), dim3(kThreads), args, h->smem_large, (cudaStream_t)stream));
+    } else {
+        k_init<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
+    }
     ++g_launches;
     CU(cudaGetLastError());
     return 0;
@@ -366,8 +427,7 @@ int pnmol_b200_step(pnmol_b200_handle* h, double t_new, double dt, const double*
     a.mean_a = const_cast<double*>(mean_in); a.chol_a = const_cast<double*>(chol_in);
     a.mean_b = mean_out; a.chol_b = chol_out;
     a.err_out = err_out; a.ref_out = ref_out; a.diff_last = diff_out; a.status = status;
-    k_run<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
-    ++g_launches;
+    if ((rc = launch_run(h, a, (cudaStream_t)stream))) return rc;
     CU(cudaGetLastError());
     return 0;
 }
@@ -387,8 +447,7 @@ int pnmol_b200_run(pnmol_b200_handle* h, double t0, const double* dts, const dou
     a.mean_a = mean; a.chol_a = chol; a.mean_b = mean_tmp; a.chol_b = chol_tmp;
     a.err_out = err_out; a.ref_out = ref_out; a.diff_last = diff_last; a.diff_sum = diff_sum;
     a.mean_traj = mean_traj; a.chol_traj = chol_traj; a.status = status;
-    k_run<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
-    ++g_launches;
+    if ((rc = launch_run(h, a, (cudaStream_t)stream))) return rc;
     CU(cudaGetLastError());
     return 0;
 }
@@ -405,6 +464,12 @@ int pnmol_b200_profile(pnmol_b200_handle* h, int enable, uint64_t* cycles_out) {
     if (h->P.prof) CU(cudaMemset(h->P.prof, 0, 24 * sizeof(uint64_t)));
     if (!enable) h->P.prof = nullptr;
     return 0;
+}
+
+int pnmol_b200_path(pnmol_b200_handle* h) {
+    if (!h) return fail(-1, "null handle");
+    if (!h->have_op) return fail(-1, "pnmol_b200_set_operator has not been called");
+    return h->large ? 1 : 0;
 }
 
 int pnmol_b200_rescale(pnmol_b200_handle* h, double* chol, const double* diff_sum, int nsteps, double* diff_cal_out,

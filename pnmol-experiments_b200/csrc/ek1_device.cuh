@@ -325,12 +325,14 @@ __device__ void evaluate_ode(const Problem& P, int b, const Smem& sm, double p0s
 // ---------------------------------------------------------------- predict stack
 // Columns m..m+D-1 of W: top D rows (A P^-1 Cl)^T, bottom D rows Ql^T.
 // white.py:104,118 / latent.py:179,194 and iwp.py:32-53, stacked_ssm.py:16-26.
+// (w0, nw): this warp's index and the number of warps sharing the loop (CTA-local by default; grid-wide on the
+// multi-CTA path, which synchronises with a grid barrier afterwards).
 __device__ void build_predict(const Problem& P, int b, const Smem& sm, const double* __restrict__ Cl,
-                              const int32_t* te, double* Wp) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                              const int32_t* te, double* Wp, int w0 = threadIdx.x >> 5, int nw = kWarps) {
+    const int lane = threadIdx.x & 31;
     const int n = P.n, D = P.D, nd = P.n * P.d;
     const double ps = P.priorscale ? P.priorscale[b] : 1.0;
-    for (int i = warp; i < D; i += kWarps) {
+    for (int i = w0; i < D; i += nw) {
         double* col = Wp + (size_t)i * P.ld;
         const int blk = i / n, ii = i - blk * n;
         double coef[kMaxN];
@@ -599,23 +601,12 @@ struct UpdateOut {
     bool scale_by_p;   // multiply by the Nordsieck preconditioner on output
 };
 
-__device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, EMode emode, double nugget,
-                             const double* __restrict__ Rsrc, const int32_t* te, const int32_t* be,
-                             const int32_t* Hcol, const double* Hval, double* W, const UpdateOut out,
-                             int* nonfinite, PhaseClock& pc) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int D = P.D, ld = P.ld, n = P.n;
-    const int nbot = emode == E_NONE ? 0 : mcur;
-    const int nrows = D + nbot;
-    // The right block always starts at column P.m of the workspace (where the predict QR
-    // left R); an update with fewer measurement rows (initialisation on y0) uses the
-    // columns P.m - mcur .. P.m - 1 for its left block.
-    double* Wl = W + (size_t)(P.m - mcur) * ld;
-    double* Wr = W + (size_t)P.m * ld;
-    const int ncols = mcur + D;
-
-    // right block: rows 0..k hold R (copied from Rsrc if given), the rest of the envelope is zero
-    for (int k = warp; k < D; k += kWarps) {
+// ---- part 1a: right block (rows 0..k hold R, copied from Rsrc if given; the rest of the envelope is zero)
+__device__ void update_build_right(const Problem& P, int mcur, int nrows, const double* __restrict__ Rsrc,
+                                   const int32_t* te, const int32_t* be, double* Wr, int w0, int nw) {
+    const int lane = threadIdx.x & 31;
+    const int D = P.D, ld = P.ld;
+    for (int k = w0; k < D; k += nw) {
         double* col = Wr + (size_t)k * ld;
         int tend = te ? te[mcur + k] : D - 1;
         if (tend > D - 1) tend = D - 1;
@@ -627,9 +618,15 @@ __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, 
         if (bend > nrows - 1) bend = nrows - 1;
         for (int i = D + lane; i <= bend; i += 32) col[i] = 0.0;
     }
-    __syncthreads();
-    // left block: top = R H^T (column r = sum over the sparse row r of H), bottom = E^T
-    for (int r = warp; r < mcur; r += kWarps) {
+}
+
+// ---- part 1b: left block: top = R H^T (column r = sum over the sparse row r of H), bottom = E^T
+__device__ void update_build_left(const Problem& P, int b, int mcur, int nrows, EMode emode, double nugget,
+                                  const int32_t* te, const int32_t* be, const int32_t* Hcol, const double* Hval,
+                                  double* Wl, const double* Wr, int w0, int nw) {
+    const int lane = threadIdx.x & 31;
+    const int D = P.D, ld = P.ld;
+    for (int r = w0; r < mcur; r += nw) {
         double* col = Wl + (size_t)r * ld;
         int tend = te ? te[r] : D - 1;
         if (tend > D - 1) tend = D - 1;
@@ -645,16 +642,14 @@ __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, 
         if (bend > nrows - 1) bend = nrows - 1;
         for (int i = D + lane; i <= bend; i += 32) col[i] = meas_sqrtm_entry(P, b, emode, nugget, r, i - D);
     }
-    __syncthreads();
+}
 
-    pc.mark(4);
-    Shape sh;
-    sh.nt = D; sh.nbot = nbot; sh.ncols = ncols; sh.te = te; sh.be = be;
-    householder_qr_blocked(Wl, ld, sh, sm.Vs, P.vld, sm.xraw, sm.sc, sm.Vr, sm.Ts, sm.Gs, qr_scratch(P, sm), sm.vbuf, sm.red, pc);
-    pc.mark(5);
-
-    // R1 = Wl[0:m, 0:m] (upper, column-major).  y = R1^-T z (for the mean),  x = R1^-1 z (quirk Q1,
-    // white.py:125 / latent.py:204).
+// ---- part 2 (one CTA): R1 = Wl[0:m, 0:m] (upper, column-major).  y = R1^-T z (for the mean),  x = R1^-1 z (quirk Q1,
+// white.py:125 / latent.py:204);  m_new = mp - R2^T y (white.py:123, sqrt.py:72) is left in sm.mp.  Returns the
+// local diffusion x.x / m.
+__device__ double update_solve(const Problem& P, const Smem& sm, int mcur, const double* Wl, const double* Wr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = P.D, ld = P.ld;
     double diff;
     if (P.ldm > 0 && mcur <= 96) {
         // stage R1 row-major in shared memory (odd leading dimension: conflict-free rows and columns), then
@@ -728,8 +723,6 @@ __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, 
         for (int r = tid; r < mcur; r += kThreads) part = fma(sm.xw[r], sm.xw[r], part);
         diff = block_sum(part, sm.red) / mcur;
     }
-    if (out.diff_out && tid == 0) *out.diff_out = diff;
-
     // m_new = mp - R2^T y   (white.py:123, sqrt.py:72)
     for (int k = warp; k < D; k += kWarps) {
         const double* col = Wr + (size_t)k * ld;
@@ -739,19 +732,32 @@ __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, 
         if (lane == 0) sm.mp[k] -= acc;
     }
     __syncthreads();
-    pc.mark(6);
+    return diff;
+}
+
+// ---- part 3a (one CTA): mean (n, dd) = P m_new reshaped (white.py:132-135).  Returns 1 on a non-finite value.
+__device__ int update_output_mean(const Problem& P, const Smem& sm, const UpdateOut& out, double diff) {
+    const int n = P.n, D = P.D;
     int bad = 0;
     if (!(diff == diff) || isinf(diff)) bad = 1;
-    // outputs: mean (n, dd) = P m_new reshaped (white.py:132-135); factor = P R3^T (white.py:132)
-    for (int k = tid; k < D; k += kThreads) {
+    for (int k = threadIdx.x; k < D; k += kThreads) {
         const int j = k / n, i = k - j * n;
         const double v = out.scale_by_p ? sm.pv[i] * sm.mp[k] : sm.mp[k];
         if (out.mean_out) out.mean_out[(size_t)i * P.dd + j] = v;
         if (out.ref_out && i == 0 && j < P.d) out.ref_out[j] = fabs(v);
         if (!isfinite(v)) bad = 1;
     }
-    for (int r = warp; r < D; r += kWarps) {
-        // row r of the factor = column m + r of R, rows m.. (R3[c][r] = W[(m + r) ld + m + c])
+    return bad;
+}
+
+// ---- part 3b: factor = P R3^T (white.py:132): row r of the factor = column m + r of R, rows m..
+// (R3[c][r] = W[(m + r) ld + m + c]).  Returns 1 on a non-finite value.
+__device__ int update_output_factor(const Problem& P, const Smem& sm, const UpdateOut& out, int mcur, int nrows,
+                                    const double* Wr, int w0, int nw) {
+    const int lane = threadIdx.x & 31;
+    const int n = P.n, D = P.D, ld = P.ld;
+    int bad = 0;
+    for (int r = w0; r < D; r += nw) {
         const double* col = Wr + (size_t)r * ld + mcur;
         const double pr = out.scale_by_p ? sm.pv[r % n] : 1.0;
         double* orow = out.chol_out + (size_t)r * D;
@@ -762,6 +768,40 @@ __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, 
             if (!isfinite(v)) bad = 1;
         }
     }
+    return bad;
+}
+
+__device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, EMode emode, double nugget,
+                             const double* __restrict__ Rsrc, const int32_t* te, const int32_t* be,
+                             const int32_t* Hcol, const double* Hval, double* W, const UpdateOut out,
+                             int* nonfinite, PhaseClock& pc) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int D = P.D, ld = P.ld;
+    const int nbot = emode == E_NONE ? 0 : mcur;
+    const int nrows = D + nbot;
+    // The right block always starts at column P.m of the workspace (where the predict QR
+    // left R); an update with fewer measurement rows (initialisation on y0) uses the
+    // columns P.m - mcur .. P.m - 1 for its left block.
+    double* Wl = W + (size_t)(P.m - mcur) * ld;
+    double* Wr = W + (size_t)P.m * ld;
+    const int ncols = mcur + D;
+
+    update_build_right(P, mcur, nrows, Rsrc, te, be, Wr, warp, kWarps);
+    __syncthreads();
+    update_build_left(P, b, mcur, nrows, emode, nugget, te, be, Hcol, Hval, Wl, Wr, warp, kWarps);
+    __syncthreads();
+
+    pc.mark(4);
+    Shape sh;
+    sh.nt = D; sh.nbot = nbot; sh.ncols = ncols; sh.te = te; sh.be = be;
+    householder_qr_blocked(Wl, ld, sh, sm.Vs, P.vld, sm.xraw, sm.sc, sm.Vr, sm.Ts, sm.Gs, qr_scratch(P, sm), sm.vbuf, sm.red, pc);
+    pc.mark(5);
+
+    const double diff = update_solve(P, sm, mcur, Wl, Wr);
+    if (out.diff_out && tid == 0) *out.diff_out = diff;
+    pc.mark(6);
+    int bad = update_output_mean(P, sm, out, diff);
+    bad |= update_output_factor(P, sm, out, mcur, nrows, Wr, warp, kWarps);
     if (bad) atomicOr(nonfinite, 1);
     __syncthreads();
     pc.mark(7);

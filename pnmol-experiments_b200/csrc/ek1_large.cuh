@@ -1,0 +1,276 @@
+// Multi-CTA EK1 kernels for large state dimension: the whole grid (cooperative launch, one CTA per SM) works on one
+// member at a time.  Same phases as ek1_step / k_init (ek1_kernels.cuh); the O(D^2) builds and read-outs are spread
+// over all warps of the grid, the two QRs run on householder_qr_large, the O(m^2) solves stay on CTA 0.  The vectors
+// the single-CTA path keeps in shared memory (mp, z, y, xw, xat) live in global scratch here (LargeQR::vec).
+#pragma once
+#include "ek1_kernels.cuh"
+#include "qr_large.cuh"
+
+namespace pnmol {
+
+__device__ __forceinline__ Smem large_vectors(const Problem& P, const LargeQR& q, const LargeSmem& ls) {
+    Smem sm;
+    double* base = q.vec;
+    sm.mp = base;   base += P.D;
+    sm.z = base;    base += P.m;
+    sm.y = base;    base += P.m;
+    sm.xw = base;   base += P.m;
+    sm.xat = base;
+    sm.vbuf = nullptr; sm.Vs = nullptr; sm.xraw = nullptr; sm.Vr = nullptr; sm.msq = nullptr;
+    sm.red = ls.red; sm.pv = ls.pv; sm.pinv = ls.pinv; sm.sc = ls.sc; sm.Ts = ls.Ts; sm.Gs = ls.Gs;
+    return sm;
+}
+
+// Error estimate (white.py:153-162) with the m x d / m x m assemblies spread over the grid and a right-looking
+// Cholesky whose trailing update is spread over the grid (the diagonal of L is kept apart in q.Ld so that no CTA
+// reads an entry another one overwrites in the same phase).  sigma and the read-out stay on CTA 0.
+__device__ void error_estimate_large(cg::grid_group& grid, const Problem& P, int b, const Smem& sm, const LargeQR& q,
+                                     double p1s, double dt, EMode emode, const int32_t* Hcol, const double* Hval,
+                                     double* F, double* S, double* err_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gw = blockIdx.x * kWarps + warp, gnw = gridDim.x * kWarps;
+    const int n = P.n, d = P.d, m = P.m;
+    const double ps = P.priorscale ? P.priorscale[b] : 1.0;
+    const double ps2 = ps * ps;
+    double q00 = 0, q01 = 0, q11 = 0;
+    for (int s = 0; s < n; ++s) {
+        q00 = fma(P.LQ1d[s], P.LQ1d[s], q00);
+        q01 = fma(P.LQ1d[s], P.LQ1d[n + s], q01);
+        q11 = fma(P.LQ1d[n + s], P.LQ1d[n + s], q11);
+    }
+    for (int r = gw; r < m; r += gnw) {  // F = At K  (m x d)
+        for (int k = lane; k < d; k += 32) {
+            double acc = 0.0;
+            for (int w = 0; w < P.wh; ++w) {
+                const int c = Hcol[(size_t)r * P.wh + w];
+                if (c >= 0 && (c % n) == 0 && c < n * d) acc = fma(Hval[(size_t)r * P.wh + w], ps2 * P.Kg[(size_t)(c / n) * d + k], acc);
+            }
+            F[(size_t)r * d + k] = acc;
+        }
+    }
+    grid.sync();
+    for (int r = gw; r < m; r += gnw) {  // S (m x m), row-major, full
+        for (int rp = lane; rp < m; rp += 32) {
+            double acc = 0.0;
+            for (int w = 0; w < P.wh; ++w) {
+                const int c = Hcol[(size_t)rp * P.wh + w];
+                if (c >= 0 && (c % n) == 0 && c < n * d) acc = fma(F[(size_t)r * d + c / n], Hval[(size_t)rp * P.wh + w], acc);
+            }
+            double val = q00 * acc;
+            double cross = 0.0;
+            if (rp < d) cross += F[(size_t)r * d + rp];
+            if (r < d) cross += F[(size_t)rp * d + r];
+            val += q01 * p1s * cross;
+            if (r < d && rp < d) val += q11 * p1s * p1s * ps2 * P.Kg[(size_t)r * d + rp];
+            S[(size_t)r * m + rp] = val + meas_cov_entry(P, b, emode, r, rp);
+        }
+    }
+    grid.sync();
+    if (blockIdx.x == 0)
+        for (int r = tid; r < m; r += kThreads) sm.y[r] = S[(size_t)r * m + r];  // diag(S) before factorisation
+    for (int k = 0; k < m; ++k) {
+        const double piv = sqrt(S[(size_t)k * m + k]);  // read-only in this phase and the next
+        if (blockIdx.x == 0 && tid == 0) q.Ld[k] = piv;
+        for (int r = k + 1 + blockIdx.x * kThreads + tid; r < m; r += gridDim.x * kThreads) S[(size_t)r * m + k] /= piv;
+        grid.sync();
+        for (int r = k + 1 + gw; r < m; r += gnw) {
+            const double lrk = S[(size_t)r * m + k];
+            for (int c = k + 1 + lane; c <= r; c += 32) S[(size_t)r * m + c] = fma(-lrk, S[(size_t)c * m + k], S[(size_t)r * m + c]);
+        }
+        grid.sync();
+    }
+    if (blockIdx.x == 0) {
+        // forward solve L u = z  (xw <- u), row-oriented dot form
+        for (int r = tid; r < m; r += kThreads) sm.xw[r] = sm.z[r];
+        __syncthreads();
+        for (int k = 0; k < m; ++k) {
+            if (warp == 0) {
+                double acc = 0.0;
+                for (int c = lane; c < k; c += 32) acc = fma(S[(size_t)k * m + c], sm.xw[c], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) sm.xw[k] = (sm.xw[k] - acc) / q.Ld[k];
+            }
+            __syncthreads();
+        }
+        double part = 0.0;
+        for (int r = tid; r < m; r += kThreads) part = fma(sm.xw[r], sm.xw[r], part);
+        const double sigma = sqrt(block_sum(part, sm.red) / m);
+        if (err_out)
+            for (int i = tid; i < d; i += kThreads) err_out[i] = dt * (sqrt(sm.y[i]) * sigma);
+        __syncthreads();
+    }
+}
+
+// update_stage (ek1_device.cuh) on the grid.  Ends with a grid barrier.
+__device__ void update_stage_large(cg::grid_group& grid, const Problem& P, int b, const Smem& sm, const LargeQR& q,
+                                   const LargeSmem& ls, int mcur, EMode emode, double nugget, const double* Rsrc,
+                                   const int32_t* te, const int32_t* be, const int32_t* Hcol, const double* Hval, double* W,
+                                   const UpdateOut out, double* diff_cta0) {
+    const int warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * kWarps + warp, gnw = gridDim.x * kWarps;
+    const int D = P.D, ld = P.ld;
+    const int nbot = emode == E_NONE ? 0 : mcur;
+    const int nrows = D + nbot;
+    double* Wl = W + (size_t)(P.m - mcur) * ld;
+    double* Wr = W + (size_t)P.m * ld;
+    update_build_right(P, mcur, nrows, Rsrc, te, be, Wr, gw, gnw);
+    grid.sync();
+    update_build_left(P, b, mcur, nrows, emode, nugget, te, be, Hcol, Hval, Wl, Wr, gw, gnw);
+    grid.sync();
+    Shape sh;
+    sh.nt = D; sh.nbot = nbot; sh.ncols = mcur + D; sh.te = te; sh.be = be;
+    householder_qr_large(grid, Wl, ld, sh, q, ls);
+    int bad = 0;
+    if (blockIdx.x == 0) {
+        const double diff = update_solve(P, sm, mcur, Wl, Wr);
+        if (threadIdx.x == 0) {
+            if (out.diff_out) *out.diff_out = diff;
+            if (diff_cta0) *diff_cta0 = diff;
+        }
+        bad = update_output_mean(P, sm, out, diff);
+    }
+    bad |= update_output_factor(P, sm, out, mcur, nrows, Wr, gw, gnw);
+    if (bad) atomicOr(q.nf, 1);
+    grid.sync();
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_run_large(const Problem P, const RunArgs a, const LargeQR q) {
+    extern __shared__ double smem_raw[];
+    cg::grid_group grid = cg::this_grid();
+    const LargeSmem ls = carve_large(smem_raw);
+    const Smem sm = large_vectors(P, q, ls);
+    __shared__ double diff_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int gw = blockIdx.x * kWarps + warp, gnw = gridDim.x * kWarps;
+    const size_t gtid = (size_t)blockIdx.x * kThreads + tid, gnt = (size_t)gridDim.x * kThreads;
+    const int n = P.n, D = P.D;
+    const size_t msz = (size_t)D, csz = (size_t)D * D;
+    double* W = P.W;
+    for (int b = 0; b < P.batch; ++b) {
+        if (blockIdx.x == 0 && tid == 0) *q.nf = 0;
+        double diffsum = 0.0;
+        for (int s = 0; s < a.nsteps; ++s) {
+            double dt;
+            __syncthreads();
+            if (a.nsteps == 1 && a.pv == nullptr) {
+                if (tid < n) { ls.pv[tid] = a.pv0[tid]; ls.pinv[tid] = a.pinv0[tid]; }
+                dt = a.dt0;
+            } else {
+                if (tid < n) { ls.pv[tid] = a.pv[(size_t)s * n + tid]; ls.pinv[tid] = a.pinv[(size_t)s * n + tid]; }
+                dt = a.dts[s];
+            }
+            __syncthreads();
+            const bool even = (s & 1) == 0;
+            const double* min_ = (even ? a.mean_a : a.mean_b) + b * msz;
+            const double* cin_ = (even ? a.chol_a : a.chol_b) + b * csz;
+            double* mout = (even ? a.mean_b : a.mean_a) + b * msz;
+            double* cout = (even ? a.chol_b : a.chol_a) + b * csz;
+            const int flags = s == 0 ? a.flags : (a.flags & ~1);
+            // [predict mean + linearisation] on CTA 0   white.py:104-113
+            if (blockIdx.x == 0) {
+                for (int k = tid; k < D; k += kThreads) {
+                    const int j = k / n, i = k - j * n;
+                    double acc = 0.0;
+                    for (int r = 0; r < n; ++r) acc = fma(P.A1d[i * n + r], ls.pinv[r] * min_[(size_t)r * P.dd + j], acc);
+                    sm.mp[k] = acc;
+                }
+                __syncthreads();
+                evaluate_ode(P, b, sm, ls.pv[0], ls.pv[1], P.Hcol, P.Hval);
+            }
+            const bool dense = flags & 1;
+            build_predict(P, b, sm, cin_, dense ? P.te_pd : P.te_p, W + (size_t)P.m * P.ld, gw, gnw);
+            grid.sync();
+            Shape sp;
+            sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p;
+            householder_qr_large(grid, W + (size_t)P.m * P.ld, P.ld, sp, q, ls);
+            if (!P.latent && !(flags & 2))
+                error_estimate_large(grid, P, b, sm, q, ls.pv[1], dt, E_STEP_WHITE, P.Hcol, P.Hval, P.F, P.S,
+                                     a.err_out ? a.err_out + (size_t)b * P.d : nullptr);
+            UpdateOut out;
+            out.mean_out = mout; out.chol_out = cout; out.diff_out = nullptr;
+            out.ref_out = (P.latent || !a.ref_out) ? nullptr : a.ref_out + (size_t)b * P.d; out.scale_by_p = true;
+            update_stage_large(grid, P, b, sm, q, ls, P.m, P.latent ? E_NONE : E_STEP_WHITE, 0.0, nullptr, P.te_u, P.be_u,
+                               P.Hcol, P.Hval, W, out, &diff_s);
+            if (blockIdx.x == 0) { __syncthreads(); diffsum += diff_s; }
+            if (a.mean_traj) {
+                double* mt = a.mean_traj + ((size_t)s * P.batch + b) * msz;
+                for (size_t k = gtid; k < msz; k += gnt) mt[k] = mout[k];
+            }
+            if (a.chol_traj) {
+                double* ct = a.chol_traj + ((size_t)s * P.batch + b) * csz;
+                for (size_t k = gtid; k < csz; k += gnt) ct[k] = cout[k];
+            }
+        }
+        if ((a.nsteps & 1) && !a.final_in_b) {  // result sits in b: bring it home
+            const double* ms = a.mean_b + b * msz; const double* cs = a.chol_b + b * csz;
+            double* md = a.mean_a + b * msz; double* cd = a.chol_a + b * csz;
+            for (size_t k = gtid; k < msz; k += gnt) md[k] = ms[k];
+            for (size_t k = gtid; k < csz; k += gnt) cd[k] = cs[k];
+        }
+        if (blockIdx.x == 0 && tid == 0) {
+            if (a.diff_last) a.diff_last[b] = diff_s;
+            if (a.diff_sum) a.diff_sum[b] = diffsum;
+            if (a.status) a.status[b] = *q.nf;
+        }
+        grid.sync();
+    }
+}
+
+// initialize() (white.py:12-80, latent.py:20-134) on the grid.
+__global__ void __launch_bounds__(kThreads, 1) k_init_large(const Problem P, const InitArgs a, const LargeQR q) {
+    extern __shared__ double smem_raw[];
+    cg::grid_group grid = cg::this_grid();
+    const LargeSmem ls = carve_large(smem_raw);
+    const Smem sm = large_vectors(P, q, ls);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gw = blockIdx.x * kWarps + warp, gnw = gridDim.x * kWarps;
+    const int n = P.n, d = P.d, D = P.D, nd = P.n * P.d;
+    double* W = P.W;
+    for (int b = 0; b < P.batch; ++b) {
+        if (blockIdx.x == 0 && tid == 0) *q.nf = 0;
+        double* chol = a.chol_out + (size_t)b * D * D;
+        double* mean = a.mean_out + (size_t)b * D;
+        const double ps = P.priorscale ? P.priorscale[b] : 1.0;
+        for (int r = gw; r < D; r += gnw) {  // C0 = kron(Lk, c0 I_n), latent: blockdiag(., kron(E_sqrtm, c0 I_n))
+            const int rb = r / n, ri = r - rb * n;
+            for (int c = lane; c < D; c += 32) {
+                const int cb = c / n, ci = c - cb * n;
+                double v = 0.0;
+                if (ri == ci && c <= r) {
+                    if (r < nd) {
+                        v = a.prior_scale0 * (ps * P.Lk[(size_t)rb * d + cb]);
+                    } else if (rb == cb) {
+                        const int comp = (rb - d) / P.npts;
+                        const double ds = P.diffscale ? P.diffscale[(size_t)b * P.ncomp + comp] : 1.0;
+                        v = a.prior_scale0 * (ds * P.Ediag[rb - d]);
+                    }
+                }
+                chol[(size_t)r * D + c] = v;
+            }
+        }
+        if (blockIdx.x == 0) {  // update on the initial condition: H = E0, z = -y0   white.py:32-39
+            for (int k = tid; k < D; k += kThreads) sm.mp[k] = 0.0;
+            for (int i = tid; i < d; i += kThreads) {
+                sm.z[i] = -a.y0[(size_t)b * d + i];
+                for (int w = 0; w < P.wh; ++w) { P.Hcol[(size_t)i * P.wh + w] = w == 0 ? i * n : -1; P.Hval[(size_t)i * P.wh + w] = w == 0 ? 1.0 : 0.0; }
+            }
+        }
+        __syncthreads();
+        if (tid < n) { ls.pv[tid] = 1.0; ls.pinv[tid] = 1.0; }
+        __syncthreads();
+        grid.sync();
+        UpdateOut o1;
+        o1.mean_out = nullptr; o1.chol_out = chol; o1.diff_out = nullptr; o1.ref_out = nullptr; o1.scale_by_p = false;
+        update_stage_large(grid, P, b, sm, q, ls, d, E_NUGGET_ONLY, a.nugget, chol, nullptr, nullptr, P.Hcol, P.Hval, W, o1, nullptr);
+        if (blockIdx.x == 0) evaluate_ode(P, b, sm, 1.0, 1.0, P.Hcol, P.Hval);  // white.py:42-48, latent.py:86-95
+        grid.sync();
+        UpdateOut o2;
+        o2.mean_out = mean; o2.chol_out = chol; o2.diff_out = nullptr; o2.ref_out = nullptr; o2.scale_by_p = false;
+        update_stage_large(grid, P, b, sm, q, ls, P.m, P.latent ? E_NUGGET_ONLY : E_STEP_PLUS_NUGGET, a.nugget, chol, nullptr,
+                           nullptr, P.Hcol, P.Hval, W, o2, nullptr);
+        if (blockIdx.x == 0 && tid == 0 && a.status) a.status[b] = *q.nf;
+        grid.sync();
+    }
+}
+
+}  // namespace pnmol

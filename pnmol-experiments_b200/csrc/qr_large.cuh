@@ -1,0 +1,384 @@
+// Multi-CTA blocked Householder QR for large state dimension (north-star kernel 2), sm_100a.
+//
+// Same mathematics, LAPACK dlarfg conventions and support envelopes as the single-CTA routines
+// (householder_columns / householder_qr_blocked); what changes is who does what.  The whole grid
+// (one CTA per SM, cooperative launch) works on ONE matrix that lives in the L2/HBM workspace:
+//
+//   per panel of kNB columns
+//     S1  CTA 0 factors the panel in shared memory (the panel's compact row list x kNB columns; when
+//         that does not fit, power-of-two sub-panels are factored in shared memory and applied to the
+//         rest of the panel from L2), writes R back, the reflectors V to global (Vg, reflector-major,
+//         compact row list) and the compact-WY T factor (dlarft, Gram matrix on the FP64 tensor pipe).
+//     --  grid barrier
+//     S2  every CTA takes (row chunk, 64-column group) items: stages the V chunk in shared memory and
+//         each warp forms the partial  Y^T = C^T V  of its 8 columns over the chunk's rows with
+//         mma.sync.m8n8k4.f64 (column data straight from global memory in the A-fragment layout);
+//         partials go to global memory (no atomics: the sum order is fixed, results are reproducible).
+//     --  grid barrier
+//     S3  same items: sum the partials, Y' = Y^T T (DMMA), C^T -= Y' V^T (DMMA) on the chunk's rows.
+//     --  grid barrier
+#pragma once
+#include <cooperative_groups.h>
+
+namespace pnmol {
+
+namespace cg = cooperative_groups;
+
+struct LargeQR {   // global scratch of the multi-CTA path (one set per handle)
+    double* Vg;    // [kNB][lv]  reflectors of the current panel
+    double* Tg;    // [kNB][kLdr] T factor of the current panel
+    double* Yp;    // [row chunk][ycols][kNB] partial Y^T
+    double* vec;   // mp | z | y | xw | xat  (the vectors the single-CTA path keeps in shared memory)
+    double* Ld;    // [m] diagonal of the Cholesky factor of S (error estimate)
+    int32_t* nf;   // non-finite flag of the member in flight
+    int lv, ycols, cap;  // cap: panel buffer capacity (doubles of shared memory)
+};
+
+struct LargeSmem {
+    double *red, *pv, *pinv, *sc, *Ts, *Gs, *scratch, *PB;
+};
+constexpr int kLargeFixed = 16 + 2 * kMaxN + 80 + 288 + 272 + kWarps * 192;
+
+__device__ __forceinline__ LargeSmem carve_large(double* base) {
+    LargeSmem s;
+    s.red = base;      base += 16;
+    s.pv = base;       base += kMaxN;
+    s.pinv = base;     base += kMaxN;
+    s.sc = base;       base += 80;
+    s.Ts = base;       base += 288;
+    s.Gs = base;       base += 272;
+    s.scratch = base;  base += kWarps * 192;
+    s.PB = base;
+    return s;
+}
+
+__device__ __forceinline__ int row_cidx(const RowMap& rm, int row) { return row < rm.a2 ? row - rm.j0 : rm.len1 + (row - rm.a2); }
+
+// Gram matrix of the panel's reflectors on the tensor pipe (upper triangle, Gs[k * 17 + i], k <= i), V(refl, c) =
+// V[refl * ldv + c] zero padded to a multiple of 8 rows; per-warp partial blocks are summed in a fixed order.
+__device__ void large_gram(const double* __restrict__ V, int ldv, int len, double* __restrict__ Gs, double* __restrict__ scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ntile = (len + 7) >> 3;
+    double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
+    double d00[2] = {0.0, 0.0}, d01[2] = {0.0, 0.0}, d11[2] = {0.0, 0.0};
+    for (int i = warp; i < ntile; i += kWarps) {
+        const double* v0 = V + (size_t)g * ldv + 8 * i + 2 * t;
+        const double* v1 = v0 + (size_t)8 * ldv;
+        const double a0 = v0[0], a1 = v1[0], b0 = v0[1], b1 = v1[1];
+        dmma884(c00[0], c00[1], a0, a0);
+        dmma884(c01[0], c01[1], a0, a1);
+        dmma884(c11[0], c11[1], a1, a1);
+        dmma884(d00[0], d00[1], b0, b0);
+        dmma884(d01[0], d01[1], b0, b1);
+        dmma884(d11[0], d11[1], b1, b1);
+    }
+    double* mine = scratch + warp * 192;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int e = g * 8 + 2 * t + q;
+        mine[e] = c00[q] + d00[q];
+        mine[64 + e] = c01[q] + d01[q];
+        mine[128 + e] = c11[q] + d11[q];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 192; e += kThreads) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) sum += scratch[w * 192 + e];
+        const int blk = e >> 6, r = (e & 63) >> 3, c = e & 7;
+        Gs[(r + (blk == 2 ? 8 : 0)) * 17 + c + (blk >= 1 ? 8 : 0)] = sum;
+    }
+    __syncthreads();
+}
+
+// S1: factor the panel (columns j0 .. j0+nbk-1) on one CTA.
+__device__ void large_panel_factor(double* __restrict__ W, int ld, const Shape& s, int j0, int nbk, const RowMap rm,
+                                   const LargeQR& q, const LargeSmem& ls) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = rm.len, lp = (L + 7) & ~7, nt = s.nt;
+    double* PB = ls.PB;
+    double* sc = ls.sc;
+    int sw = kNB;
+    while (sw > 1 && (size_t)sw * lp > (size_t)q.cap) sw >>= 1;
+    // reflector slots beyond the panel are zero
+    for (int idx = tid; idx < (kNB - nbk) * lp; idx += kThreads) q.Vg[(size_t)(nbk + idx / lp) * q.lv + idx % lp] = 0.0;
+    for (int i0 = 0; i0 < nbk; i0 += sw) {
+        const int ncs = nbk - i0 < sw ? nbk - i0 : sw;
+        // ---- load the sub-panel (entries outside a column's own envelope are zero)
+        for (int idx = tid; idx < ncs * lp; idx += kThreads) {
+            const int cc = idx / lp, c = idx - cc * lp;
+            const int j = j0 + i0 + cc;
+            double v = 0.0;
+            if (c < L) {
+                const int row = rm.row(c);
+                const bool ok = row < nt ? row <= env_top(s, j) : row <= env_bot(s, j);
+                if (ok) v = W[(size_t)j * ld + row];
+            }
+            PB[(size_t)cc * lp + c] = v;
+        }
+        __syncthreads();
+        // ---- factor it column by column
+        for (int cc = 0; cc < ncs; ++cc) {
+            const int i = i0 + cc;
+            const int cd = row_cidx(rm, j0 + i);
+            double* x = PB + (size_t)cc * lp;
+            double ss = 0.0;
+            for (int c = cd + 1 + tid; c < L; c += kThreads) ss = fma(x[c], x[c], ss);
+            ss = block_sum(ss, ls.red);
+            const double alpha = x[cd];
+            double tau = 0.0, beta = alpha, scale = 0.0;
+            if (ss != 0.0) {  // dlarfg: xnorm == 0 -> H = I
+                const double nrm = sqrt(fma(alpha, alpha, ss));
+                beta = -copysign(nrm, alpha);  // Fortran SIGN semantics of dlarfg
+                tau = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            __syncthreads();  // alpha has been read by everyone
+            if (tau != 0.0) {
+                for (int c = cd + 1 + tid; c < L; c += kThreads) x[c] *= scale;
+            }
+            if (tid == 0) { x[cd] = 1.0; sc[3 * i] = tau; sc[3 * i + 1] = beta; }
+            __syncthreads();
+            if (tau != 0.0) {
+                for (int k = cc + 1 + warp; k < ncs; k += kWarps) {
+                    double* y = PB + (size_t)k * lp;
+                    double d0 = 0.0, d1 = 0.0;
+                    int c = cd + lane;
+                    for (; c + 32 < L; c += 64) { d0 = fma(x[c], y[c], d0); d1 = fma(x[c + 32], y[c + 32], d1); }
+                    if (c < L) d0 = fma(x[c], y[c], d0);
+                    const double w = tau * warp_sum(d0 + d1);
+                    for (int c2 = cd + lane; c2 < L; c2 += 32) y[c2] = fma(-w, x[c2], y[c2]);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- write R back, export V (the buffer keeps the pure reflectors: zero above the unit diagonal)
+        for (int idx = tid; idx < ncs * lp; idx += kThreads) {
+            const int cc = idx / lp, c = idx - cc * lp;
+            const int i = i0 + cc, j = j0 + i;
+            const int cd = row_cidx(rm, j);
+            const double tau = sc[3 * i];
+            const double xv = PB[(size_t)cc * lp + c];
+            if (c < L) {
+                const int row = rm.row(c);
+                const bool ok = row < nt ? row <= env_top(s, j) : row <= env_bot(s, j);
+                if (ok) W[(size_t)j * ld + row] = c < cd ? xv : (c == cd ? sc[3 * i + 1] : 0.0);
+            }
+            const double vv = (tau != 0.0 && c >= cd && c < L) ? xv : 0.0;
+            PB[(size_t)cc * lp + c] = vv;
+            q.Vg[(size_t)i * q.lv + c] = vv;
+        }
+        __syncthreads();
+        // ---- apply the sub-panel's reflectors to the rest of the panel (streamed from L2), one warp per column
+        if (i0 + ncs < nbk) {
+            for (int k = j0 + i0 + ncs + warp; k < j0 + nbk; k += kWarps) {
+                double* col = W + (size_t)k * ld;
+                for (int cc = 0; cc < ncs; ++cc) {
+                    const double tau = sc[3 * (i0 + cc)];
+                    if (tau == 0.0) continue;
+                    const double* v = PB + (size_t)cc * lp;
+                    const int cd = row_cidx(rm, j0 + i0 + cc);
+                    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+                    int c = cd + lane;
+                    for (; c + 96 < L; c += 128) {
+                        const double a0 = col[rm.row(c)], a1 = col[rm.row(c + 32)], a2 = col[rm.row(c + 64)], a3 = col[rm.row(c + 96)];
+                        d0 = fma(v[c], a0, d0); d1 = fma(v[c + 32], a1, d1); d2 = fma(v[c + 64], a2, d2); d3 = fma(v[c + 96], a3, d3);
+                    }
+                    for (; c < L; c += 32) d0 = fma(v[c], col[rm.row(c)], d0);
+                    const double w = tau * warp_sum((d0 + d1) + (d2 + d3));
+                    c = cd + lane;
+                    for (; c + 96 < L; c += 128) {
+                        const int r0 = rm.row(c), r1 = rm.row(c + 32), r2 = rm.row(c + 64), r3 = rm.row(c + 96);
+                        const double a0 = col[r0], a1 = col[r1], a2 = col[r2], a3 = col[r3];
+                        col[r0] = fma(-w, v[c], a0); col[r1] = fma(-w, v[c + 32], a1);
+                        col[r2] = fma(-w, v[c + 64], a2); col[r3] = fma(-w, v[c + 96], a3);
+                    }
+                    for (; c < L; c += 32) { const int r0 = rm.row(c); col[r0] = fma(-w, v[c], col[r0]); }
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- T factor
+    __threadfence_block();
+    large_gram(sw == kNB ? PB : q.Vg, sw == kNB ? lp : q.lv, L, ls.Gs, ls.scratch);
+    if (warp == 0) panel_t_factor(ls.Gs, sc, nbk, ls.Ts);
+    __syncthreads();
+    for (int idx = tid; idx < kNB * kLdr; idx += kThreads) q.Tg[idx] = ls.Ts[idx];
+}
+
+// S2: partial Y^T = C^T V per (row chunk, column group) item.
+__device__ void large_trailing_y(const double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
+                                 const LargeQR& q, int RC, double* __restrict__ Vr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int first = j0 + nbk, ntrail = ncols - first, L = rm.len;
+    const int ncg = (ntrail + 63) >> 6, nrc = (L + RC - 1) / RC;
+    for (int it = blockIdx.x; it < nrc * ncg; it += gridDim.x) {
+        const int rcx = it / ncg, cgx = it - rcx * ncg;
+        const int c0 = rcx * RC;
+        const int rows = L - c0 < RC ? L - c0 : RC;
+        const int nt8 = (rows + 7) >> 3;
+        __syncthreads();
+        for (int idx = tid; idx < kNB * 8 * nt8; idx += kThreads) {
+            const int refl = idx / (8 * nt8), cl = idx - refl * (8 * nt8);
+            Vr[cl * kLdr + refl] = cl < rows ? q.Vg[(size_t)refl * q.lv + c0 + cl] : 0.0;
+        }
+        __syncthreads();
+        const int cbase = (cgx * 8 + warp) * 8;
+        if (cbase >= ntrail) continue;
+        const int cidx = cbase + g;
+        const bool have = cidx < ntrail;
+        const double* cp = W + (size_t)(first + (have ? cidx : cbase)) * ld;
+        double y[2][2][2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int n = 0; n < 2; ++n) { y[e][n][0] = 0.0; y[e][n][1] = 0.0; }
+        for (int i0 = 0; i0 < nt8; i0 += kCh) {
+            double xa[kCh][2];
+#pragma unroll
+            for (int a = 0; a < kCh; ++a) {
+                const int cl = 8 * (i0 + a) + 2 * t;
+                xa[a][0] = (have && cl < rows) ? cp[rm.row(c0 + cl)] : 0.0;
+                xa[a][1] = (have && cl + 1 < rows) ? cp[rm.row(c0 + cl + 1)] : 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < kCh; ++a) {
+                if (i0 + a < nt8) {
+                    const double* v0 = Vr + (8 * (i0 + a) + 2 * t) * kLdr + g;
+                    dmma884(y[0][0][0], y[0][0][1], xa[a][0], v0[0]);
+                    dmma884(y[0][1][0], y[0][1][1], xa[a][0], v0[8]);
+                    dmma884(y[1][0][0], y[1][0][1], xa[a][1], v0[kLdr]);
+                    dmma884(y[1][1][0], y[1][1][1], xa[a][1], v0[kLdr + 8]);
+                }
+            }
+        }
+        if (have) {
+            double* yp = q.Yp + ((size_t)rcx * q.ycols + cidx) * kNB;
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                yp[8 * n + 2 * t] = y[0][n][0] + y[1][n][0];
+                yp[8 * n + 2 * t + 1] = y[0][n][1] + y[1][n][1];
+            }
+        }
+    }
+}
+
+// S3: C^T -= (Y^T T) V^T on the rows of each item's chunk.
+__device__ void large_trailing_u(double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
+                                 const LargeQR& q, int RC, double* __restrict__ Vs, double* __restrict__ Ts) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int first = j0 + nbk, ntrail = ncols - first, L = rm.len;
+    const int ncg = (ntrail + 63) >> 6, nrc = (L + RC - 1) / RC;
+    const int ldt = RC + 2;
+    __syncthreads();
+    for (int idx = tid; idx < kNB * kLdr; idx += kThreads) Ts[idx] = q.Tg[idx];
+    __syncthreads();
+    double tf[2][2][2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int sx = 0; sx < 2; ++sx)
+#pragma unroll
+            for (int n = 0; n < 2; ++n) tf[h][sx][n] = Ts[(8 * h + 2 * t + sx) * kLdr + g + 8 * n];
+    for (int it = blockIdx.x; it < nrc * ncg; it += gridDim.x) {
+        const int rcx = it / ncg, cgx = it - rcx * ncg;
+        const int c0 = rcx * RC;
+        const int rows = L - c0 < RC ? L - c0 : RC;
+        const int nt8 = (rows + 7) >> 3;
+        __syncthreads();
+        for (int idx = tid; idx < kNB * 8 * nt8; idx += kThreads) {
+            const int refl = idx / (8 * nt8), cl = idx - refl * (8 * nt8);
+            Vs[refl * ldt + cl] = cl < rows ? q.Vg[(size_t)refl * q.lv + c0 + cl] : 0.0;
+        }
+        __syncthreads();
+        const int cbase = (cgx * 8 + warp) * 8;
+        if (cbase >= ntrail) continue;
+        const int cidx = cbase + g;
+        const bool have = cidx < ntrail;
+        double* cp = W + (size_t)(first + (have ? cidx : cbase)) * ld;
+        double yt[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // Y^T[col g][reflectors 8n + 2t, 8n + 2t + 1]
+        if (have) {
+            for (int r = 0; r < nrc; ++r) {
+                const double* yp = q.Yp + ((size_t)r * q.ycols + cidx) * kNB;
+#pragma unroll
+                for (int n = 0; n < 2; ++n) { yt[n][0] += yp[8 * n + 2 * t]; yt[n][1] += yp[8 * n + 2 * t + 1]; }
+            }
+        }
+        double z[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int sx = 0; sx < 2; ++sx)
+#pragma unroll
+                for (int n = 0; n < 2; ++n) dmma884(z[n][0], z[n][1], yt[h][sx], tf[h][sx][n]);
+#pragma unroll
+        for (int n = 0; n < 2; ++n) { z[n][0] = -z[n][0]; z[n][1] = -z[n][1]; }
+        for (int i0 = 0; i0 < nt8; i0 += kCh) {
+            double xa[kCh][2];
+#pragma unroll
+            for (int a = 0; a < kCh; ++a) {
+                const int cl = 8 * (i0 + a) + 2 * t;
+                xa[a][0] = (have && cl < rows) ? cp[rm.row(c0 + cl)] : 0.0;
+                xa[a][1] = (have && cl + 1 < rows) ? cp[rm.row(c0 + cl + 1)] : 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < kCh; ++a) {
+                if (i0 + a < nt8) {
+                    const double* vb = Vs + 8 * (i0 + a) + g;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int sx = 0; sx < 2; ++sx) dmma884(xa[a][0], xa[a][1], z[h][sx], vb[(8 * h + 2 * t + sx) * ldt]);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < kCh; ++a) {
+                const int cl = 8 * (i0 + a) + 2 * t;
+                if (have && cl < rows) cp[rm.row(c0 + cl)] = xa[a][0];
+                if (have && cl + 1 < rows) cp[rm.row(c0 + cl + 1)] = xa[a][1];
+            }
+        }
+    }
+}
+
+// Rows per chunk of the trailing phases: about two items per CTA, chunks of 64 .. 1024 rows (multiple of 8).
+__device__ __forceinline__ int large_chunk_rows(int L, int ntrail, int cap) {
+    const int ncg = (ntrail + 63) >> 6;
+    int want = (2 * (int)gridDim.x + ncg - 1) / ncg;
+    if (want < 1) want = 1;
+    int RC = (L + want - 1) / want;
+    RC = (RC + 7) & ~7;
+    if (RC < 64) RC = 64;
+    int rcmax = 1024;
+    while (rcmax > 64 && (size_t)rcmax * kLdr > (size_t)cap) rcmax >>= 1;
+    if (RC > rcmax) RC = rcmax;
+    return RC;
+}
+
+// Grid-wide blocked QR.  On return (after a grid barrier) the upper triangle holds R.
+__device__ void householder_qr_large(cg::grid_group& grid, double* __restrict__ W, int ld, const Shape s, const LargeQR& q,
+                                     const LargeSmem& ls) {
+    const int nrows = s.nt + s.nbot;
+    const int nref = nrows < s.ncols ? nrows : s.ncols;
+    for (int j0 = 0; j0 < nref; j0 += kNB) {
+        const int nbk = nref - j0 < kNB ? nref - j0 : kNB;
+        const RowMap rm = panel_rows(s, j0, j0 + nbk - 1);
+        if (blockIdx.x == 0) large_panel_factor(W, ld, s, j0, nbk, rm, q, ls);
+        grid.sync();
+        const int ntrail = s.ncols - (j0 + nbk);
+        if (ntrail > 0) {
+            const int RC = large_chunk_rows(rm.len, ntrail, q.cap);
+            large_trailing_y(W, ld, s.ncols, j0, nbk, rm, q, RC, ls.PB);
+            grid.sync();
+            large_trailing_u(W, ld, s.ncols, j0, nbk, rm, q, RC, ls.PB, ls.Ts);
+            grid.sync();
+        }
+    }
+}
+
+}  // namespace pnmol

@@ -112,6 +112,14 @@ class Engine:
             except Exception:
                 pass
 
+    @property
+    def path(self):
+        """"single_cta" (one CTA per member, ensembles) or "multi_cta" (whole grid per member, large state dimension)."""
+        rc = self.lib.pnmol_b200_path(self.h)
+        if rc < 0:
+            _lib.check(rc)
+        return "multi_cta" if rc == 1 else "single_cta"
+
     # ------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=torch.float64):
         return torch.empty(shape, dtype=dtype, device=self.device)

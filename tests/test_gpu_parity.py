@@ -83,6 +83,28 @@ def test_update_sqrt(m, D, noise):
 @pytest.mark.parametrize("name,kind,bcond,num", KIND_CASES)
 def test_initialize_and_steps_from_oracle_state(name, kind, bcond, num):
     """Every step starts from the oracle's state: pure per-step parity (no error accumulation)."""
+    _check_initialize_and_steps(name, kind, bcond, num, "single_cta")
+
+
+LARGE_CASES = [("heat", "white_linear", "dirichlet", 6, 0), ("heat", "white_linear", "neumann", 50, 0),
+               ("heat", "white_linear", "dirichlet", 50, 1280), ("heat", "latent_linear", "neumann", 6, 0),
+               ("spruce", "latent_semilinear", "dirichlet", 24, 1280), ("sir", "white_semilinear", "neumann", 17, 0),
+               ("sir", "white_semilinear", "neumann", 17, 1280), ("lv", "white_semilinear", "neumann", 6, 0)]
+
+
+@pytest.mark.parametrize("name,kind,bcond,num,cap", LARGE_CASES)
+def test_multi_cta_path_initialize_and_steps(name, kind, bcond, num, cap, monkeypatch):
+    """The large-state kernels (whole grid per member, multi-CTA blocked QR with DMMA trailing updates) forced onto
+    small problems: same per-step parity as the single-CTA path.  A reduced panel-buffer capacity (cap doubles of
+    shared memory) makes the panel factorisation run in sub-panels that are applied to the rest of the panel from L2,
+    as it does for BASELINE config C4."""
+    monkeypatch.setenv("PNMOL_B200_FORCE_LARGE", "1")
+    if cap:
+        monkeypatch.setenv("PNMOL_B200_LARGE_CAP", str(cap))
+    _check_initialize_and_steps(name, kind, bcond, num, "multi_cta")
+
+
+def _check_initialize_and_steps(name, kind, bcond, num, path):
     from pnmol_b200 import pdefilter
     from pnmol_b200.base import rv
 
@@ -92,6 +114,7 @@ def test_initialize_and_steps_from_oracle_state(name, kind, bcond, num):
     init, stepf, semil = ek1_np.KINDS[kind]
     st = init(case["opde"], case["nu"], case["gram_sqrtm"], 1.0, semil)
     s0 = solver.initialize(case["pde"])
+    assert solver._engine.path == path
     assert s0.t == case["pde"].t0 and s0.error_estimate is None and s0.diffusion_squared_local == []
     assert cases.cov_excess(_np(s0.y.cov_sqrtm), st.cov_sqrtm, n) < 1
     # Some initial means are ill-conditioned in the reference itself (latent + Neumann with an initial condition
@@ -212,7 +235,7 @@ def test_dense_input_factor_and_adaptive_steps():
 def test_baseline_configs_c2_c3_full_size(name, kind, bcond, num, dt):
     """BASELINE.json configs 2 and 3 at full size (SIR N=100: D=900, m=306; spruce N=200 latent: D=1200, m=202),
     with the prior kernels of SURVEY section 8(d): initialisation and two steps, each from the oracle's state.  These
-    sizes exceed the register-resident panels (row lists > 512), so they also cover the column-by-column fallback."""
+    sizes do not fit the single-CTA kernels and run on the multi-CTA path (ek1_large.cuh)."""
     import time
 
     from pnmol_b200 import pdefilter
@@ -227,6 +250,7 @@ def test_baseline_configs_c2_c3_full_size(name, kind, bcond, num, dt):
     s0 = solver.initialize(case["pde"])
     torch.cuda.synchronize()
     t_init = time.perf_counter() - t0
+    assert solver._engine.path == "multi_cta"
     assert cases.cov_excess(_np(s0.y.cov_sqrtm), st.cov_sqrtm, n) < 1
     assert cases.mean_excess(_np(s0.y.mean), st.mean, spread=st_eps.mean) < 1
     dev = s0.y.mean.device
@@ -241,13 +265,12 @@ def test_baseline_configs_c2_c3_full_size(name, kind, bcond, num, dt):
         st = stepf(case["opde"], st, dt, case["nu"], case["gram_sqrtm"], semil)
         assert cases.mean_excess(_np(new.y.mean), st.mean) < 1
         assert cases.cov_excess(_np(new.y.cov_sqrtm), st.cov_sqrtm, n) < 1
-    print(f"[{name} N={num} D={st.cov_sqrtm.shape[0]}] initialize {t_init:.2f} s, step {t_step:.2f} s (single CTA path)")
+    print(f"[{name} N={num} D={st.cov_sqrtm.shape[0]}] initialize {t_init:.3f} s, step {t_step:.3f} s (multi-CTA path)")
 
 
-@pytest.mark.skipif(not os.environ.get("PNMOL_B200_SLOW"), reason="minutes on the single-CTA path; set PNMOL_B200_SLOW=1")
+@pytest.mark.skipif(not os.environ.get("PNMOL_B200_SLOW"), reason="the NumPy oracle needs ~1 min of host time at D=3072; set PNMOL_B200_SLOW=1")
 def test_baseline_config_c4_full_size():
-    """BASELINE.json config 4 (heat N=1024: D=3072, m=1026): one step from the oracle's state.  Until the multi-CTA
-    large-D kernel exists this runs on one CTA (column-by-column path) and takes minutes -- opt-in."""
+    """BASELINE.json config 4 (heat N=1024: D=3072, m=1026): one step from the oracle's state (multi-CTA path)."""
     import time
 
     from pnmol_b200 import pdefilter
@@ -266,7 +289,8 @@ def test_baseline_config_c4_full_size():
     ref = ek1_np.white_step(case["opde"], st, case["dt"], 2, case["gram_sqrtm"])
     assert cases.mean_excess(_np(new.y.mean), ref.mean) < 1
     assert cases.cov_excess(_np(new.y.cov_sqrtm), ref.cov_sqrtm, 3) < 1
-    print(f"[heat N=1024 D=3072] step {t_step:.1f} s (single CTA path)")
+    assert solver._engine.path == "multi_cta"
+    print(f"[heat N=1024 D=3072] step {t_step:.3f} s (multi-CTA path)")
 
 
 # ------------------------------------------------------------------------- ensembles
