@@ -293,7 +293,10 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
         P.ldm = P.m <= 96 ? (P.m | 1) : 0;  // odd leading dimension: conflict-free rows and columns
         h->smem_bytes = smem_doubles(P.D, P.m, P.dd, P.vld, P.ldm) * sizeof(double);
         const char* force = std::getenv("PNMOL_B200_FORCE_LARGE");
-        h->large = h->smem_bytes > h->smem_optin || (force && std::atoi(force) != 0);
+        // auto: the single-CTA kernels need their shared memory to fit and are only fast while every panel's row list
+        // fits the register-resident panels (<= 32 * kRPL rows); beyond that the whole grid works on one member
+        h->large = h->smem_bytes > h->smem_optin || maxlen > 32 * kRPL;
+        if (force && h->smem_bytes <= h->smem_optin) h->large = std::atoi(force) != 0;
         if (h->large) {
             // one member at a time on the whole grid: one workspace, vectors in global scratch
             LargeQR& q = h->q;

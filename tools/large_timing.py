@@ -10,7 +10,7 @@ CONFIGS = {"c2": ("sir", "white_semilinear", "neumann", 100, 2.0 ** -3, "matern"
            "c3": ("spruce", "latent_semilinear", "dirichlet", 200, 2.0 ** -4, "se"),
            "c4": ("heat", "white_linear", "dirichlet", 1024, 2.0 ** -4, "se"),
            "c1": ("heat", "white_linear", "dirichlet", 50, 2.0 ** -4, "se")}
-args = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c2", "c3"]
+args = [a for a in sys.argv[1:] if a in CONFIGS] or ["c2", "c3"]
 steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 4
 for name in args:
     pname, kind, bcond, num, dt, prior = CONFIGS[name]
