@@ -304,7 +304,8 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
             if (const char* e = std::getenv("PNMOL_B200_LARGE_CAP")) cap = std::max(1280, std::min(cap, std::atoi(e)));  // >= one 64-row V chunk (64 x kLdr)
             cap &= ~15;
             const int lp = (maxlen + 7) & ~7;
-            if (lp > cap) return fail(-1, "state dimension too large: one panel column does not fit in shared memory");
+            if (lp > cap || (size_t)P.m * 17 > (size_t)cap)
+                return fail(-1, "state dimension too large: one panel column does not fit in shared memory");
             q.cap = cap;
             q.lv = lp + 8;
             q.ycols = P.m + P.D;

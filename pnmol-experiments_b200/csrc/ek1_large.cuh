@@ -25,7 +25,7 @@ __device__ __forceinline__ Smem large_vectors(const Problem& P, const LargeQR& q
 // Cholesky whose trailing update is spread over the grid (the diagonal of L is kept apart in q.Ld so that no CTA
 // reads an entry another one overwrites in the same phase).  sigma and the read-out stay on CTA 0.
 __device__ void error_estimate_large(cg::grid_group& grid, const Problem& P, int b, const Smem& sm, const LargeQR& q,
-                                     double p1s, double dt, EMode emode, const int32_t* Hcol, const double* Hval,
+                                     const LargeSmem& ls, double p1s, double dt, EMode emode, const int32_t* Hcol, const double* Hval,
                                      double* F, double* S, double* err_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gw = blockIdx.x * kWarps + warp, gnw = gridDim.x * kWarps;
@@ -68,14 +68,62 @@ __device__ void error_estimate_large(cg::grid_group& grid, const Problem& P, int
     grid.sync();
     if (blockIdx.x == 0)
         for (int r = tid; r < m; r += kThreads) sm.y[r] = S[(size_t)r * m + r];  // diag(S) before factorisation
-    for (int k = 0; k < m; ++k) {
-        const double piv = sqrt(S[(size_t)k * m + k]);  // read-only in this phase and the next
-        if (blockIdx.x == 0 && tid == 0) q.Ld[k] = piv;
-        for (int r = k + 1 + blockIdx.x * kThreads + tid; r < m; r += gridDim.x * kThreads) S[(size_t)r * m + k] /= piv;
+    // Right-looking blocked Cholesky of the lower triangle (row-major), panels of kCB columns staged in shared memory
+    // (leading dimension kCB + 1): CTA 0 factors the (m - k0) x kCB panel there and writes L back (its diagonal also to
+    // q.Ld), then every CTA stages the panel and applies the rank-kCB update to its share of the rows below.
+    constexpr int kCB = 16, kCL = kCB + 1;
+    double* Lp = ls.PB;
+    for (int k0 = 0; k0 < m; k0 += kCB) {
+        const int kb = m - k0 < kCB ? m - k0 : kCB;
+        const int pr = m - k0;  // panel rows
+        if (blockIdx.x == 0) {
+            for (int idx = tid; idx < pr * kCB; idx += kThreads) {
+                const int r = idx / kCB, kk = idx - r * kCB;
+                Lp[r * kCL + kk] = (kk < kb && kk <= r) ? S[(size_t)(k0 + r) * m + k0 + kk] : 0.0;
+            }
+            __syncthreads();
+            for (int kk = 0; kk < kb; ++kk) {
+                const double piv = sqrt(Lp[kk * kCL + kk]);
+                const double rinv = 1.0 / piv;
+                __syncthreads();
+                for (int r = kk + tid; r < pr; r += kThreads) Lp[r * kCL + kk] = r == kk ? piv : Lp[r * kCL + kk] * rinv;
+                __syncthreads();
+                const int rem = kb - kk - 1;  // S[r][c] -= L[r][kk] L[c][kk],  c in (kk, kb), r >= c
+                for (int idx = tid; idx < (pr - kk - 1) * rem; idx += kThreads) {
+                    const int r = kk + 1 + idx / rem, c = kk + 1 + idx % rem;
+                    if (c <= r) Lp[r * kCL + c] = fma(-Lp[r * kCL + kk], Lp[c * kCL + kk], Lp[r * kCL + c]);
+                }
+                __syncthreads();
+            }
+            for (int idx = tid; idx < pr * kCB; idx += kThreads) {
+                const int r = idx / kCB, kk = idx - r * kCB;
+                if (kk < kb && kk <= r) S[(size_t)(k0 + r) * m + k0 + kk] = Lp[r * kCL + kk];
+            }
+            if (tid < kb) q.Ld[k0 + tid] = Lp[tid * kCL + tid];
+        }
         grid.sync();
-        for (int r = k + 1 + gw; r < m; r += gnw) {
-            const double lrk = S[(size_t)r * m + k];
-            for (int c = k + 1 + lane; c <= r; c += 32) S[(size_t)r * m + c] = fma(-lrk, S[(size_t)c * m + k], S[(size_t)r * m + c]);
+        const int c0 = k0 + kb;
+        if (c0 < m) {
+            const int tr = m - c0;  // rows below the panel
+            if (blockIdx.x != 0) {  // (CTA 0 still holds the panel: rows c0.. start at local row kb)
+                for (int idx = tid; idx < tr * kCB; idx += kThreads) {
+                    const int r = idx / kCB, kk = idx - r * kCB;
+                    Lp[(kb + r) * kCL + kk] = kk < kb ? S[(size_t)(c0 + r) * m + k0 + kk] : 0.0;
+                }
+            }
+            __syncthreads();
+            for (int r = c0 + gw; r < m; r += gnw) {  // S[r][c] -= sum_k L[r][k] L[c][k],  c0 <= c <= r
+                double lr[kCB];
+#pragma unroll
+                for (int kk = 0; kk < kCB; ++kk) lr[kk] = kk < kb ? Lp[(r - k0) * kCL + kk] : 0.0;
+                for (int c = c0 + lane; c <= r; c += 32) {
+                    const double* lc = Lp + (c - k0) * kCL;
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < kCB; kk += 2) { a0 = fma(lr[kk], lc[kk], a0); a1 = fma(lr[kk + 1], lc[kk + 1], a1); }
+                    S[(size_t)r * m + c] -= a0 + a1;
+                }
+            }
         }
         grid.sync();
     }
@@ -105,7 +153,7 @@ __device__ void error_estimate_large(cg::grid_group& grid, const Problem& P, int
 __device__ void update_stage_large(cg::grid_group& grid, const Problem& P, int b, const Smem& sm, const LargeQR& q,
                                    const LargeSmem& ls, int mcur, EMode emode, double nugget, const double* Rsrc,
                                    const int32_t* te, const int32_t* be, const int32_t* Hcol, const double* Hval, double* W,
-                                   const UpdateOut out, double* diff_cta0) {
+                                   const UpdateOut out, double* diff_cta0, PhaseClock& pc) {
     const int warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kWarps + warp, gnw = gridDim.x * kWarps;
     const int D = P.D, ld = P.ld;
@@ -119,7 +167,8 @@ __device__ void update_stage_large(cg::grid_group& grid, const Problem& P, int b
     grid.sync();
     Shape sh;
     sh.nt = D; sh.nbot = nbot; sh.ncols = mcur + D; sh.te = te; sh.be = be;
-    householder_qr_large(grid, Wl, ld, sh, q, ls);
+    pc.mark(4);
+    householder_qr_large(grid, Wl, ld, sh, q, ls, pc);
     int bad = 0;
     if (blockIdx.x == 0) {
         const double diff = update_solve(P, sm, mcur, Wl, Wr);
@@ -129,9 +178,11 @@ __device__ void update_stage_large(cg::grid_group& grid, const Problem& P, int b
         }
         bad = update_output_mean(P, sm, out, diff);
     }
+    pc.mark(6);
     bad |= update_output_factor(P, sm, out, mcur, nrows, Wr, gw, gnw);
     if (bad) atomicOr(q.nf, 1);
     grid.sync();
+    pc.mark(7);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_run_large(const Problem P, const RunArgs a, const LargeQR q) {
@@ -146,6 +197,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_run_large(const Problem P, cons
     const int n = P.n, D = P.D;
     const size_t msz = (size_t)D, csz = (size_t)D * D;
     double* W = P.W;
+    PhaseClock pc;  // phase cycles as seen by CTA 0 (pnmol_b200_profile); indices as in ek1_step, 8..13 = QR: panel
+    pc.start(blockIdx.x == 0 ? P.prof : nullptr);  // factor, barrier, partial Y, barrier, update, barrier
     for (int b = 0; b < P.batch; ++b) {
         if (blockIdx.x == 0 && tid == 0) *q.nf = 0;
         double diffsum = 0.0;
@@ -178,19 +231,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_run_large(const Problem P, cons
                 evaluate_ode(P, b, sm, ls.pv[0], ls.pv[1], P.Hcol, P.Hval);
             }
             const bool dense = flags & 1;
+            pc.mark(0);
             build_predict(P, b, sm, cin_, dense ? P.te_pd : P.te_p, W + (size_t)P.m * P.ld, gw, gnw);
             grid.sync();
+            pc.mark(1);
             Shape sp;
             sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p;
-            householder_qr_large(grid, W + (size_t)P.m * P.ld, P.ld, sp, q, ls);
+            householder_qr_large(grid, W + (size_t)P.m * P.ld, P.ld, sp, q, ls, pc);
             if (!P.latent && !(flags & 2))
-                error_estimate_large(grid, P, b, sm, q, ls.pv[1], dt, E_STEP_WHITE, P.Hcol, P.Hval, P.F, P.S,
+                error_estimate_large(grid, P, b, sm, q, ls, ls.pv[1], dt, E_STEP_WHITE, P.Hcol, P.Hval, P.F, P.S,
                                      a.err_out ? a.err_out + (size_t)b * P.d : nullptr);
+            pc.mark(3);
             UpdateOut out;
             out.mean_out = mout; out.chol_out = cout; out.diff_out = nullptr;
             out.ref_out = (P.latent || !a.ref_out) ? nullptr : a.ref_out + (size_t)b * P.d; out.scale_by_p = true;
             update_stage_large(grid, P, b, sm, q, ls, P.m, P.latent ? E_NONE : E_STEP_WHITE, 0.0, nullptr, P.te_u, P.be_u,
-                               P.Hcol, P.Hval, W, out, &diff_s);
+                               P.Hcol, P.Hval, W, out, &diff_s, pc);
             if (blockIdx.x == 0) { __syncthreads(); diffsum += diff_s; }
             if (a.mean_traj) {
                 double* mt = a.mean_traj + ((size_t)s * P.batch + b) * msz;
@@ -226,6 +282,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_init_large(const Problem P, con
     const int gw = blockIdx.x * kWarps + warp, gnw = gridDim.x * kWarps;
     const int n = P.n, d = P.d, D = P.D, nd = P.n * P.d;
     double* W = P.W;
+    PhaseClock pc;
+    pc.start(nullptr);
     for (int b = 0; b < P.batch; ++b) {
         if (blockIdx.x == 0 && tid == 0) *q.nf = 0;
         double* chol = a.chol_out + (size_t)b * D * D;
@@ -261,13 +319,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_init_large(const Problem P, con
         grid.sync();
         UpdateOut o1;
         o1.mean_out = nullptr; o1.chol_out = chol; o1.diff_out = nullptr; o1.ref_out = nullptr; o1.scale_by_p = false;
-        update_stage_large(grid, P, b, sm, q, ls, d, E_NUGGET_ONLY, a.nugget, chol, nullptr, nullptr, P.Hcol, P.Hval, W, o1, nullptr);
+        update_stage_large(grid, P, b, sm, q, ls, d, E_NUGGET_ONLY, a.nugget, chol, nullptr, nullptr, P.Hcol, P.Hval, W, o1, nullptr, pc);
         if (blockIdx.x == 0) evaluate_ode(P, b, sm, 1.0, 1.0, P.Hcol, P.Hval);  // white.py:42-48, latent.py:86-95
         grid.sync();
         UpdateOut o2;
         o2.mean_out = mean; o2.chol_out = chol; o2.diff_out = nullptr; o2.ref_out = nullptr; o2.scale_by_p = false;
         update_stage_large(grid, P, b, sm, q, ls, P.m, P.latent ? E_NUGGET_ONLY : E_STEP_PLUS_NUGGET, a.nugget, chol, nullptr,
-                           nullptr, P.Hcol, P.Hval, W, o2, nullptr);
+                           nullptr, P.Hcol, P.Hval, W, o2, nullptr, pc);
         if (blockIdx.x == 0 && tid == 0 && a.status) a.status[b] = *q.nf;
         grid.sync();
     }

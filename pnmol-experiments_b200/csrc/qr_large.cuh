@@ -93,40 +93,60 @@ __device__ void large_gram(const double* __restrict__ V, int ldv, int len, doubl
 }
 
 // S1: factor the panel (columns j0 .. j0+nbk-1) on one CTA.
+//
+// Two block barriers per column: the warp that updates the next column also reduces that column's norm and diagonal
+// entry (published in shared memory), so every thread derives the next reflector's scalars without another
+// reduction round; each warp updates two panel columns at once (one pass over the reflector).
 __device__ void large_panel_factor(double* __restrict__ W, int ld, const Shape& s, int j0, int nbk, const RowMap rm,
-                                   const LargeQR& q, const LargeSmem& ls) {
+                                   const LargeQR& q, const LargeSmem& ls, PhaseClock& pc) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = rm.len, lp = (L + 7) & ~7, nt = s.nt;
     double* PB = ls.PB;
-    double* sc = ls.sc;
+    double* sc = ls.sc;          // [3 i] tau, [3 i + 1] beta
+    double* nxt = ls.sc + 64;    // [0] ||x||^2 below the diagonal of the next column, [1] its diagonal entry
+    __shared__ int env[2 * kNB];  // own envelope of every panel column: last top row, last bottom row
     int sw = kNB;
     while (sw > 1 && (size_t)sw * lp > (size_t)q.cap) sw >>= 1;
+    if (tid < nbk) { env[tid] = env_top(s, j0 + tid); env[kNB + tid] = env_bot(s, j0 + tid); }
     // reflector slots beyond the panel are zero
     for (int idx = tid; idx < (kNB - nbk) * lp; idx += kThreads) q.Vg[(size_t)(nbk + idx / lp) * q.lv + idx % lp] = 0.0;
+    __syncthreads();
     for (int i0 = 0; i0 < nbk; i0 += sw) {
         const int ncs = nbk - i0 < sw ? nbk - i0 : sw;
-        // ---- load the sub-panel (entries outside a column's own envelope are zero)
-        for (int idx = tid; idx < ncs * lp; idx += kThreads) {
-            const int cc = idx / lp, c = idx - cc * lp;
-            const int j = j0 + i0 + cc;
-            double v = 0.0;
-            if (c < L) {
+        // ---- load the sub-panel with 8-byte asynchronous copies (global -> shared, no register staging: every thread
+        // has all its copies in flight at once); entries outside a column's own envelope are zero
+        for (int cc = 0; cc < ncs; ++cc) {
+            const int et = env[i0 + cc], eb = env[kNB + i0 + cc];
+            const double* src = W + (size_t)(j0 + i0 + cc) * ld;
+            double* dstc = PB + (size_t)cc * lp;
+            for (int c = tid; c < lp; c += kThreads) {
                 const int row = rm.row(c);
-                const bool ok = row < nt ? row <= env_top(s, j) : row <= env_bot(s, j);
-                if (ok) v = W[(size_t)j * ld + row];
+                if (c < L && (row < nt ? row <= et : row <= eb)) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(dstc + c);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src + row) : "memory");
+                } else {
+                    dstc[c] = 0.0;
+                }
             }
-            PB[(size_t)cc * lp + c] = v;
         }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
         __syncthreads();
+        pc.mark(14);
+        {   // norm and diagonal of the sub-panel's first column
+            const int cd = row_cidx(rm, j0 + i0);
+            double ss = 0.0;
+            for (int c = cd + 1 + tid; c < L; c += kThreads) ss = fma(PB[c], PB[c], ss);
+            ss = block_sum(ss, ls.red);
+            if (tid == 0) { nxt[0] = ss; nxt[1] = PB[cd]; }
+            __syncthreads();
+        }
+        pc.mark(15);
         // ---- factor it column by column
         for (int cc = 0; cc < ncs; ++cc) {
             const int i = i0 + cc;
             const int cd = row_cidx(rm, j0 + i);
             double* x = PB + (size_t)cc * lp;
-            double ss = 0.0;
-            for (int c = cd + 1 + tid; c < L; c += kThreads) ss = fma(x[c], x[c], ss);
-            ss = block_sum(ss, ls.red);
-            const double alpha = x[cd];
+            const double ss = nxt[0], alpha = nxt[1];
             double tau = 0.0, beta = alpha, scale = 0.0;
             if (ss != 0.0) {  // dlarfg: xnorm == 0 -> H = I
                 const double nrm = sqrt(fma(alpha, alpha, ss));
@@ -134,42 +154,92 @@ __device__ void large_panel_factor(double* __restrict__ W, int ld, const Shape& 
                 tau = (beta - alpha) / beta;
                 scale = 1.0 / (alpha - beta);
             }
-            __syncthreads();  // alpha has been read by everyone
             if (tau != 0.0) {
-                for (int c = cd + 1 + tid; c < L; c += kThreads) x[c] *= scale;
+                int c = cd + 1 + tid;
+                for (; c + 3 * kThreads < L; c += 4 * kThreads) {
+                    const double v0 = x[c], v1 = x[c + kThreads], v2 = x[c + 2 * kThreads], v3 = x[c + 3 * kThreads];
+                    x[c] = v0 * scale; x[c + kThreads] = v1 * scale; x[c + 2 * kThreads] = v2 * scale; x[c + 3 * kThreads] = v3 * scale;
+                }
+                for (; c < L; c += kThreads) x[c] *= scale;
             }
             if (tid == 0) { x[cd] = 1.0; sc[3 * i] = tau; sc[3 * i + 1] = beta; }
-            __syncthreads();
-            if (tau != 0.0) {
-                for (int k = cc + 1 + warp; k < ncs; k += kWarps) {
-                    double* y = PB + (size_t)k * lp;
-                    double d0 = 0.0, d1 = 0.0;
+            __syncthreads();  // v complete; nxt consumed by everyone
+            // apply H to the remaining columns of the sub-panel, two per warp; the first one is the next pivot column
+            for (int k0 = cc + 1 + warp; k0 < ncs; k0 += 2 * kWarps) {
+                const int k1 = k0 + kWarps;
+                const bool two = k1 < ncs;
+                double* y0 = PB + (size_t)k0 * lp;
+                double* y1 = PB + (size_t)(two ? k1 : k0) * lp;
+                double wa = 0.0, wb = 0.0;
+                if (tau != 0.0) {
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
                     int c = cd + lane;
-                    for (; c + 32 < L; c += 64) { d0 = fma(x[c], y[c], d0); d1 = fma(x[c + 32], y[c + 32], d1); }
-                    if (c < L) d0 = fma(x[c], y[c], d0);
-                    const double w = tau * warp_sum(d0 + d1);
-                    for (int c2 = cd + lane; c2 < L; c2 += 32) y[c2] = fma(-w, x[c2], y[c2]);
+                    for (; c + 96 < L; c += 128) {
+                        const double x0 = x[c], x1 = x[c + 32], x2 = x[c + 64], x3 = x[c + 96];
+                        a0 = fma(x0, y0[c], a0); a1 = fma(x1, y0[c + 32], a1); a2 = fma(x2, y0[c + 64], a2); a3 = fma(x3, y0[c + 96], a3);
+                        b0 = fma(x0, y1[c], b0); b1 = fma(x1, y1[c + 32], b1); b2 = fma(x2, y1[c + 64], b2); b3 = fma(x3, y1[c + 96], b3);
+                    }
+                    for (; c < L; c += 32) { a0 = fma(x[c], y0[c], a0); b0 = fma(x[c], y1[c], b0); }
+                    a0 = (a0 + a1) + (a2 + a3); b0 = (b0 + b1) + (b2 + b3);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ta = __shfl_xor_sync(0xffffffffu, a0, o), tb = __shfl_xor_sync(0xffffffffu, b0, o);
+                        a0 += ta; b0 += tb;
+                    }
+                    wa = tau * a0; wb = tau * b0;
+                }
+                const bool pivot = k0 == cc + 1;  // this warp owns the next pivot column: reduce its norm on the fly
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int c = cd + lane;
+                for (; c + 96 < L; c += 128) {  // loads first: the compiler cannot prove x, y0, y1 distinct
+                    const double x0 = x[c], x1 = x[c + 32], x2 = x[c + 64], x3 = x[c + 96];
+                    const double p0 = y0[c], p1 = y0[c + 32], p2 = y0[c + 64], p3 = y0[c + 96];
+                    const double q0 = y1[c], q1 = y1[c + 32], q2 = y1[c + 64], q3 = y1[c + 96];
+                    const double r0 = fma(-wa, x0, p0), r1 = fma(-wa, x1, p1), r2 = fma(-wa, x2, p2), r3 = fma(-wa, x3, p3);
+                    y0[c] = r0; y0[c + 32] = r1; y0[c + 64] = r2; y0[c + 96] = r3;
+                    if (two) {
+                        y1[c] = fma(-wb, x0, q0); y1[c + 32] = fma(-wb, x1, q1); y1[c + 64] = fma(-wb, x2, q2); y1[c + 96] = fma(-wb, x3, q3);
+                    }
+                    if (pivot) {
+                        if (c > cd + 1) s0 = fma(r0, r0, s0);
+                        s1 = fma(r1, r1, s1); s2 = fma(r2, r2, s2); s3 = fma(r3, r3, s3);
+                    }
+                }
+                for (; c < L; c += 32) {
+                    const double xv = x[c];
+                    const double ya = fma(-wa, xv, y0[c]);
+                    y0[c] = ya;
+                    if (two) y1[c] = fma(-wb, xv, y1[c]);
+                    if (pivot && c > cd + 1) s0 = fma(ya, ya, s0);
+                }
+                if (pivot) {
+                    const double ssn = warp_sum((s0 + s1) + (s2 + s3));
+                    __syncwarp();
+                    if (lane == 0) { nxt[0] = ssn; nxt[1] = y0[cd + 1]; }
                 }
             }
             __syncthreads();
         }
+        pc.mark(16);
         // ---- write R back, export V (the buffer keeps the pure reflectors: zero above the unit diagonal)
-        for (int idx = tid; idx < ncs * lp; idx += kThreads) {
-            const int cc = idx / lp, c = idx - cc * lp;
+        for (int cc = 0; cc < ncs; ++cc) {
             const int i = i0 + cc, j = j0 + i;
-            const int cd = row_cidx(rm, j);
-            const double tau = sc[3 * i];
-            const double xv = PB[(size_t)cc * lp + c];
-            if (c < L) {
+            const int cd = row_cidx(rm, j), et = env[i], eb = env[kNB + i];
+            const double tau = sc[3 * i], beta = sc[3 * i + 1];
+            double* colp = PB + (size_t)cc * lp;
+            double* wj = W + (size_t)j * ld;
+            double* vg = q.Vg + (size_t)i * q.lv;
+            for (int c = tid; c < lp; c += kThreads) {
+                const double xv = colp[c];
                 const int row = rm.row(c);
-                const bool ok = row < nt ? row <= env_top(s, j) : row <= env_bot(s, j);
-                if (ok) W[(size_t)j * ld + row] = c < cd ? xv : (c == cd ? sc[3 * i + 1] : 0.0);
+                if (c < L && (row < nt ? row <= et : row <= eb)) wj[row] = c < cd ? xv : (c == cd ? beta : 0.0);
+                const double vv = (tau != 0.0 && c >= cd && c < L) ? xv : 0.0;
+                colp[c] = vv;
+                vg[c] = vv;
             }
-            const double vv = (tau != 0.0 && c >= cd && c < L) ? xv : 0.0;
-            PB[(size_t)cc * lp + c] = vv;
-            q.Vg[(size_t)i * q.lv + c] = vv;
         }
         __syncthreads();
+        pc.mark(17);
         // ---- apply the sub-panel's reflectors to the rest of the panel (streamed from L2), one warp per column
         if (i0 + ncs < nbk) {
             for (int k = j0 + i0 + ncs + warp; k < j0 + nbk; k += kWarps) {
@@ -201,12 +271,13 @@ __device__ void large_panel_factor(double* __restrict__ W, int ld, const Shape& 
             __syncthreads();
         }
     }
+    pc.mark(18);
     // ---- T factor
-    __threadfence_block();
     large_gram(sw == kNB ? PB : q.Vg, sw == kNB ? lp : q.lv, L, ls.Gs, ls.scratch);
     if (warp == 0) panel_t_factor(ls.Gs, sc, nbk, ls.Ts);
     __syncthreads();
     for (int idx = tid; idx < kNB * kLdr; idx += kThreads) q.Tg[idx] = ls.Ts[idx];
+    pc.mark(19);
 }
 
 // S2: partial Y^T = C^T V per (row chunk, column group) item.
@@ -362,21 +433,27 @@ __device__ __forceinline__ int large_chunk_rows(int L, int ntrail, int cap) {
 
 // Grid-wide blocked QR.  On return (after a grid barrier) the upper triangle holds R.
 __device__ void householder_qr_large(cg::grid_group& grid, double* __restrict__ W, int ld, const Shape s, const LargeQR& q,
-                                     const LargeSmem& ls) {
+                                     const LargeSmem& ls, PhaseClock& pc) {
     const int nrows = s.nt + s.nbot;
     const int nref = nrows < s.ncols ? nrows : s.ncols;
     for (int j0 = 0; j0 < nref; j0 += kNB) {
         const int nbk = nref - j0 < kNB ? nref - j0 : kNB;
         const RowMap rm = panel_rows(s, j0, j0 + nbk - 1);
-        if (blockIdx.x == 0) large_panel_factor(W, ld, s, j0, nbk, rm, q, ls);
+        if (blockIdx.x == 0) large_panel_factor(W, ld, s, j0, nbk, rm, q, ls, pc);
+        pc.mark(8);
         grid.sync();
+        pc.mark(9);
         const int ntrail = s.ncols - (j0 + nbk);
         if (ntrail > 0) {
             const int RC = large_chunk_rows(rm.len, ntrail, q.cap);
             large_trailing_y(W, ld, s.ncols, j0, nbk, rm, q, RC, ls.PB);
+            pc.mark(10);
             grid.sync();
+            pc.mark(11);
             large_trailing_u(W, ld, s.ncols, j0, nbk, rm, q, RC, ls.PB, ls.Ts);
+            pc.mark(12);
             grid.sync();
+            pc.mark(13);
         }
     }
 }

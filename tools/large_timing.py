@@ -25,9 +25,23 @@ for name in args:
     mean, chol = s0.y.mean.clone().reshape(1, eng.n, eng.dd), s0.y.cov_sqrtm.clone().reshape(1, D, D)
     dts = np.full(steps, dt)
     eng.run(case["pde"].t0, dts[:1], mean.clone(), chol.clone())   # warm-up
+    from pnmol_b200 import _lib
+    prof = "--profile" in sys.argv
+    if prof:
+        _lib.check(eng.lib.pnmol_b200_profile(eng.h, 1, None))
     e[2].record(); out = eng.run(case["pde"].t0, dts, mean, chol); e[3].record()
     torch.cuda.synchronize()
     ms_init, ms_step = e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3]) / steps
     flop = (10.0 / 3.0) * D ** 3 + 4.0 * m * D * D + 3.0 * m * m * D
     print(f"{name}: {pname} N={num} {kind} D={D} m={m} path={eng.path} host set-up {t_setup:.1f} s | initialize {ms_init:.2f} ms | "
           f"step {ms_step:.3f} ms = {1e3 / ms_step:.1f} steps/s | F_alg {flop / 1e9:.2f} Gflop -> {flop / ms_step / 1e9:.2f} TFLOP/s | status {int(out['status'].max())}")
+    if prof:
+        cyc = np.zeros(24, np.uint64)
+        _lib.check(eng.lib.pnmol_b200_profile(eng.h, 0, _lib.ptr(cyc)))
+        names = ["mean+evaluate_ode (CTA 0)", "build predict + barrier", "-", "error estimate", "build update", "-", "solves+mean+factor out", "end barrier",
+                 "qr: panel factor (CTA 0)", "qr: barrier after panel", "qr: partial Y", "qr: barrier", "qr: update", "qr: barrier",
+                 "panel: load", "panel: first norm", "panel: column loop", "panel: write-back + V", "panel: streamed apply", "panel: Gram + T"]
+        tot = float(cyc.sum())
+        for nme, c in zip(names, cyc[:20]):
+            if c:
+                print(f"    {nme:28s} {100.0 * float(c) / tot:6.2f} %  {float(c) / steps / 1.965e6:9.3f} ms/step")
