@@ -74,10 +74,14 @@ int64_t pnmol_b200_launch_count(void);
  * 3 error estimate, 4 build update matrix, 5 update QR, 6 triangular solves + mean, 7 outputs. */
 int pnmol_b200_profile(pnmol_b200_handle* h, int enable, uint64_t* cycles_out);
 
-/* Which kernel family serves this handle (valid after pnmol_b200_set_operator): 0 = one CTA per member
- * (register/shared-memory blocked QR, thousands of members in flight), 1 = the whole grid per member
- * (multi-CTA blocked QR with FP64 tensor-core trailing updates; chosen when the state does not fit the
- * single-CTA kernels, i.e. BASELINE configs C2-C4, or with PNMOL_B200_FORCE_LARGE=1).  <0 = error. */
+/* Which kernel family serves this handle (valid after pnmol_b200_set_operator):
+ *   2 = one WARP per member (register-resident 8-column panels, per-warp tensor-core trailing updates, no block
+ *       barriers; chosen when every panel's row list has <= 256 rows: C1/C5-sized ensembles),
+ *   0 = one CTA per member (blocked QR with 16-column panels; row lists up to 512 rows),
+ *   1 = the whole grid per member (multi-CTA blocked QR with FP64 tensor-core trailing updates; BASELINE
+ *       configs C2-C4).
+ * The environment variable PNMOL_B200_PATH=warp|cta|large overrides the choice where the problem fits (used by
+ * the parity tests to run every family on the same inputs).  <0 = error. */
 int pnmol_b200_path(pnmol_b200_handle* h);
 
 /* Create a solver handle for `batch` independent members of one discretised problem.

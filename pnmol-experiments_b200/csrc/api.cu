@@ -3,6 +3,7 @@
 #include "../../include/pnmol_b200.h"
 #include "ek1_kernels.cuh"
 #include "ek1_large.cuh"
+#include "ek1_warp.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -108,6 +109,10 @@ struct pnmol_b200_handle {
     bool large = false;
     LargeQR q{};
     size_t smem_large = 0;
+    // warp-per-member path (ek1_warp.cuh): every panel row list <= 256 rows; PNMOL_B200_PATH=cta|warp|large overrides
+    bool warp = false;
+    WarpGeom geo{};
+    size_t smem_warp = 0;
 };
 
 namespace {
@@ -169,7 +174,9 @@ int upload_steps(pnmol_b200_handle* h, int nsteps, double t0, const double* dts,
 }
 
 int launch_run(pnmol_b200_handle* h, RunArgs& a, cudaStream_t st) {
-    if (h->large) {
+    if (h->warp) {
+        k_run_warp<<<h->grid, 32 * h->geo.nwarps, h->smem_warp, st>>>(h->P, a, h->geo);
+    } else if (h->large) {
         void* args[] = {(void*)&h->P, (void*)&a, (void*)&h->q};
         CU(cudaLaunchCooperativeKernel((const void*)k_run_large, dim3(h->grid), dim3(kThreads), args, h->smem_large, st));
     } else {
@@ -297,6 +304,36 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
         // fits the register-resident panels (<= 32 * kRPL rows); beyond that the whole grid works on one member
         h->large = h->smem_bytes > h->smem_optin || maxlen > 32 * kRPL;
         if (force && h->smem_bytes <= h->smem_optin) h->large = std::atoi(force) != 0;
+        const char* pathenv = std::getenv("PNMOL_B200_PATH");
+        const std::string want_path = pathenv ? pathenv : "";
+        if (want_path == "large") h->large = true;
+        if (want_path == "cta" && h->smem_bytes <= h->smem_optin) h->large = false;
+        if (!h->large && want_path != "cta" && maxlen <= 32 * kWR) {
+            WarpGeom& geo = h->geo;
+            geo.ldv = warp_ldv(maxlen);
+            geo.per_warp = warp_smem_doubles(P.D, P.m, P.dd, P.ldm, geo.ldv);
+            geo.nwarps = std::min(8, (int)(h->smem_optin / sizeof(double)) / geo.per_warp);
+            if (geo.nwarps >= 4 || want_path == "warp") h->warp = geo.nwarps >= 1;
+        }
+        if (want_path == "warp" && !h->warp) return fail(-1, "PNMOL_B200_PATH=warp: problem does not fit the warp-per-member kernels");
+        if (h->warp) {
+            const WarpGeom& geo = h->geo;
+            h->smem_warp = (size_t)geo.per_warp * geo.nwarps * sizeof(double);
+            CU(cudaFuncSetAttribute(k_run_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_warp));
+            CU(cudaFuncSetAttribute(k_init_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_warp));
+            h->grid = std::min((P.batch + geo.nwarps - 1) / geo.nwarps, h->num_sms);
+            if (const char* e = std::getenv("PNMOL_B200_GRID")) h->grid = std::max(1, std::min(h->grid, std::atoi(e)));
+            const size_t slots = (size_t)h->grid * geo.nwarps;
+            const size_t wsz = (size_t)P.ld * (P.m + P.D);
+            if ((rc = dev_alloc(h, &P.W, wsz * slots))) return rc;
+            if ((rc = dev_alloc(h, &P.Hcol, slots * P.m * P.wh))) return rc;
+            if ((rc = dev_alloc(h, &P.Hval, slots * P.m * P.wh))) return rc;
+            if ((rc = dev_alloc(h, &P.F, slots * P.m * P.d))) return rc;
+            if ((rc = dev_alloc(h, &P.S, slots * P.m * P.m))) return rc;
+            CU(cudaMemset(P.W, 0, wsz * slots * sizeof(double)));
+            h->have_op = true;
+            return 0;
+        }
         if (h->large) {
             // one member at a time on the whole grid: one workspace, vectors in global scratch
             LargeQR& q = h->q;
@@ -405,7 +442,9 @@ int pnmol_b200_initialize(pnmol_b200_handle* h, const double* y0, double t0, dou
     a.y0 = y0; a.t0 = t0; a.prior_scale0 = diffuse_prior_scale;
     a.nugget = h->P.latent ? 1e-6 : 1e-10;  // latent.py:71,98 / white.py:33,51
     a.mean_out = mean_out; a.chol_out = chol_out; a.status = status;
-    if (h->large) {
+    if (h->warp) {
+        k_init_warp<<<h->grid, 32 * h->geo.nwarps, h->smem_warp, (cudaStream_t)stream>>>(h->P, a, h->geo);
+    } else if (h->large) {
         void* args[] = {(void*)&h->P, (void*)&a, (void*)&h->q};
         CU(cudaLaunchCooperativeKernel((const void*)k_init_large, dim3(h->grid), dim3(kThreads), args, h->smem_large, (cudaStream_t)stream));
     } else {
@@ -473,7 +512,7 @@ int pnmol_b200_profile(pnmol_b200_handle* h, int enable, uint64_t* cycles_out) {
 int pnmol_b200_path(pnmol_b200_handle* h) {
     if (!h) return fail(-1, "null handle");
     if (!h->have_op) return fail(-1, "pnmol_b200_set_operator has not been called");
-    return h->large ? 1 : 0;
+    return h->warp ? 2 : (h->large ? 1 : 0);
 }
 
 int pnmol_b200_rescale(pnmol_b200_handle* h, double* chol, const double* diff_sum, int nsteps, double* diff_cal_out,

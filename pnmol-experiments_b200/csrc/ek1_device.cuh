@@ -93,6 +93,23 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;
 }
 
+// A "team" is the set of threads that works on one ensemble member: the whole CTA on the blocked path, one warp on
+// the warp-per-member path (ek1_warp.cuh).  The O(D^2) phases below are written once against this interface.
+struct CtaTeam {
+    static constexpr int size = kThreads, nwarps = kWarps;
+    static __device__ __forceinline__ int tid() { return threadIdx.x; }
+    static __device__ __forceinline__ int warp() { return threadIdx.x >> 5; }
+    static __device__ __forceinline__ void sync() { __syncthreads(); }
+    static __device__ __forceinline__ double sum(double v, double* red) { return block_sum(v, red); }
+};
+struct WarpTeam {
+    static constexpr int size = 32, nwarps = 1;
+    static __device__ __forceinline__ int tid() { return threadIdx.x & 31; }
+    static __device__ __forceinline__ int warp() { return 0; }
+    static __device__ __forceinline__ void sync() { __syncwarp(); }
+    static __device__ __forceinline__ double sum(double v, double*) { return warp_sum(v); }
+};
+
 __host__ __device__ __forceinline__ size_t smem_doubles(int D, int m, int dd, int vld, int ldm) {
     return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 80 + 2 * (size_t)vld + 16 * ((size_t)vld + 2) + 18 * (size_t)vld + 288 + 272 +
            (size_t)m * ldm + 8;
@@ -244,14 +261,15 @@ __device__ __forceinline__ void reaction_point(int id, const double* prm, const 
 // Builds z (smem) and the sparse rows of H (global scratch, ELL width wh) from the
 // predicted mean mp (smem), with projections p0 = E0 P, p1 = E1 P reduced to the two
 // scalars p0s, p1s.  white.py:169-208, latent.py:237-292.
+template <class T = CtaTeam>
 __device__ void evaluate_ode(const Problem& P, int b, const Smem& sm, double p0s, double p1s, int32_t* Hcol,
                              double* Hval) {
-    const int tid = threadIdx.x;
+    const int tid = T::tid();
     const int n = P.n, d = P.d;
-    for (int j = tid; j < P.dd; j += kThreads) sm.xat[j] = p0s * sm.mp[j * n];
-    __syncthreads();
+    for (int j = tid; j < P.dd; j += T::size) sm.xat[j] = p0s * sm.mp[j * n];
+    T::sync();
     const double* prm = P.rparams ? P.rparams + (size_t)b * P.nparams : nullptr;
-    for (int i = tid; i < d; i += kThreads) {
+    for (int i = tid; i < d; i += T::size) {
         const int comp = i / P.npts, pt = i - comp * P.npts;
         const double ds = P.diffscale ? P.diffscale[(size_t)b * P.ncomp + comp] : 1.0;
         int32_t* hc = Hcol + (size_t)i * P.wh;
@@ -299,7 +317,7 @@ __device__ void evaluate_ode(const Problem& P, int b, const Smem& sm, double p0s
         for (; w < P.wh; ++w) { hc[w] = -1; hv[w] = 0.0; }
         sm.z[i] = hz + shift;
     }
-    for (int r = tid; r < P.nb; r += kThreads) {
+    for (int r = tid; r < P.nb; r += T::size) {
         int32_t* hc = Hcol + (size_t)(d + r) * P.wh;
         double* hv = Hval + (size_t)(d + r) * P.wh;
         double acc = 0.0;
@@ -319,7 +337,7 @@ __device__ void evaluate_ode(const Problem& P, int b, const Smem& sm, double p0s
         for (; w < P.wh; ++w) { hc[w] = -1; hv[w] = 0.0; }
         sm.z[d + r] = acc;
     }
-    __syncthreads();
+    T::sync();
 }
 
 // ---------------------------------------------------------------- predict stack
@@ -327,9 +345,10 @@ __device__ void evaluate_ode(const Problem& P, int b, const Smem& sm, double p0s
 // white.py:104,118 / latent.py:179,194 and iwp.py:32-53, stacked_ssm.py:16-26.
 // (w0, nw): this warp's index and the number of warps sharing the loop (CTA-local by default; grid-wide on the
 // multi-CTA path, which synchronises with a grid barrier afterwards).
+template <class T = CtaTeam>
 __device__ void build_predict(const Problem& P, int b, const Smem& sm, const double* __restrict__ Cl,
-                              const int32_t* te, double* Wp, int w0 = threadIdx.x >> 5, int nw = kWarps) {
-    const int lane = threadIdx.x & 31;
+                              const int32_t* te, double* Wp, int w0 = T::warp(), int nw = T::nwarps) {
+    const int lane = T::tid() & 31;
     const int n = P.n, D = P.D, nd = P.n * P.d;
     const double ps = P.priorscale ? P.priorscale[b] : 1.0;
     for (int i = w0; i < D; i += nw) {
@@ -359,7 +378,7 @@ __device__ void build_predict(const Problem& P, int b, const Smem& sm, const dou
             }
         }
     }
-    __syncthreads();
+    T::sync();
 }
 
 // ---------------------------------------------------------------- error estimate
@@ -384,10 +403,11 @@ __device__ __forceinline__ double meas_cov_entry(const Problem& P, int b, EMode 
     return ee;
 }
 
+template <class T = CtaTeam>
 __device__ void error_estimate_global(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode,
                                       double nugget, const int32_t* Hcol, const double* Hval, double* F, double* S,
                                       double* err_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = T::tid(), lane = tid & 31, warp = T::warp();
     const int n = P.n, d = P.d, m = P.m;
     const double ps = P.priorscale ? P.priorscale[b] : 1.0;
     const double ps2 = ps * ps;
@@ -398,7 +418,7 @@ __device__ void error_estimate_global(const Problem& P, int b, const Smem& sm, d
         q11 = fma(P.LQ1d[n + s], P.LQ1d[n + s], q11);
     }
     // F = At K  (m x d)
-    for (int r = warp; r < m; r += kWarps) {
+    for (int r = warp; r < m; r += T::nwarps) {
         for (int k = lane; k < d; k += 32) {
             double acc = 0.0;
             for (int w = 0; w < P.wh; ++w) {
@@ -408,9 +428,9 @@ __device__ void error_estimate_global(const Problem& P, int b, const Smem& sm, d
             F[(size_t)r * d + k] = acc;
         }
     }
-    __syncthreads();
+    T::sync();
     // S (m x m), row-major, full
-    for (int r = warp; r < m; r += kWarps) {
+    for (int r = warp; r < m; r += T::nwarps) {
         for (int rp = lane; rp < m; rp += 32) {
             double acc = 0.0;
             for (int w = 0; w < P.wh; ++w) {
@@ -426,24 +446,24 @@ __device__ void error_estimate_global(const Problem& P, int b, const Smem& sm, d
             S[(size_t)r * m + rp] = val + meas_cov_entry(P, b, emode, r, rp);
         }
     }
-    __syncthreads();
-    for (int r = tid; r < m; r += kThreads) sm.y[r] = S[(size_t)r * m + r];  // diag(S) before factorisation
-    __syncthreads();
+    T::sync();
+    for (int r = tid; r < m; r += T::size) sm.y[r] = S[(size_t)r * m + r];  // diag(S) before factorisation
+    T::sync();
     // right-looking Cholesky on the lower triangle (row-major)
     for (int k = 0; k < m; ++k) {
         const double piv = sqrt(S[(size_t)k * m + k]);
-        __syncthreads();
-        for (int r = k + tid; r < m; r += kThreads) S[(size_t)r * m + k] = r == k ? piv : S[(size_t)r * m + k] / piv;
-        __syncthreads();
-        for (int r = k + 1 + warp; r < m; r += kWarps) {
+        T::sync();
+        for (int r = k + tid; r < m; r += T::size) S[(size_t)r * m + k] = r == k ? piv : S[(size_t)r * m + k] / piv;
+        T::sync();
+        for (int r = k + 1 + warp; r < m; r += T::nwarps) {
             const double lrk = S[(size_t)r * m + k];
             for (int c = k + 1 + lane; c <= r; c += 32) S[(size_t)r * m + c] = fma(-lrk, S[(size_t)c * m + k], S[(size_t)r * m + c]);
         }
-        __syncthreads();
+        T::sync();
     }
     // forward solve L u = z  (xw <- u), row-oriented dot form
-    for (int r = tid; r < m; r += kThreads) sm.xw[r] = sm.z[r];
-    __syncthreads();
+    for (int r = tid; r < m; r += T::size) sm.xw[r] = sm.z[r];
+    T::sync();
     for (int k = 0; k < m; ++k) {
         if (warp == 0) {
             double acc = 0.0;
@@ -451,21 +471,22 @@ __device__ void error_estimate_global(const Problem& P, int b, const Smem& sm, d
             acc = warp_sum(acc);
             if (lane == 0) sm.xw[k] = (sm.xw[k] - acc) / S[(size_t)k * m + k];
         }
-        __syncthreads();
+        T::sync();
     }
     double part = 0.0;
-    for (int r = tid; r < m; r += kThreads) part = fma(sm.xw[r], sm.xw[r], part);
-    const double sigma = sqrt(block_sum(part, sm.red) / m);
+    for (int r = tid; r < m; r += T::size) part = fma(sm.xw[r], sm.xw[r], part);
+    const double sigma = sqrt(T::sum(part, sm.red) / m);
     if (err_out)
-        for (int i = tid; i < d; i += kThreads) err_out[i] = dt * (sqrt(sm.y[i]) * sigma);
-    __syncthreads();
+        for (int i = tid; i < d; i += T::size) err_out[i] = dt * (sqrt(sm.y[i]) * sigma);
+    T::sync();
 }
 
 // Shared-memory variant for small m (P.ldm > 0): S is assembled entry by entry straight from the sparse rows of
 // At and the L2-resident Gram matrix (all loads independent), factorised and solved in sm.msq.
+template <class T = CtaTeam>
 __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode,
                                     const int32_t* Hcol, const double* Hval, double* err_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = T::tid(), lane = tid & 31, warp = T::warp();
     const int n = P.n, d = P.d, m = P.m, ldm = P.ldm;
     const double ps = P.priorscale ? P.priorscale[b] : 1.0;
     const double ps2 = ps * ps;
@@ -478,7 +499,7 @@ __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, dou
     double* S = sm.msq;
     const int na_ode = P.wl + (P.semilinear ? P.ncomp : 0);  // order-0 entries come first in a row of H
     const int ntri = m * (m + 1) / 2;
-    for (int idx = tid; idx < ntri; idx += kThreads) {
+    for (int idx = tid; idx < ntri; idx += T::size) {
         int r = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
         while (r * (r + 1) / 2 > idx) --r;
         while ((r + 1) * (r + 2) / 2 <= idx) ++r;
@@ -513,23 +534,23 @@ __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, dou
         S[r * ldm + rp] = val;
         if (r == rp) sm.y[r] = val;  // diag(S) before factorisation
     }
-    __syncthreads();
+    T::sync();
     // right-looking Cholesky of the lower triangle, two barriers per column; the diagonal of L goes to sm.xw so
     // that S[k][k] is never written while other threads may still read it
     for (int k = 0; k < m; ++k) {
-        __syncthreads();
+        T::sync();
         const double skk = S[k * ldm + k];
         const double rinv = rsqrt(skk);
-        for (int r = k + 1 + tid; r < m; r += kThreads) S[r * ldm + k] *= rinv;
+        for (int r = k + 1 + tid; r < m; r += T::size) S[r * ldm + k] *= rinv;
         if (tid == 0) sm.xw[k] = skk * rinv;
-        __syncthreads();
+        T::sync();
         const int rem = m - k - 1;
-        for (int idx = tid; idx < rem * rem; idx += kThreads) {
+        for (int idx = tid; idx < rem * rem; idx += T::size) {
             const int r = k + 1 + idx / rem, c = k + 1 + idx % rem;
             if (c <= r) S[r * ldm + c] = fma(-S[r * ldm + k], S[c * ldm + k], S[r * ldm + c]);
         }
     }
-    __syncthreads();
+    T::sync();
     // forward solve L u = z by warp 0 (column oriented: each lane owns rows lane, lane + 32, lane + 64)
     if (warp == 0) {
         double u[3], acc[3];
@@ -553,19 +574,20 @@ __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, dou
         part = warp_sum(part);
         if (lane == 0) sm.red[15] = sqrt(part / m);
     }
-    __syncthreads();
+    T::sync();
     const double sigma = sm.red[15];
     if (err_out)
-        for (int i = tid; i < d; i += kThreads) err_out[i] = dt * (sqrt(sm.y[i]) * sigma);
-    __syncthreads();
+        for (int i = tid; i < d; i += T::size) err_out[i] = dt * (sqrt(sm.y[i]) * sigma);
+    T::sync();
 }
 
+template <class T = CtaTeam>
 __device__ void error_estimate(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode, double nugget,
                                const int32_t* Hcol, const double* Hval, double* F, double* S, double* err_out) {
     if (P.ldm > 0 && P.m <= 96)
-        error_estimate_smem(P, b, sm, p1s, dt, emode, Hcol, Hval, err_out);
+        error_estimate_smem<T>(P, b, sm, p1s, dt, emode, Hcol, Hval, err_out);
     else
-        error_estimate_global(P, b, sm, p1s, dt, emode, nugget, Hcol, Hval, F, S, err_out);
+        error_estimate_global<T>(P, b, sm, p1s, dt, emode, nugget, Hcol, Hval, F, S, err_out);
 }
 
 // ---------------------------------------------------------------- update stage
@@ -647,8 +669,9 @@ __device__ void update_build_left(const Problem& P, int b, int mcur, int nrows, 
 // ---- part 2 (one CTA): R1 = Wl[0:m, 0:m] (upper, column-major).  y = R1^-T z (for the mean),  x = R1^-1 z (quirk Q1,
 // white.py:125 / latent.py:204);  m_new = mp - R2^T y (white.py:123, sqrt.py:72) is left in sm.mp.  Returns the
 // local diffusion x.x / m.
+template <class T = CtaTeam>
 __device__ double update_solve(const Problem& P, const Smem& sm, int mcur, const double* Wl, const double* Wr) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = T::tid(), lane = tid & 31, warp = T::warp();
     const int D = P.D, ld = P.ld;
     double diff;
     if (P.ldm > 0 && mcur <= 96) {
@@ -656,11 +679,11 @@ __device__ double update_solve(const Problem& P, const Smem& sm, int mcur, const
         // warp 0 solves R1^T y = z and warp 1 solves R1 x = z concurrently, column oriented
         const int ldm = P.ldm;
         double* Rs = sm.msq;
-        for (int idx = tid; idx < mcur * mcur; idx += kThreads) {
+        for (int idx = tid; idx < mcur * mcur; idx += T::size) {
             const int k = idx / mcur, c = idx - k * mcur;  // column k, row c
             if (c <= k) Rs[c * ldm + k] = Wl[(size_t)k * ld + c];
         }
-        __syncthreads();
+        T::sync();
         if (warp == 0) {  // forward: y_k = (z_k - sum_{c<k} R1[c][k] y_c) / R1[k][k]
             double zz[3], acc[3];
 #pragma unroll
@@ -677,7 +700,8 @@ __device__ double update_solve(const Problem& P, const Smem& sm, int mcur, const
                     if (j == k) sm.y[j] = yk;
                 }
             }
-        } else if (warp == 1) {  // backward: x_k = (z_k - sum_{c>k} R1[k][c] x_c) / R1[k][k]
+        }
+        if (warp == (T::nwarps > 1 ? 1 : 0)) {  // backward: x_k = (z_k - sum_{c>k} R1[k][c] x_c) / R1[k][k]
             double zz[3];
 #pragma unroll
             for (int q = 0; q < 3; ++q) { const int j = lane + 32 * q; zz[q] = j < mcur ? sm.z[j] : 0.0; }
@@ -696,11 +720,11 @@ __device__ double update_solve(const Problem& P, const Smem& sm, int mcur, const
             }
             if (lane == 0) sm.red[14] = part / mcur;
         }
-        __syncthreads();
+        T::sync();
         diff = sm.red[14];
     } else {
-        for (int r = tid; r < mcur; r += kThreads) { sm.y[r] = sm.z[r]; sm.xw[r] = sm.z[r]; }
-        __syncthreads();
+        for (int r = tid; r < mcur; r += T::size) { sm.y[r] = sm.z[r]; sm.xw[r] = sm.z[r]; }
+        T::sync();
         for (int k = 0; k < mcur; ++k) {  // forward: dot form over contiguous column k of R1
             if (warp == 0) {
                 const double* ck = Wl + (size_t)k * ld;
@@ -709,38 +733,39 @@ __device__ double update_solve(const Problem& P, const Smem& sm, int mcur, const
                 acc = warp_sum(acc);
                 if (lane == 0) sm.y[k] = (sm.y[k] - acc) / ck[k];
             }
-            __syncthreads();
+            T::sync();
         }
         for (int k = mcur - 1; k >= 0; --k) {  // backward: axpy form over contiguous column k of R1
             const double* ck = Wl + (size_t)k * ld;
             const double xk = sm.xw[k] / ck[k];
-            __syncthreads();
-            for (int c = tid; c < k; c += kThreads) sm.xw[c] = fma(-xk, ck[c], sm.xw[c]);
+            T::sync();
+            for (int c = tid; c < k; c += T::size) sm.xw[c] = fma(-xk, ck[c], sm.xw[c]);
             if (tid == 0) sm.xw[k] = xk;
-            __syncthreads();
+            T::sync();
         }
         double part = 0.0;
-        for (int r = tid; r < mcur; r += kThreads) part = fma(sm.xw[r], sm.xw[r], part);
-        diff = block_sum(part, sm.red) / mcur;
+        for (int r = tid; r < mcur; r += T::size) part = fma(sm.xw[r], sm.xw[r], part);
+        diff = T::sum(part, sm.red) / mcur;
     }
     // m_new = mp - R2^T y   (white.py:123, sqrt.py:72)
-    for (int k = warp; k < D; k += kWarps) {
+    for (int k = warp; k < D; k += T::nwarps) {
         const double* col = Wr + (size_t)k * ld;
         double acc = 0.0;
         for (int i = lane; i < mcur; i += 32) acc = fma(col[i], sm.y[i], acc);
         acc = warp_sum(acc);
         if (lane == 0) sm.mp[k] -= acc;
     }
-    __syncthreads();
+    T::sync();
     return diff;
 }
 
 // ---- part 3a (one CTA): mean (n, dd) = P m_new reshaped (white.py:132-135).  Returns 1 on a non-finite value.
+template <class T = CtaTeam>
 __device__ int update_output_mean(const Problem& P, const Smem& sm, const UpdateOut& out, double diff) {
     const int n = P.n, D = P.D;
     int bad = 0;
     if (!(diff == diff) || isinf(diff)) bad = 1;
-    for (int k = threadIdx.x; k < D; k += kThreads) {
+    for (int k = T::tid(); k < D; k += T::size) {
         const int j = k / n, i = k - j * n;
         const double v = out.scale_by_p ? sm.pv[i] * sm.mp[k] : sm.mp[k];
         if (out.mean_out) out.mean_out[(size_t)i * P.dd + j] = v;

@@ -80,10 +80,13 @@ def test_update_sqrt(m, D, noise):
 
 
 # ------------------------------------------------------------------------- EK1 steps
+@pytest.mark.parametrize("path", ["warp", "cta"])
 @pytest.mark.parametrize("name,kind,bcond,num", KIND_CASES)
-def test_initialize_and_steps_from_oracle_state(name, kind, bcond, num):
-    """Every step starts from the oracle's state: pure per-step parity (no error accumulation)."""
-    _check_initialize_and_steps(name, kind, bcond, num, "single_cta")
+def test_initialize_and_steps_from_oracle_state(name, kind, bcond, num, path, monkeypatch):
+    """Every step starts from the oracle's state: pure per-step parity (no error accumulation).  Both ensemble kernel
+    families (one warp per member, the default at these sizes; one CTA per member) on the same inputs."""
+    monkeypatch.setenv("PNMOL_B200_PATH", path)
+    _check_initialize_and_steps(name, kind, bcond, num, "warp" if path == "warp" else "single_cta")
 
 
 LARGE_CASES = [("heat", "white_linear", "dirichlet", 6, 0), ("heat", "white_linear", "neumann", 50, 0),
@@ -98,7 +101,7 @@ def test_multi_cta_path_initialize_and_steps(name, kind, bcond, num, cap, monkey
     small problems: same per-step parity as the single-CTA path.  A reduced panel-buffer capacity (cap doubles of
     shared memory) makes the panel factorisation run in sub-panels that are applied to the rest of the panel from L2,
     as it does for BASELINE config C4."""
-    monkeypatch.setenv("PNMOL_B200_FORCE_LARGE", "1")
+    monkeypatch.setenv("PNMOL_B200_PATH", "large")
     if cap:
         monkeypatch.setenv("PNMOL_B200_LARGE_CAP", str(cap))
     _check_initialize_and_steps(name, kind, bcond, num, "multi_cta")
