@@ -75,9 +75,9 @@ int64_t pnmol_b200_launch_count(void);
 int pnmol_b200_profile(pnmol_b200_handle* h, int enable, uint64_t* cycles_out);
 
 /* Which kernel family serves this handle (valid after pnmol_b200_set_operator):
- *   2 = one WARP per member (register-resident 8-column panels, per-warp tensor-core trailing updates, no block
- *       barriers; chosen when every panel's row list has <= 256 rows: C1/C5-sized ensembles),
- *   0 = one CTA per member (blocked QR with 16-column panels; row lists up to 512 rows),
+ *   0 = one CTA per member (blocked QR with 16-column panels; row lists up to 512 rows; the default for ensembles),
+ *   2 = one WARP per member (8-column panels in the warp's shared-memory slice, per-warp tensor-core trailing
+ *       updates, no block barriers; row lists up to 224 rows; opt-in, measured slower on B200),
  *   1 = the whole grid per member (multi-CTA blocked QR with FP64 tensor-core trailing updates; BASELINE
  *       configs C2-C4).
  * The environment variable PNMOL_B200_PATH=warp|cta|large overrides the choice where the problem fits (used by

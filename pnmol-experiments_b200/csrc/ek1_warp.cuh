@@ -61,7 +61,7 @@ __device__ double update_stage_warp(const Problem& P, int b, const Smem& sm, con
     pc.mark(4);
     Shape sh;
     sh.nt = D; sh.nbot = nbot; sh.ncols = mcur + D; sh.te = te; sh.be = be;
-    householder_qr_warp(Wl, ld, sh, q);
+    householder_qr_warp(Wl, ld, sh, q, pc);
     pc.mark(5);
     const double diff = update_solve<WarpTeam>(P, sm, mcur, Wl, Wr);
     pc.mark(6);
@@ -95,7 +95,7 @@ __device__ double ek1_step_warp(const Problem& P, int b, int slot, const Smem& s
     pc.mark(1);
     Shape sp;
     sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p;
-    householder_qr_warp(W + (size_t)P.m * P.ld, P.ld, sp, q);
+    householder_qr_warp(W + (size_t)P.m * P.ld, P.ld, sp, q, pc);
     pc.mark(2);
     if (!P.latent && !(flags & 2)) {
         error_estimate<WarpTeam>(P, b, sm, sm.pv[1], dt, E_STEP_WHITE, 0.0, Hcol, Hval, P.F + (size_t)slot * P.m * P.d,

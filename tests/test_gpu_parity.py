@@ -84,7 +84,7 @@ def test_update_sqrt(m, D, noise):
 @pytest.mark.parametrize("name,kind,bcond,num", KIND_CASES)
 def test_initialize_and_steps_from_oracle_state(name, kind, bcond, num, path, monkeypatch):
     """Every step starts from the oracle's state: pure per-step parity (no error accumulation).  Both ensemble kernel
-    families (one warp per member, the default at these sizes; one CTA per member) on the same inputs."""
+    families (one CTA per member, the default; one warp per member, opt-in) on the same inputs."""
     monkeypatch.setenv("PNMOL_B200_PATH", path)
     _check_initialize_and_steps(name, kind, bcond, num, "warp" if path == "warp" else "single_cta")
 
