@@ -318,8 +318,8 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
         maxlen = std::max(maxlen, max_panel_len(P.D, P.latent ? 0 : P.m, P.m + P.D, te_u.data(), be_u.data()));
         maxlen = std::max(maxlen, max_panel_len(P.D, P.d, P.d + P.D, nullptr, nullptr));   // initialisation updates
         maxlen = std::max(maxlen, max_panel_len(P.D, P.m, P.m + P.D, nullptr, nullptr));
-        const int G = maxlen <= 64 ? 4 : maxlen <= 128 ? 8 : maxlen <= 256 ? 16 : 32;
-        P.vld = 16 * G;
+        const int G = maxlen <= 4 * kRPL ? 4 : maxlen <= 8 * kRPL ? 8 : maxlen <= 16 * kRPL ? 16 : 32;
+        P.vld = kRPL * G;
         P.ldm = P.m <= 96 ? (P.m | 1) : 0;  // odd leading dimension: conflict-free rows and columns
         h->smem_bytes = smem_doubles(P.D, P.m, P.dd, P.vld, P.ldm) * sizeof(double);
         const char* force = std::getenv("PNMOL_B200_FORCE_LARGE");

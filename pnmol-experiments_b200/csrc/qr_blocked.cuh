@@ -34,7 +34,11 @@ constexpr bool kUseDmmaTrailing = PNMOL_DMMA_TRAILING != 0;
 #define PNMOL_DMMA_PAIR 0
 #endif
 constexpr bool kUseDmmaPair = PNMOL_DMMA_PAIR != 0;  // warp-pair single-pass variant (measured slower: L2 access efficiency)
-constexpr int kRPL = 16;  // rows per lane (upper bound; chunks of 4 beyond the row list are skipped)
+#ifndef PNMOL_RPL
+#define PNMOL_RPL 8
+#endif
+constexpr int kRPL = PNMOL_RPL;  // rows per lane (upper bound; chunks of 4 beyond the row list are skipped)
+constexpr int kQ = kRPL / 4;
 
 struct RowMap {  // compact row list of a panel: c < len1 -> j0 + c, else a2 + (c - len1)
     int j0, len1, a2, len;
@@ -111,7 +115,7 @@ __device__ __forceinline__ void apply_reflector(const double (&v)[kRPL], double 
                                                 double tau) {
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < kQ; ++q) {
         if (q < nq) {
 #pragma unroll
             for (int rr = 0; rr < 4; rr += 2) {
@@ -127,7 +131,7 @@ __device__ __forceinline__ void apply_reflector(const double (&v)[kRPL], double 
     group_sum2<G>(d0, d1);
     const double w0 = -tau * d0, w1 = -tau * d1;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < kQ; ++q) {
         if (q < nq) {
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
@@ -328,6 +332,37 @@ __device__ __forceinline__ void panel_t_factor(const double* __restrict__ Gs, co
     }
 }
 
+// Tile fetch/store of the tensor-core trailing update.  An 8-row tile that lies entirely inside one segment of the
+// compact row list (the common case) is two unpredicated accesses at (segment base) + constant; only the tile that
+// straddles the segments and the last, partial tile take the per-element path.  `cp` points at the lane's column
+// (a valid dummy column for lanes beyond the matrix, which never store).
+__device__ __forceinline__ void tile_load(const double* __restrict__ cp, const RowMap& rm, int tb, int t, double& x0, double& x1) {
+    if (tb + 8 <= rm.len1) {
+        const double* p = cp + rm.j0 + tb + 2 * t;
+        x0 = p[0]; x1 = p[1];
+    } else if (tb >= rm.len1 && tb + 8 <= rm.len) {
+        const double* p = cp + (rm.a2 - rm.len1) + tb + 2 * t;
+        x0 = p[0]; x1 = p[1];
+    } else {
+        const int c0 = tb + 2 * t, c1 = c0 + 1;
+        x0 = c0 < rm.len ? cp[rm.row(c0)] : 0.0;
+        x1 = c1 < rm.len ? cp[rm.row(c1)] : 0.0;
+    }
+}
+__device__ __forceinline__ void tile_store(double* __restrict__ cp, const RowMap& rm, int tb, int t, double x0, double x1) {
+    if (tb + 8 <= rm.len1) {
+        double* p = cp + rm.j0 + tb + 2 * t;
+        p[0] = x0; p[1] = x1;
+    } else if (tb >= rm.len1 && tb + 8 <= rm.len) {
+        double* p = cp + (rm.a2 - rm.len1) + tb + 2 * t;
+        p[0] = x0; p[1] = x1;
+    } else {
+        const int c0 = tb + 2 * t, c1 = c0 + 1;
+        if (c0 < rm.len) cp[rm.row(c0)] = x0;
+        if (c1 < rm.len) cp[rm.row(c1)] = x1;
+    }
+}
+
 __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
                                            const double* __restrict__ Vs, int ldt, const double* __restrict__ Vr,
                                            const double* __restrict__ Ts) {
@@ -356,9 +391,8 @@ __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int n
             double xa[kCh][2];
 #pragma unroll
             for (int a = 0; a < kCh; ++a) {
-                const int c0 = 8 * (i0 + a) + 2 * t, c1 = c0 + 1;
-                xa[a][0] = (have && c0 < rm.len) ? cp[rm.row(c0)] : 0.0;
-                xa[a][1] = (have && c1 < rm.len) ? cp[rm.row(c1)] : 0.0;
+                xa[a][0] = 0.0; xa[a][1] = 0.0;
+                if (i0 + a < ntile) tile_load(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
             }
 #pragma unroll
             for (int a = 0; a < kCh; ++a) {
@@ -375,7 +409,7 @@ __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int n
 #pragma unroll
         for (int n = 0; n < 2; ++n)
 #pragma unroll
-            for (int q = 0; q < 2; ++q) yt[n][q] = y[0][n][q] + y[1][n][q];
+            for (int q = 0; q < 2; ++q) yt[n][q] = have ? y[0][n][q] + y[1][n][q] : 0.0;
         // ---- Y'^T = Y^T T
         double z[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
@@ -391,9 +425,8 @@ __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int n
             double xa[kCh][2];
 #pragma unroll
             for (int a = 0; a < kCh; ++a) {
-                const int c0 = 8 * (i0 + a) + 2 * t, c1 = c0 + 1;
-                xa[a][0] = (have && c0 < rm.len) ? cp[rm.row(c0)] : 0.0;
-                xa[a][1] = (have && c1 < rm.len) ? cp[rm.row(c1)] : 0.0;
+                xa[a][0] = 0.0; xa[a][1] = 0.0;
+                if (i0 + a < ntile) tile_load(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
             }
 #pragma unroll
             for (int a = 0; a < kCh; ++a) {
@@ -405,11 +438,10 @@ __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int n
                         for (int sx = 0; sx < 2; ++sx) dmma884(xa[a][0], xa[a][1], z[h][sx], vb[(8 * h + 2 * t + sx) * ldt]);
                 }
             }
+            if (have) {
 #pragma unroll
-            for (int a = 0; a < kCh; ++a) {
-                const int c0 = 8 * (i0 + a) + 2 * t, c1 = c0 + 1;
-                if (have && c0 < rm.len) cp[rm.row(c0)] = xa[a][0];
-                if (have && c1 < rm.len) cp[rm.row(c1)] = xa[a][1];
+                for (int a = 0; a < kCh; ++a)
+                    if (i0 + a < ntile) tile_store(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
             }
         }
     }
@@ -567,12 +599,11 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
             }
         }
         __syncthreads();
-        pc.mark(20);
         if (wlast < i) continue;  // no live panel column in this warp: only keep the barrier
         const double al = sc[3 * i + 1];
         double d0 = 0.0, ss = 0.0, d0b = 0.0, ssb = 0.0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < kQ; ++q) {
             if (q < nq) {
 #pragma unroll
                 for (int rr = 0; rr < 4; rr += 2) {
@@ -593,7 +624,6 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
         if (G < 8 && ri == 3) e0 = x0[3];
         e0 = __shfl_sync(0xffffffffu, e0, (lane & ~(G - 1)) | si);
         group_sum2<G>(d0, ss);
-        pc.mark(21);
         // dlarfg on (alpha, ||x||^2): beta = -sign(alpha) ||(alpha, x)||, tau = (beta - alpha) / beta, v = x / (alpha - beta)
         double tau = 0.0, beta = al, scale = 0.0;
         if (ss != 0.0) {  // zero sub-column -> H = I
@@ -604,7 +634,6 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
             tau = (beta - al) * -copysign(rn, al);
             scale = __drcp_rn(al - beta);
         }
-        pc.mark(22);
         if (own && sl == 0) sc[3 * i] = tau;
         if (own && tau == 0.0) {
 #pragma unroll
@@ -614,7 +643,7 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
             const double f0 = p0 > i && hp ? -tau * fma(scale, d0, e0) : 0.0;
             const double g0 = f0 * scale;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < kQ; ++q) {
                 if (q < nq) {
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
@@ -698,7 +727,7 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
                 double v[kRPL];
                 const double* vp = vbase + i * ldt;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < kQ; ++q) {
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) v[4 * q + rr] = q < nq ? vp[G * (4 * q + rr)] : 0.0;
                 }
@@ -730,13 +759,14 @@ __device__ void householder_qr_blocked(double* __restrict__ W, int ld, const Sha
     while (j0 < nref) {
         int nbk = nref - j0 < kNB ? nref - j0 : kNB;
         RowMap rm = panel_rows(s, j0, j0 + nbk - 1);
+        // lanes per column: the smallest group that holds the row list in kRPL rows per lane
         const int G = rm.len <= 4 * kRPL ? 4 : rm.len <= 8 * kRPL ? 8 : rm.len <= 16 * kRPL ? 16 : 32;
         const int cap = kWarps * (32 / G);  // panel columns the CTA can hold in registers (one per lane group)
         if (nbk > cap) {
             nbk = cap;
             rm = panel_rows(s, j0, j0 + nbk - 1);
         }
-        if (rm.len > 32 * kRPL || 16 * G > vld) {
+        if (rm.len > 32 * kRPL || kRPL * G > vld) {
             householder_columns(W, ld, s, j0, j0 + nbk, vbuf, red);
         } else if (G == 4) {
             qr_panel_step<4>(W, ld, s, j0, nbk, rm, Vs, vld, xraw, sc, Vr, Ts, Gs, scratch, pc);
