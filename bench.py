@@ -51,6 +51,12 @@ def member_parameters(num_members, x, seed):
     return y0, diff, prior
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of pnmol::k_run per member-step, from the committed `ncu --set full`
+# capture profiles/r01_ncu_k_run_full_summary_v5.csv (296 members x 8 steps per launch: 635 MB read + 2820 MB written).
+# Four times the algorithmic 363 KB: the L2-resident per-CTA workspaces are written back to HBM as dirty lines.
+NCU_DRAM_BYTES_PER_MEMBER_STEP = (635.245056e6 + 2819.685e6) / (296 * 8)
+
+
 def work_model(D, m, d):
     """Algorithmic bytes / flops per member-step."""
     b_alg = 8.0 * (2 * (D * D + D) + d + 2)
@@ -284,7 +290,10 @@ def run_b200_arm(args):
     ach_tf = f_alg * M * T / (kernel_ms * 1e-3) * 1e-12
     ach_gbs = b_alg * M * T / (kernel_ms * 1e-3) * 1e-9
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                "traffic": None, "kernel": "pnmol::k_run", "kernel_ms_per_launch": kernel_ms,
+                "traffic": NCU_DRAM_BYTES_PER_MEMBER_STEP * M * T,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per member-step "
+                                  "(profiles/r01_ncu_k_run_full_summary_v5.csv) x member-steps per launch",
+                "kernel": "pnmol::k_run", "kernel_ms_per_launch": kernel_ms,
                 "algorithmic_flops_per_member_step": f_alg, "algorithmic_bytes_per_member_step": b_alg,
                 "peak_source": "measured in this run: cuBLAS DGEMM 4096^3 via torch.matmul(float64), best of 5 "
                                "(tools/fp64_peak.cu measured DMMA 37.2 / DFMA 34.0 TFLOP/s on this pool)",
@@ -313,17 +322,59 @@ def run_b200_arm(args):
            "d2h_bytes_per_step": int(M * (D + D * D + 1) * 8 + M * 4),
            "includes": "H2D of y0, initialize (2 QR updates), 48-step time loop, rescale, D2H of means + factors"}
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        other = other_configs_timing(dev, fp64_peak)
+
     if rank == 0:
         line = {
             "metric": "ek1_filter_steps_per_sec", "value": value, "unit": "member-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, T), "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "other_configs": other,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs_timing(dev, fp64_peak):
+    """BASELINE configs C2-C4 (single large solves, multi-CTA kernels): device-timed ms per EK1 step, not part of
+    `value`.  C4 needs ~0.5 GB of workspace and a few hundred ms; everything here stays below ~10 s."""
+    import torch
+
+    import cases
+
+    configs = {"c2_sir_N100_white_semilinear": ("sir", "white_semilinear", "neumann", 100, 2.0 ** -3, "matern"),
+               "c3_spruce_N200_latent_semilinear": ("spruce", "latent_semilinear", "dirichlet", 200, 2.0 ** -4, "se"),
+               "c4_heat_N1024_white_linear": ("heat", "white_linear", "dirichlet", 1024, 2.0 ** -4, "se")}
+    out = {}
+    for name, (pname, kind, bcond, num, dt, prior) in configs.items():
+        try:
+            steps = 4 if num < 1000 else 2
+            case = cases.make_case(pname, num=num, bcond=bcond, dt=dt, prior=prior, tmax=steps * dt)
+            solver = cases.make_solver(kind, case)
+            s0 = solver.initialize(case["pde"])
+            eng = solver._engine
+            D, m = eng.D, eng.m
+            mean, chol = s0.y.mean.clone().reshape(1, eng.n, eng.dd), s0.y.cov_sqrtm.clone().reshape(1, D, D)
+            dts = np.full(steps, dt)
+            eng.run(case["pde"].t0, dts[:1], mean.clone(), chol.clone())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = eng.run(case["pde"].t0, dts, mean, chol)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            f_alg = work_model(D, m, eng.d)[1]
+            out[name] = {"D": D, "m": m, "path": eng.path, "ms_per_step": ms, "steps_per_sec": 1e3 / ms,
+                         "fp64_frac": f_alg / (ms * 1e-3) * 1e-12 / fp64_peak, "status": int(res["status"].max())}
+            del solver, eng, mean, chol, s0
+            torch.cuda.empty_cache()
+        except Exception as exc:  # never lose the headline line to a side measurement
+            out[name] = {"error": repr(exc)[:200]}
+    return out
 
 
 def main():
@@ -334,6 +385,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--members", type=int, default=4096, help="ensemble members per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the C2-C4 side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
