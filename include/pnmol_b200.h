@@ -152,6 +152,21 @@ int pnmol_b200_run(pnmol_b200_handle* h, double t0, const double* dts, const dou
                    double* chol_tmp, double* err_out, double* ref_out, double* diff_last, double* diff_sum,
                    double* mean_traj, double* chol_traj, int32_t* status, int flags, void* stream);
 
+/* Persistent multi-step run that returns MARGINALS instead of the factor trajectory:
+ * mean_traj dev [nsteps, batch, n, dd] and std_traj dev [nsteps, batch, dd] with
+ * std[j] = sqrt((E0 L L^T E0^T)[j][j]) = norm of row j n of the factor, the read-out of
+ * experiments/figure1.py:76-89 and figure3.py:87-93 (read_mean_and_std*), fused into the step kernel so that the
+ * T x D^2 factor trajectory of pnmol_b200_run is never written.  Other arguments as pnmol_b200_run. */
+int pnmol_b200_run_marginals(pnmol_b200_handle* h, double t0, const double* dts, const double* precond,
+                             const double* precond_inv, int nsteps, double* mean, double* chol, double* mean_tmp,
+                             double* chol_tmp, double* diff_last, double* diff_sum, double* mean_traj, double* std_traj,
+                             int32_t* status, int flags, void* stream);
+
+/* Marginal standard deviations of `count` factors: chol dev [count, D, D] -> std_out dev [count, D / (nu + 1)]
+ * (same read-out as above for states that already exist, e.g. the initial state or PDESolution.cov_sqrtm). */
+int pnmol_b200_marginal_std(const double* chol, double* std_out, int D, int num_derivatives, int count, int device,
+                            void* stream);
+
 /* cov_sqrtm <- cov_sqrtm * sqrt(mean of the local diffusions), the last line of
  * simulate_final_state (src/pnmol/pdefilter.py:113-116).  chol dev [batch, D, D] in place,
  * diff_sum dev [batch] as returned by pnmol_b200_run, diff_cal_out dev [batch] or NULL

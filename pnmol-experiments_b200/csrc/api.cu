@@ -506,10 +506,11 @@ int pnmol_b200_step(pnmol_b200_handle* h, double t_new, double dt, const double*
     return 0;
 }
 
-int pnmol_b200_run(pnmol_b200_handle* h, double t0, const double* dts, const double* precond, const double* precond_inv,
-                   int nsteps, double* mean, double* chol, double* mean_tmp, double* chol_tmp, double* err_out,
-                   double* ref_out, double* diff_last, double* diff_sum, double* mean_traj, double* chol_traj,
-                   int32_t* status, int flags, void* stream) {
+namespace {
+int run_common(pnmol_b200_handle* h, double t0, const double* dts, const double* precond, const double* precond_inv,
+               int nsteps, double* mean, double* chol, double* mean_tmp, double* chol_tmp, double* err_out, double* ref_out,
+               double* diff_last, double* diff_sum, double* mean_traj, double* chol_traj, double* std_traj,
+               int32_t* status, int flags, void* stream) {
     int rc = ensure_ready(h);
     if (rc) return rc;
     if (nsteps <= 0) return fail(-1, "nsteps must be positive");
@@ -520,8 +521,39 @@ int pnmol_b200_run(pnmol_b200_handle* h, double t0, const double* dts, const dou
     if ((rc = upload_steps(h, nsteps, t0, dts, precond, precond_inv, (cudaStream_t)stream, &a))) return rc;
     a.mean_a = mean; a.chol_a = chol; a.mean_b = mean_tmp; a.chol_b = chol_tmp;
     a.err_out = err_out; a.ref_out = ref_out; a.diff_last = diff_last; a.diff_sum = diff_sum;
-    a.mean_traj = mean_traj; a.chol_traj = chol_traj; a.status = status;
+    a.mean_traj = mean_traj; a.chol_traj = chol_traj; a.std_traj = std_traj; a.status = status;
     if ((rc = launch_run(h, a, (cudaStream_t)stream))) return rc;
+    CU(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+
+int pnmol_b200_run(pnmol_b200_handle* h, double t0, const double* dts, const double* precond, const double* precond_inv,
+                   int nsteps, double* mean, double* chol, double* mean_tmp, double* chol_tmp, double* err_out,
+                   double* ref_out, double* diff_last, double* diff_sum, double* mean_traj, double* chol_traj,
+                   int32_t* status, int flags, void* stream) {
+    return run_common(h, t0, dts, precond, precond_inv, nsteps, mean, chol, mean_tmp, chol_tmp, err_out, ref_out, diff_last,
+                      diff_sum, mean_traj, chol_traj, nullptr, status, flags, stream);
+}
+
+int pnmol_b200_run_marginals(pnmol_b200_handle* h, double t0, const double* dts, const double* precond,
+                             const double* precond_inv, int nsteps, double* mean, double* chol, double* mean_tmp,
+                             double* chol_tmp, double* diff_last, double* diff_sum, double* mean_traj, double* std_traj,
+                             int32_t* status, int flags, void* stream) {
+    if (!mean_traj || !std_traj) return fail(-1, "null trajectory buffer");
+    return run_common(h, t0, dts, precond, precond_inv, nsteps, mean, chol, mean_tmp, chol_tmp, nullptr, nullptr, diff_last,
+                      diff_sum, mean_traj, nullptr, std_traj, status, flags, stream);
+}
+
+int pnmol_b200_marginal_std(const double* chol, double* std_out, int D, int num_derivatives, int count, int device, void* stream) {
+    const int n = num_derivatives + 1;
+    if (!chol || !std_out || D <= 0 || n < 1 || D % n || count <= 0) return fail(-1, "invalid argument");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(-3, "no such CUDA device (libpnmol_b200 has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    k_marginal_std<<<std::min(count, 4 * 148), 256, 0, (cudaStream_t)stream>>>(chol, std_out, D, n, D / n, count);
+    ++g_launches;
     CU(cudaGetLastError());
     return 0;
 }

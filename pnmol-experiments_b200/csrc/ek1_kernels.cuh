@@ -11,7 +11,24 @@ struct RunArgs {
     double *mean_a, *chol_a, *mean_b, *chol_b;                // ping-pong state; step 0 reads a
     double *err_out, *ref_out, *diff_last, *diff_sum, *mean_traj, *chol_traj;
     int32_t* status;
+    double* std_traj;  // [nsteps][batch][dd] marginal standard deviations of the 0th derivative, or nullptr
 };
+
+// Fused marginal read-out (experiments/figure1.py:76-89, figure3.py:87-93: sqrt(diag(E0 L L^T E0^T))): the standard
+// deviation of state component j is the norm of row j n of the factor.  Warps [w0, w0 + nw) share the rows.
+__device__ __forceinline__ void marginal_std_rows(const double* __restrict__ chol, int D, int n, int dd, double* __restrict__ out,
+                                                  int w0, int nw) {
+    const int lane = threadIdx.x & 31;
+    for (int j = w0; j < dd; j += nw) {
+        const double* row = chol + (size_t)(j * n) * D;
+        double a0 = 0.0, a1 = 0.0;
+        int c = lane;
+        for (; c + 32 < D; c += 64) { a0 = fma(row[c], row[c], a0); a1 = fma(row[c + 32], row[c + 32], a1); }
+        if (c < D) a0 = fma(row[c], row[c], a0);
+        const double ssq = warp_sum(a0 + a1);
+        if (lane == 0) out[j] = sqrt(ssq);
+    }
+}
 
 struct InitArgs {
     const double* y0;
@@ -102,6 +119,7 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem 
                 double* ct = a.chol_traj + ((size_t)s * P.batch + b) * csz;
                 for (size_t k = tid; k < csz; k += kThreads) ct[k] = cout[k];
             }
+            if (a.std_traj) marginal_std_rows(cout, P.D, P.n, P.dd, a.std_traj + ((size_t)s * P.batch + b) * P.dd, tid >> 5, kWarps);
             __syncthreads();
         }
         if ((a.nsteps & 1) && !a.final_in_b) {  // result sits in b: bring it home
@@ -186,6 +204,12 @@ __global__ void k_rescale(double* chol, const double* diff_sum, double* diff_cal
     if (blockIdx.x == 0 && threadIdx.x == 0 && diff_cal) diff_cal[b] = cal;
     double* c = chol + (size_t)b * csz;
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < csz; k += (size_t)gridDim.x * blockDim.x) c[k] *= s;
+}
+
+// Stand-alone marginal read-out of `count` factors (D x D each): out[count][dd].
+__global__ void k_marginal_std(const double* chol, double* out, int D, int n, int dd, int count) {
+    for (int b = blockIdx.x; b < count; b += gridDim.x)
+        marginal_std_rows(chol + (size_t)b * D * D, D, n, dd, out + (size_t)b * dd, threadIdx.x >> 5, blockDim.x >> 5);
 }
 
 // K = Lk Lk^T (spatial Gram matrix), once per set_prior.

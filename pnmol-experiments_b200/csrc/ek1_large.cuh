@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_run_large(const Problem P, cons
                 double* ct = a.chol_traj + ((size_t)s * P.batch + b) * csz;
                 for (size_t k = gtid; k < csz; k += gnt) ct[k] = cout[k];
             }
+            if (a.std_traj) marginal_std_rows(cout, D, n, P.dd, a.std_traj + ((size_t)s * P.batch + b) * P.dd, gw, gnw);
         }
         if ((a.nsteps & 1) && !a.final_in_b) {  // result sits in b: bring it home
             const double* ms = a.mean_b + b * msz; const double* cs = a.chol_b + b * csz;

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256, 1) k_run_warp(const Problem P, const RunA
                 double* ct = a.chol_traj + ((size_t)s * P.batch + b) * csz;
                 for (size_t k = lane; k < csz; k += 32) ct[k] = cout[k];
             }
+            if (a.std_traj) marginal_std_rows(cout, P.D, P.n, P.dd, a.std_traj + ((size_t)s * P.batch + b) * P.dd, 0, 1);
             __syncwarp();
         }
         if ((a.nsteps & 1) && !a.final_in_b) {  // result sits in b: bring it home

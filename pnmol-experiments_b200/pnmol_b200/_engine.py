@@ -180,6 +180,28 @@ class Engine:
         out["_keepalive"] = (mean_tmp, chol_tmp)
         return out
 
+    def run_marginals(self, t0, dts, mean, chol, *, flags=0):
+        """Multi-step run that returns the mean trajectory and the marginal standard deviations of the 0th derivative
+        (fused read-out: the factor trajectory is never written).  mean/chol are updated in place to the final state."""
+        dts = np.ascontiguousarray(np.asarray(dts, dtype=np.float64))
+        T = len(dts)
+        pv, pinv = self._precond(dts)
+        assert mean.is_contiguous() and chol.is_contiguous()
+        mean_tmp, chol_tmp = torch.empty_like(mean), torch.empty_like(chol)
+        out = dict(diff_last=self._empty(self.batch), diff_sum=self._empty(self.batch),
+                   status=self._empty(self.batch, dtype=torch.int32),
+                   mean_traj=self._empty(T, self.batch, self.n, self.dd), std_traj=self._empty(T, self.batch, self.dd))
+        _lib.check(self.lib.pnmol_b200_run_marginals(
+            self.h, float(t0), _lib.ptr(dts), _lib.ptr(pv), _lib.ptr(pinv), T, _lib.ptr(mean), _lib.ptr(chol),
+            _lib.ptr(mean_tmp), _lib.ptr(chol_tmp), _lib.ptr(out["diff_last"]), _lib.ptr(out["diff_sum"]),
+            _lib.ptr(out["mean_traj"]), _lib.ptr(out["std_traj"]), _lib.ptr(out["status"]), int(flags), self._stream()))
+        out["_keepalive"] = (mean_tmp, chol_tmp)
+        return out
+
+    def marginal_std(self, chol):
+        """sqrt(diag(E0 L L^T E0^T)) for factors of shape (..., D, D) -> (..., dd)."""
+        return marginal_std(chol, self.nu)
+
     def rescale(self, chol, diff_sum, nsteps):
         cal = self._empty(self.batch)
         _lib.check(self.lib.pnmol_b200_rescale(self.h, _lib.ptr(chol), _lib.ptr(diff_sum), int(nsteps), _lib.ptr(cal),
@@ -201,6 +223,24 @@ class Engine:
             self.h, _lib.ptr(y0_host), float(t0), float(diffuse_prior_scale), _lib.ptr(dts), _lib.ptr(pv), _lib.ptr(pinv),
             len(dts), _lib.ptr(mean_host), _lib.ptr(chol_host), _lib.ptr(cal), _lib.ptr(status), int(flags), self._stream()))
         return mean_host, chol_host, cal, status
+
+
+def marginal_std(chol, num_derivatives):
+    """Marginal standard deviations of the 0th derivative: norm of every (nu+1)-th row of the factor (device kernel)."""
+    chol = torch.as_tensor(chol, dtype=torch.float64)
+    if not chol.is_cuda:
+        if not torch.cuda.is_available():
+            raise _lib.PnmolB200Error("pnmol_b200 needs a CUDA device: the read-out has no CPU fallback")
+        chol = chol.cuda()
+    chol = chol.contiguous()
+    D = chol.shape[-1]
+    n = num_derivatives + 1
+    lead = chol.shape[:-2]
+    count = int(np.prod(lead)) if len(lead) else 1
+    out = torch.empty((count, D // n), dtype=torch.float64, device=chol.device)
+    _lib.check(_lib.load().pnmol_b200_marginal_std(_lib.ptr(chol), _lib.ptr(out), D, int(num_derivatives), count,
+                                                   chol.device.index or 0, _lib.current_stream(chol.device)))
+    return out.reshape(*lead, D // n)
 
 
 def _as_host(x, shape):

@@ -125,6 +125,32 @@ class PDEFilter(ABC):
         cal = out["diff_sum"][0] / len(dts)
         return PDESolution(t=np.asarray(ts), mean=means, cov_sqrtm=covs, info=info, diffusion_squared_calibrated=cal)
 
+    def solve_marginals(self, pde):
+        """Like solve(), but returns MarginalSolution(t, mean (T+1, n, dd), std (T+1, dd), info, diffusion) -- the
+        marginal standard deviations of the 0th derivative instead of the factor trajectory (constant steps only;
+        the read-out is fused into the persistent step kernel)."""
+        from . import marginals
+
+        if not self._persistent_ok(None, False):
+            raise NotImplementedError("solve_marginals needs a Constant step rule")
+        state0 = self.initialize(pde)
+        dts = _engine.constant_step_schedule(pde.t0, pde.tmax, self.steprule.first_dt(pde))
+        eng = self._engine
+        mean = state0.y.mean[None].clone()
+        chol = state0.y.cov_sqrtm[None].clone()
+        std0 = eng.marginal_std(chol)
+        out = eng.run_marginals(pde.t0, dts, mean, chol)
+        ts = [pde.t0]
+        for h in dts:
+            ts.append(ts[-1] + h)
+        info = _new_info()
+        info.update(num_f_evaluations=len(dts), num_df_evaluations=len(dts), num_steps=len(dts),
+                    num_attempted_steps=len(dts))
+        means = torch.cat([state0.y.mean[None], out["mean_traj"][:, 0]])
+        stds = torch.cat([std0, out["std_traj"][:, 0]])
+        return marginals.MarginalSolution(t=np.asarray(ts), mean=means, std=stds, info=info,
+                                          diffusion_squared_calibrated=out["diff_sum"][0] / len(dts))
+
     def solution_generator(self, pde, /, *, stop_at=None, progressbar=False):
         """Generate solver steps (pdefilter.py:118-165)."""
         time_stopper = self._process_event_inputs(stop_at_locations=stop_at)

@@ -208,6 +208,39 @@ def test_simulate_final_state(kind, name, bcond):
     assert np.isfinite(ratio) and ratio > 0 and (kind.startswith("latent") or 0.2 < ratio < 5.0)
 
 
+@pytest.mark.parametrize("kind,name,path", [("white_linear", "heat", "cta"), ("latent_semilinear", "spruce", "cta"),
+                                            ("white_semilinear", "sir", "large"), ("white_linear", "heat", "warp")])
+def test_fused_marginal_readout(kind, name, path, monkeypatch):
+    """solve_marginals (std fused into the step kernel, no factor trajectory) equals the read-out of
+    experiments/figure1.py:76-89 applied to solve()'s full trajectory, and the oracle's marginals."""
+    from pnmol_b200 import marginals
+
+    monkeypatch.setenv("PNMOL_B200_PATH", path)
+    case = cases.make_case(name, num=7 if name != "sir" else 5, bcond="neumann" if name != "spruce" else "dirichlet", tmax=0.5)
+    n = case["nu"] + 1
+    sol = cases.make_solver(kind, case).solve(case["pde"])
+    marg = cases.make_solver(kind, case).solve_marginals(case["pde"])
+    assert np.array_equal(marg.t, np.asarray(sol.t)) and marg.info == sol.info
+    assert torch.equal(marg.mean, sol.mean)
+    L = _np(sol.cov_sqrtm)
+    want = np.sqrt(np.einsum("tij,tij->ti", L, L)[:, ::n])
+    assert marg.std.shape == want.shape
+    assert np.allclose(_np(marg.std), want, rtol=1e-13, atol=0)
+    assert float(marg.diffusion_squared_calibrated) == pytest.approx(float(sol.diffusion_squared_calibrated), rel=1e-12)
+    E0 = np.kron(np.eye(case["pde"].L.shape[0]), np.eye(n)[:1])
+    if kind.startswith("white"):
+        means, stds = marginals.read_mean_and_std(sol, E0)
+        assert torch.equal(means, sol.mean[:, 0]) and np.allclose(_np(stds), want, rtol=1e-13)
+    else:
+        means, stds = marginals.read_mean_and_std_latent(sol, E0)
+        d = E0.shape[0]
+        assert np.allclose(_np(stds), want[:, :d], rtol=1e-13) and torch.equal(means, sol.mean[:, 0, :d])
+    ref = ek1_np.solve(kind, case["opde"], case["dt"], case["nu"], case["gram_sqrtm"])
+    ref_std = np.sqrt(np.einsum("tij,tij->ti", ref.cov_sqrtm, ref.cov_sqrtm)[:, ::n])
+    big = ref_std > 1e-6 * ref_std.max()
+    assert np.allclose(_np(marg.std)[big], ref_std[big], rtol=1e-6)
+
+
 def test_dense_input_factor_and_adaptive_steps():
     from pnmol_b200 import pdefilter, white
     from pnmol_b200.base import rv
