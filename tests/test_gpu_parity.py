@@ -148,9 +148,14 @@ def _check_initialize_and_steps(name, kind, bcond, num, path):
             assert new.error_estimate is None and new.reference_state is None
 
 
-@pytest.mark.parametrize("name,kind,bcond,num", [c for c in KIND_CASES if not (c[1].startswith("latent") and c[2] == "neumann")])
-def test_solve_trajectory(name, kind, bcond, num):
-    """Free-running trajectory (exactly representable dt): solve() against the oracle's solve()."""
+TRAJ_CASES = [c for c in KIND_CASES if not (c[1].startswith("latent") and c[2] == "neumann")]
+
+
+@pytest.mark.parametrize("name,kind,bcond,num,path", [c + ("cta",) for c in TRAJ_CASES] + [c + ("large",) for c in TRAJ_CASES[::3]] +
+                         [c + ("warp",) for c in TRAJ_CASES[1::3]])
+def test_solve_trajectory(name, kind, bcond, num, path, monkeypatch):
+    """Free-running trajectory (exactly representable dt): solve() against the oracle's solve(), on every kernel family."""
+    monkeypatch.setenv("PNMOL_B200_PATH", path)
     case = cases.make_case(name, num=num, bcond=bcond, tmax=0.75)
     n = case["nu"] + 1
     sol = cases.make_solver(kind, case).solve(case["pde"])
@@ -189,8 +194,10 @@ def test_generator_path_equals_persistent_path_and_reference_time_grid():
         assert cases.mean_excess(_np(sol.mean[k]), ref.mean[k], spread=ref_eps.mean[k]) < 1
 
 
+@pytest.mark.parametrize("path", ["cta", "large"])
 @pytest.mark.parametrize("kind,name,bcond", [("white_linear", "heat", "neumann"), ("latent_semilinear", "spruce", "dirichlet")])
-def test_simulate_final_state(kind, name, bcond):
+def test_simulate_final_state(kind, name, bcond, path, monkeypatch):
+    monkeypatch.setenv("PNMOL_B200_PATH", path)
     case = cases.make_case(name, num=7, bcond=bcond, tmax=0.5)
     state, info = cases.make_solver(kind, case).simulate_final_state(case["pde"])
     (ref, cal), (ref_eps, _) = cases.oracle_pair(
@@ -330,9 +337,12 @@ def test_baseline_config_c4_full_size():
 
 
 # ------------------------------------------------------------------------- ensembles
-def test_ensemble_members_match_individual_oracle_solves():
+@pytest.mark.parametrize("path", ["cta", "large", "warp"])
+def test_ensemble_members_match_individual_oracle_solves(path, monkeypatch):
     from oracle import setup_np
     from pnmol_b200 import ensemble
+
+    monkeypatch.setenv("PNMOL_B200_PATH", path)
 
     case = cases.make_case("heat", num=9, tmax=0.5)
     pde, o = case["pde"], case["opde"]
