@@ -69,23 +69,22 @@ void compute_structure(int latent, int semilinear, int d, int n, int nb, int nco
     }
 }
 
-// Largest compact row list of any kNB-wide panel (mirrors panel_rows in qr_blocked.cuh).
-int max_panel_len(int nt, int nbot, int ncols, const int32_t* te, const int32_t* be) {
+// Largest compact row list of any kNB-wide panel (mirrors panel_rows in qr_blocked.cuh; ldr > 0: tile-aligned lists).
+int max_panel_len(int nt, int nbot, int ncols, const int32_t* te, const int32_t* be, int ldr = 0) {
     const int nrows = nt + nbot, nref = std::min(nrows, ncols);
     int best = 1;
     for (int j0 = 0; j0 < nref; j0 += kNB) {
         const int jl = std::min(j0 + kNB, nref) - 1;
         auto top = [&](int j) { return std::min(te ? te[j] : nt - 1, nt - 1); };
         auto bot = [&](int j) { return std::min(be ? be[j] : nrows - 1, nrows - 1); };
-        int len;
+        RowMap rm;
         if (j0 < nt) {
             const int jt = std::min(jl, nt - 1);
-            const int e1 = std::max(top(jt), jt), e2 = bot(jl);
-            len = e1 - j0 + 1 + (e2 >= nt ? e2 - nt + 1 : 0);
+            rm = make_row_map(nt, ldr, j0, std::max(top(jt), jt), bot(jl));
         } else {
-            len = std::max(bot(jl), jl) - j0 + 1;
+            rm = make_row_map(nt, ldr, j0, 0, std::max(bot(jl), jl));
         }
-        best = std::max(best, len);
+        best = std::max(best, rm.len);
     }
     return best;
 }
@@ -256,7 +255,7 @@ int pnmol_b200_create(pnmol_b200_handle** out, int kind, int d, int num_derivati
     P.D = n * P.dd;
     P.m = d + nb;
     P.batch = batch;
-    P.ld = 2 * P.D;
+    P.ld = 2 * P.D + 8;  // 8 spare rows per column: panel row lists are padded to whole 8-row tiles
     if (P.D < P.m) { delete h; return fail(-1, "update_sqrt needs D >= m (src/pnmol/base/sqrt.py:55-57)"); }
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -313,11 +312,11 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
     if ((rc = dev_upload(h, &P.be_u, be_u.data(), be_u.size()))) return rc;
     // panel geometry of the blocked QR: V buffer rows = 16 G for the largest row list (<= 512, else fallback)
     {
-        int maxlen = max_panel_len(P.D, P.D, P.D, te_p.data(), be_p.data());
-        maxlen = std::max(maxlen, max_panel_len(P.D, P.D, P.D, te_pd.data(), be_p.data()));
-        maxlen = std::max(maxlen, max_panel_len(P.D, P.latent ? 0 : P.m, P.m + P.D, te_u.data(), be_u.data()));
-        maxlen = std::max(maxlen, max_panel_len(P.D, P.d, P.d + P.D, nullptr, nullptr));   // initialisation updates
-        maxlen = std::max(maxlen, max_panel_len(P.D, P.m, P.m + P.D, nullptr, nullptr));
+        int maxlen = max_panel_len(P.D, P.D, P.D, te_p.data(), be_p.data(), P.ld);
+        maxlen = std::max(maxlen, max_panel_len(P.D, P.D, P.D, te_pd.data(), be_p.data(), P.ld));
+        maxlen = std::max(maxlen, max_panel_len(P.D, P.latent ? 0 : P.m, P.m + P.D, te_u.data(), be_u.data(), P.ld));
+        maxlen = std::max(maxlen, max_panel_len(P.D, P.d, P.d + P.D, nullptr, nullptr, P.ld));   // initialisation updates
+        maxlen = std::max(maxlen, max_panel_len(P.D, P.m, P.m + P.D, nullptr, nullptr, P.ld));
         const int G = maxlen <= 4 * kRPL ? 4 : maxlen <= 8 * kRPL ? 8 : maxlen <= 16 * kRPL ? 16 : 32;
         P.vld = kRPL * G;
         P.ldm = P.m <= 96 ? (P.m | 1) : 0;  // odd leading dimension: conflict-free rows and columns

@@ -70,6 +70,7 @@ struct Shape {  // QR row structure: rows [0,nt) top, [nt, nt+nbot) bottom
     int nt, nbot, ncols;
     const int32_t* te;  // nullptr = dense
     const int32_t* be;
+    int ldr = 0;  // > 0: rows that exist in every workspace column; panel row lists are then aligned to 8-row tiles
 };
 
 struct Smem {
@@ -818,7 +819,7 @@ __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, 
 
     pc.mark(4);
     Shape sh;
-    sh.nt = D; sh.nbot = nbot; sh.ncols = ncols; sh.te = te; sh.be = be;
+    sh.nt = D; sh.nbot = nbot; sh.ncols = ncols; sh.te = te; sh.be = be; sh.ldr = ld;
     householder_qr_blocked(Wl, ld, sh, sm.Vs, P.vld, sm.xraw, sm.sc, sm.Vr, sm.Ts, sm.Gs, qr_scratch(P, sm), sm.vbuf, sm.red, pc);
     pc.mark(5);
 

@@ -62,7 +62,7 @@ __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, doub
     build_predict(P, b, sm, chol_in, dense ? P.te_pd : P.te_p, W + (size_t)P.m * P.ld);
     pc.mark(1);
     Shape sp;
-    sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p;
+    sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p; sp.ldr = P.ld;
     householder_qr_blocked(W + (size_t)P.m * P.ld, P.ld, sp, sm.Vs, P.vld, sm.xraw, sm.sc, sm.Vr, sm.Ts, sm.Gs, qr_scratch(P, sm), sm.vbuf, sm.red, pc);
     pc.mark(2);
     if (!P.latent && !(flags & 2)) {
@@ -132,6 +132,10 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem 
             if (a.diff_last) a.diff_last[b] = diff_s;
             if (a.diff_sum) a.diff_sum[b] = diffsum;
             if (a.status) a.status[b] = nonfinite;
+        }
+        if (nonfinite) {  // rows outside the envelopes are read (times zero) by the tile-aligned trailing updates:
+            double* Wz = P.W + (size_t)blockIdx.x * P.ld * (P.m + P.D);  // do not leave NaNs behind for the next member
+            for (size_t k = tid; k < (size_t)P.ld * (P.m + P.D); k += kThreads) Wz[k] = 0.0;
         }
         __syncthreads();
     }

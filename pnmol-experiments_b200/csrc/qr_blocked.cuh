@@ -42,7 +42,8 @@ constexpr int kQ = kRPL / 4;
 
 struct RowMap {  // compact row list of a panel: c < len1 -> j0 + c, else a2 + (c - len1)
     int j0, len1, a2, len;
-    __device__ __forceinline__ int row(int c) const { return c + (c < len1 ? j0 : a2 - len1); }
+    bool aligned;  // every 8-row tile [8k, 8k+8) lies in one segment (or the segments are contiguous) and len % 8 == 0
+    __host__ __device__ __forceinline__ int row(int c) const { return c + (c < len1 ? j0 : a2 - len1); }
 };
 
 __device__ __forceinline__ int env_top(const Shape& s, int j) {
@@ -55,25 +56,58 @@ __device__ __forceinline__ int env_bot(const Shape& s, int j) {
     return e > last ? last : e;
 }
 
-__device__ __forceinline__ RowMap panel_rows(const Shape& s, int j0, int jl) {
+// Row list of the panel j0 .. jl.  With s.ldr > 0 the list is aligned to the 8-row tiles of the tensor-core trailing
+// update: the top segment is extended by real rows below its envelope (the reflectors are zero there, the trailing
+// update rewrites them unchanged) to a multiple of 8 rows -- or, when that reaches the bottom block, to the bottom
+// block itself, which makes the two segments one contiguous range -- and the end of the list likewise while the rows
+// exist in the column.  rm.aligned then says that every tile lies in one segment (or the segments are contiguous).
+__host__ __device__ __forceinline__ RowMap make_row_map(int nt, int ldr, int j0, int e1, int e2) {
+    // j0 < nt: e1 = last top row of the panel's union, e2 = env_bot(last column); else e2 = last row of the union
     RowMap rm;
     rm.j0 = j0;
+    int last;            // last workspace row of the list
+    bool single_top = false;
+    if (j0 < nt) {
+        int len1 = e1 - j0 + 1;
+        const int len2 = e2 >= nt ? e2 - nt + 1 : 0;
+        if (ldr > 0 && len2 > 0) {
+            const int pad1 = (-len1) & 7;
+            if (j0 + len1 + pad1 >= nt) len1 = nt - j0;  // reaches the bottom block: one contiguous range
+            else len1 += pad1;
+        }
+        rm.len1 = len1;
+        rm.a2 = nt;
+        rm.len = len1 + len2;
+        single_top = len2 == 0;
+        last = len2 > 0 ? nt + len2 - 1 : j0 + len1 - 1;
+    } else {
+        rm.len1 = 0;
+        rm.a2 = j0;
+        rm.len = e2 - j0 + 1;
+        last = e2;
+    }
+    rm.aligned = false;
+    if (ldr > 0) {
+        const int pad = (-rm.len) & 7;
+        if (last + pad < ldr) {
+            rm.len += pad;
+            if (single_top) rm.len1 += pad;
+        }
+        rm.aligned = (rm.len & 7) == 0 && ((rm.len1 & 7) == 0 || rm.a2 - rm.len1 == rm.j0 || rm.len1 == rm.len);
+    }
+    return rm;
+}
+
+__device__ __forceinline__ RowMap panel_rows(const Shape& s, int j0, int jl) {
     if (j0 < s.nt) {
         const int jt = jl < s.nt ? jl : s.nt - 1;
         int e1 = env_top(s, jt);
         if (e1 < jt) e1 = jt;
-        rm.len1 = e1 - j0 + 1;
-        rm.a2 = s.nt;
-        const int e2 = env_bot(s, jl);
-        rm.len = rm.len1 + (e2 >= s.nt ? e2 - s.nt + 1 : 0);
-    } else {
-        rm.len1 = 0;
-        rm.a2 = j0;
-        int e2 = env_bot(s, jl);
-        if (e2 < jl) e2 = jl;
-        rm.len = e2 - j0 + 1;
+        return make_row_map(s.nt, s.ldr, j0, e1, env_bot(s, jl));
     }
-    return rm;
+    int e2 = env_bot(s, jl);
+    if (e2 < jl) e2 = jl;
+    return make_row_map(s.nt, s.ldr, j0, 0, e2);
 }
 
 // Interleaved butterfly reductions inside a G-lane group.
@@ -336,12 +370,10 @@ __device__ __forceinline__ void panel_t_factor(const double* __restrict__ Gs, co
 // compact row list (the common case) is two unpredicated accesses at (segment base) + constant; only the tile that
 // straddles the segments and the last, partial tile take the per-element path.  `cp` points at the lane's column
 // (a valid dummy column for lanes beyond the matrix, which never store).
+template <bool ALIGNED>
 __device__ __forceinline__ void tile_load(const double* __restrict__ cp, const RowMap& rm, int tb, int t, double& x0, double& x1) {
-    if (tb + 8 <= rm.len1) {
-        const double* p = cp + rm.j0 + tb + 2 * t;
-        x0 = p[0]; x1 = p[1];
-    } else if (tb >= rm.len1 && tb + 8 <= rm.len) {
-        const double* p = cp + (rm.a2 - rm.len1) + tb + 2 * t;
+    if (ALIGNED) {  // every tile is (its segment's base) + constant
+        const double* p = cp + (tb < rm.len1 ? rm.j0 : rm.a2 - rm.len1) + tb + 2 * t;
         x0 = p[0]; x1 = p[1];
     } else {
         const int c0 = tb + 2 * t, c1 = c0 + 1;
@@ -349,12 +381,10 @@ __device__ __forceinline__ void tile_load(const double* __restrict__ cp, const R
         x1 = c1 < rm.len ? cp[rm.row(c1)] : 0.0;
     }
 }
+template <bool ALIGNED>
 __device__ __forceinline__ void tile_store(double* __restrict__ cp, const RowMap& rm, int tb, int t, double x0, double x1) {
-    if (tb + 8 <= rm.len1) {
-        double* p = cp + rm.j0 + tb + 2 * t;
-        p[0] = x0; p[1] = x1;
-    } else if (tb >= rm.len1 && tb + 8 <= rm.len) {
-        double* p = cp + (rm.a2 - rm.len1) + tb + 2 * t;
+    if (ALIGNED) {
+        double* p = cp + (tb < rm.len1 ? rm.j0 : rm.a2 - rm.len1) + tb + 2 * t;
         p[0] = x0; p[1] = x1;
     } else {
         const int c0 = tb + 2 * t, c1 = c0 + 1;
@@ -363,6 +393,7 @@ __device__ __forceinline__ void tile_store(double* __restrict__ cp, const RowMap
     }
 }
 
+template <bool ALIGNED>
 __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
                                            const double* __restrict__ Vs, int ldt, const double* __restrict__ Vr,
                                            const double* __restrict__ Ts) {
@@ -392,7 +423,7 @@ __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int n
 #pragma unroll
             for (int a = 0; a < kCh; ++a) {
                 xa[a][0] = 0.0; xa[a][1] = 0.0;
-                if (i0 + a < ntile) tile_load(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
+                if (i0 + a < ntile) tile_load<ALIGNED>(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
             }
 #pragma unroll
             for (int a = 0; a < kCh; ++a) {
@@ -426,7 +457,7 @@ __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int n
 #pragma unroll
             for (int a = 0; a < kCh; ++a) {
                 xa[a][0] = 0.0; xa[a][1] = 0.0;
-                if (i0 + a < ntile) tile_load(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
+                if (i0 + a < ntile) tile_load<ALIGNED>(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
             }
 #pragma unroll
             for (int a = 0; a < kCh; ++a) {
@@ -441,7 +472,7 @@ __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int n
             if (have) {
 #pragma unroll
                 for (int a = 0; a < kCh; ++a)
-                    if (i0 + a < ntile) tile_store(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
+                    if (i0 + a < ntile) tile_store<ALIGNED>(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
             }
         }
     }
@@ -696,7 +727,8 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
             __syncthreads();
             pc.mark(14);
             if (kUseDmmaPair && rm.len <= 16 * kHalf) trailing_dmma_pair(W, ld, s.ncols, j0, nbk, rm, Vs, ldt, Vr, Ts, scratch, pc);
-            else trailing_dmma(W, ld, s.ncols, j0, nbk, rm, Vs, ldt, Vr, Ts);
+            else if (rm.aligned) trailing_dmma<true>(W, ld, s.ncols, j0, nbk, rm, Vs, ldt, Vr, Ts);
+            else trailing_dmma<false>(W, ld, s.ncols, j0, nbk, rm, Vs, ldt, Vr, Ts);
         }
     } else
     if (kUseWyTrailing && rm.len <= 256) {
