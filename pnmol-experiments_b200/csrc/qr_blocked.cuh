@@ -393,6 +393,54 @@ __device__ __forceinline__ void tile_store(double* __restrict__ cp, const RowMap
     }
 }
 
+// One chunk of kCh tiles of the two passes (FULL: all kCh tiles exist, no per-tile guards).
+template <bool ALIGNED, bool FULL>
+__device__ __forceinline__ void trailing_pass1_chunk(const double* __restrict__ cp, const RowMap& rm, int i0, int ntile, int g, int t,
+                                                     const double* __restrict__ Vr, double (&y)[2][2][2]) {
+    double xa[kCh][2];
+#pragma unroll
+    for (int a = 0; a < kCh; ++a) {
+        xa[a][0] = 0.0; xa[a][1] = 0.0;
+        if (FULL || i0 + a < ntile) tile_load<ALIGNED>(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
+    }
+#pragma unroll
+    for (int a = 0; a < kCh; ++a) {
+        if (FULL || i0 + a < ntile) {
+            const double* v0 = Vr + (8 * (i0 + a) + 2 * t) * kLdr + g;
+            dmma884(y[0][0][0], y[0][0][1], xa[a][0], v0[0]);
+            dmma884(y[0][1][0], y[0][1][1], xa[a][0], v0[8]);
+            dmma884(y[1][0][0], y[1][0][1], xa[a][1], v0[kLdr]);
+            dmma884(y[1][1][0], y[1][1][1], xa[a][1], v0[kLdr + 8]);
+        }
+    }
+}
+template <bool ALIGNED, bool FULL>
+__device__ __forceinline__ void trailing_pass2_chunk(double* __restrict__ cp, const RowMap& rm, int i0, int ntile, int g, int t, bool have,
+                                                     const double* __restrict__ Vs, int ldt, const double (&z)[2][2]) {
+    double xa[kCh][2];
+#pragma unroll
+    for (int a = 0; a < kCh; ++a) {
+        xa[a][0] = 0.0; xa[a][1] = 0.0;
+        if (FULL || i0 + a < ntile) tile_load<ALIGNED>(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
+    }
+    const double* vt = Vs + (2 * t) * ldt + g;
+#pragma unroll
+    for (int a = 0; a < kCh; ++a) {
+        if (FULL || i0 + a < ntile) {
+            const double* vb = vt + 8 * (i0 + a);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int sx = 0; sx < 2; ++sx) dmma884(xa[a][0], xa[a][1], z[h][sx], vb[(8 * h + sx) * ldt]);
+        }
+    }
+    if (have) {
+#pragma unroll
+        for (int a = 0; a < kCh; ++a)
+            if (FULL || i0 + a < ntile) tile_store<ALIGNED>(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
+    }
+}
+
 template <bool ALIGNED>
 __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
                                            const double* __restrict__ Vs, int ldt, const double* __restrict__ Vr,
@@ -418,24 +466,9 @@ __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int n
         for (int e = 0; e < 2; ++e)
 #pragma unroll
             for (int n = 0; n < 2; ++n) { y[e][n][0] = 0.0; y[e][n][1] = 0.0; }
-        for (int i0 = 0; i0 < ntile; i0 += kCh) {
-            double xa[kCh][2];
-#pragma unroll
-            for (int a = 0; a < kCh; ++a) {
-                xa[a][0] = 0.0; xa[a][1] = 0.0;
-                if (i0 + a < ntile) tile_load<ALIGNED>(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
-            }
-#pragma unroll
-            for (int a = 0; a < kCh; ++a) {
-                if (i0 + a < ntile) {
-                    const double* v0 = Vr + (8 * (i0 + a) + 2 * t) * kLdr + g;
-                    dmma884(y[0][0][0], y[0][0][1], xa[a][0], v0[0]);
-                    dmma884(y[0][1][0], y[0][1][1], xa[a][0], v0[8]);
-                    dmma884(y[1][0][0], y[1][0][1], xa[a][1], v0[kLdr]);
-                    dmma884(y[1][1][0], y[1][1][1], xa[a][1], v0[kLdr + 8]);
-                }
-            }
-        }
+        int i0 = 0;
+        for (; i0 + kCh <= ntile; i0 += kCh) trailing_pass1_chunk<ALIGNED, true>(cp, rm, i0, ntile, g, t, Vr, y);
+        if (i0 < ntile) trailing_pass1_chunk<ALIGNED, false>(cp, rm, i0, ntile, g, t, Vr, y);
         double yt[2][2];  // Y^T[col g][reflectors 8n + 2t, 8n + 2t + 1]
 #pragma unroll
         for (int n = 0; n < 2; ++n)
@@ -452,29 +485,8 @@ __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int n
 #pragma unroll
         for (int n = 0; n < 2; ++n) { z[n][0] = -z[n][0]; z[n][1] = -z[n][1]; }
         // ---- C^T -= Y'^T V^T, again in chunks of kCh tiles
-        for (int i0 = 0; i0 < ntile; i0 += kCh) {
-            double xa[kCh][2];
-#pragma unroll
-            for (int a = 0; a < kCh; ++a) {
-                xa[a][0] = 0.0; xa[a][1] = 0.0;
-                if (i0 + a < ntile) tile_load<ALIGNED>(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
-            }
-#pragma unroll
-            for (int a = 0; a < kCh; ++a) {
-                if (i0 + a < ntile) {
-                    const double* vb = Vs + 8 * (i0 + a) + g;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int sx = 0; sx < 2; ++sx) dmma884(xa[a][0], xa[a][1], z[h][sx], vb[(8 * h + 2 * t + sx) * ldt]);
-                }
-            }
-            if (have) {
-#pragma unroll
-                for (int a = 0; a < kCh; ++a)
-                    if (i0 + a < ntile) tile_store<ALIGNED>(cp, rm, 8 * (i0 + a), t, xa[a][0], xa[a][1]);
-            }
-        }
+        for (i0 = 0; i0 + kCh <= ntile; i0 += kCh) trailing_pass2_chunk<ALIGNED, true>(cp, rm, i0, ntile, g, t, have, Vs, ldt, z);
+        if (i0 < ntile) trailing_pass2_chunk<ALIGNED, false>(cp, rm, i0, ntile, g, t, have, Vs, ldt, z);
     }
 }
 
