@@ -631,7 +631,7 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
         if (warp + kWarps * gg < nbk) wlast = warp + kWarps * gg;
     for (int i = 0; i < nbk; ++i) {
         const bool own = hp && p0 == i;
-        const int ri = i / G, si = i % G;  // register slot and lane that hold row i  (ri < 16 / G <= 4)
+        const int ri = G >= kNB ? 0 : i / G, si = G >= kNB ? i : i % G;  // register slot and lane that hold row i (slot 0 for G >= 16: compile time)
         double* xr = xraw + (i & 1) * vld;  // double buffered: the next owner may publish while others still read
         if (own) {
 #pragma unroll
