@@ -162,6 +162,20 @@ int pnmol_b200_run_marginals(pnmol_b200_handle* h, double t0, const double* dts,
                              double* chol_tmp, double* diff_last, double* diff_sum, double* mean_traj, double* std_traj,
                              int32_t* status, int flags, void* stream);
 
+/* Adaptive time loop on the device: solution_generator + perform_full_step with
+ * step.Adaptive (src/pnmol/pdefilter.py:118-227, src/pnmol/odetools/step.py:58-119) for every member, each with its own
+ * step size; accept/reject, the step-size proposal and the Nordsieck preconditioner are evaluated in the kernel.
+ * White-noise solvers on the CTA-per-member path only (-4 otherwise: use pnmol_b200_step from a host loop).
+ *   dt0 dev [batch] first step (Adaptive.first_dt), mean/chol dev: state at t0 in, state at tmax out (unscaled factor;
+ *   pnmol_b200_rescale applies the calibration with nsteps = num_steps), *_tmp scratch of the same shapes,
+ *   t_out/dt_out/diff_sum/diff_last dev [batch], num_steps/num_attempts/status dev int32 [batch]
+ *   (status bit 0: non-finite state, bit 1: max_attempts reached before tmax). */
+int pnmol_b200_run_adaptive(pnmol_b200_handle* h, double t0, double tmax, const double* dt0, double abstol, double reltol,
+                            double change_min, double change_max, double safety_scale, int max_attempts, double* mean,
+                            double* chol, double* mean_tmp, double* chol_tmp, double* t_out, double* dt_out,
+                            double* diff_sum, double* diff_last, int32_t* num_steps, int32_t* num_attempts,
+                            int32_t* status, int flags, void* stream);
+
 /* Marginal standard deviations of `count` factors: chol dev [count, D, D] -> std_out dev [count, D / (nu + 1)]
  * (same read-out as above for states that already exist, e.g. the initial state or PDESolution.cov_sqrtm). */
 int pnmol_b200_marginal_std(const double* chol, double* std_out, int D, int num_derivatives, int count, int device,

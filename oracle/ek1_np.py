@@ -232,3 +232,39 @@ def simulate_final_state(kind, prob, dt, nu, gram_sqrtm, prior_scale=1.0):
             diffs.append(st.diffusion_squared_local)
     cal = np.mean(np.array(diffs))
     return st._replace(cov_sqrtm=st.cov_sqrtm * np.sqrt(cal)), cal
+
+
+def adaptive_first_dt(prob, semilinear=False):
+    """``Adaptive.first_dt`` (odetools/step.py:103-133): 0.01 ||y0|| / ||f(t0, y0)||."""
+    dy0 = prob.f(prob.t0, prob.y0) if semilinear else prob.L @ prob.y0
+    return 0.01 * np.linalg.norm(prob.y0) / np.linalg.norm(dy0)
+
+
+def simulate_final_state_adaptive(kind, prob, nu, gram_sqrtm, *, abstol=1e-4, reltol=1e-2, max_changes=(0.2, 10.0),
+                                  safety_scale=0.95, prior_scale=1.0, first_dt=None):
+    """``PDEFilter.simulate_final_state`` with ``step.Adaptive`` (pdefilter.py:105-227, odetools/step.py:58-119):
+    returns (final state with the factor rescaled, calibration, info)."""
+    init, step, semil = KINDS[kind]
+    state = init(prob, nu, gram_sqrtm, prior_scale, semil)
+    dt = adaptive_first_dt(prob, semil) if first_dt is None else first_dt
+    diffs, nsteps, nattempts = [], 0, 0
+    small, large = max_changes
+    while state.t < prob.tmax:
+        accepted = False
+        while not accepted:
+            proposed = step(prob, state, dt, nu, gram_sqrtm, semil)
+            nattempts += 1
+            ratio = (dt * proposed.error_estimate) / (abstol + reltol * proposed.reference_state)
+            norm = np.linalg.norm(ratio) / np.sqrt(ratio.size)
+            accepted = bool(norm < 1)
+            change = safety_scale * (1.0 / norm) ** (1.0 / (nu + 1))
+            suggested = max(small, min(change, large)) * dt
+            dt = min(suggested, prob.tmax - (proposed.t if accepted else state.t))
+            assert dt >= 0, f"Invalid step size: dt={dt}"
+        state = proposed
+        nsteps += 1
+        diffs.append(state.diffusion_squared_local)
+    cal = np.mean(np.array(diffs))
+    info = dict(num_f_evaluations=nattempts, num_df_evaluations=nattempts, num_df_diagonal_evaluations=0,
+                num_steps=nsteps, num_attempted_steps=nattempts)
+    return state._replace(cov_sqrtm=state.cov_sqrtm * np.sqrt(cal)), cal, info

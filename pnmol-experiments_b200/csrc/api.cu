@@ -126,6 +126,7 @@ struct pnmol_b200_handle {
     double *hs_y0 = nullptr, *hs_mean_a = nullptr, *hs_mean_b = nullptr, *hs_chol_a = nullptr, *hs_chol_b = nullptr,
            *hs_diffsum = nullptr, *hs_diffcal = nullptr;
     int32_t* hs_status = nullptr;
+    double *hs_err = nullptr, *hs_ref = nullptr;  // scratch of pnmol_b200_run_adaptive
     // multi-CTA path for large state dimension (ek1_large.cuh): chosen when the single-CTA kernels' shared memory
     // does not fit (or PNMOL_B200_FORCE_LARGE=1, used by the parity tests to run both paths on the same inputs)
     bool large = false;
@@ -271,7 +272,7 @@ int pnmol_b200_destroy(pnmol_b200_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->steparr) cudaFree(h->steparr);
     for (void* p : {(void*)h->hs_y0, (void*)h->hs_mean_a, (void*)h->hs_mean_b, (void*)h->hs_chol_a, (void*)h->hs_chol_b,
-                    (void*)h->hs_diffsum, (void*)h->hs_diffcal, (void*)h->hs_status})
+                    (void*)h->hs_diffsum, (void*)h->hs_diffcal, (void*)h->hs_status, (void*)h->hs_err, (void*)h->hs_ref})
         if (p) cudaFree(p);
     delete h;
     return 0;
@@ -542,6 +543,38 @@ int pnmol_b200_run_marginals(pnmol_b200_handle* h, double t0, const double* dts,
     if (!mean_traj || !std_traj) return fail(-1, "null trajectory buffer");
     return run_common(h, t0, dts, precond, precond_inv, nsteps, mean, chol, mean_tmp, chol_tmp, nullptr, nullptr, diff_last,
                       diff_sum, mean_traj, nullptr, std_traj, status, flags, stream);
+}
+
+int pnmol_b200_run_adaptive(pnmol_b200_handle* h, double t0, double tmax, const double* dt0, double abstol, double reltol,
+                            double change_min, double change_max, double safety_scale, int max_attempts, double* mean,
+                            double* chol, double* mean_tmp, double* chol_tmp, double* t_out, double* dt_out,
+                            double* diff_sum, double* diff_last, int32_t* num_steps, int32_t* num_attempts,
+                            int32_t* status, int flags, void* stream) {
+    int rc = ensure_ready(h);
+    if (rc) return rc;
+    if (h->P.latent) return fail(-1, "adaptive steps need an error estimate: white-noise solvers only (src/pnmol/latent.py:217-223)");
+    if (h->large || h->warp) return fail(-4, "the on-device adaptive loop is served by the CTA-per-member kernels only");
+    if (!dt0 || !mean || !chol || !mean_tmp || !chol_tmp || !t_out || !dt_out || !diff_sum || !diff_last || !num_steps ||
+        !num_attempts || !status)
+        return fail(-1, "null argument");
+    if (!(tmax > t0) || max_attempts <= 0) return fail(-1, "invalid time span or attempt limit");
+    const Problem& P = h->P;
+    if (!h->hs_err) {
+        CU(cudaMalloc((void**)&h->hs_err, sizeof(double) * P.batch * P.d));
+        CU(cudaMalloc((void**)&h->hs_ref, sizeof(double) * P.batch * P.d));
+    }
+    AdaptiveArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.t0 = t0; a.tmax = tmax; a.abstol = abstol; a.reltol = reltol; a.change_min = change_min; a.change_max = change_max;
+    a.safety = safety_scale; a.inv_rate = 1.0 / (double)P.n;  // local convergence rate = num_derivatives + 1 (pdefilter.py:215)
+    a.dt0 = dt0; a.mean_a = mean; a.chol_a = chol; a.mean_b = mean_tmp; a.chol_b = chol_tmp;
+    a.err = h->hs_err; a.ref = h->hs_ref; a.t_out = t_out; a.dt_out = dt_out; a.diff_sum = diff_sum; a.diff_last = diff_last;
+    a.nsteps = num_steps; a.nattempts = num_attempts; a.status = status; a.max_attempts = max_attempts; a.flags = flags;
+    CU(cudaFuncSetAttribute(k_run_adaptive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    k_run_adaptive<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
 }
 
 int pnmol_b200_marginal_std(const double* chol, double* std_out, int D, int num_derivatives, int count, int device, void* stream) {

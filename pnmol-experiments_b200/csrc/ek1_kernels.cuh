@@ -141,6 +141,101 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem 
     }
 }
 
+// Adaptive time loop on the device (src/pnmol/pdefilter.py:118-227 with src/pnmol/odetools/step.py:58-119): every
+// member advances with its own step size, accept/reject and step-size proposal happen in the kernel.  White-noise
+// solvers only (the latent-force solvers return no error estimate, src/pnmol/latent.py:217-223).
+struct AdaptiveArgs {
+    double t0, tmax, abstol, reltol, change_min, change_max, safety, inv_rate;
+    const double* dt0;            // [batch] first step size (step.py:103-133, computed on the host)
+    double *mean_a, *chol_a, *mean_b, *chol_b;   // current state in a; b is the proposal buffer
+    double *err, *ref;            // [batch][d] scratch: error estimate and reference state of the proposal
+    double *t_out, *dt_out, *diff_sum, *diff_last;   // [batch]
+    int32_t *nsteps, *nattempts, *status;            // [batch]; status: 1 non-finite, 2 attempt limit reached
+    int max_attempts, flags;
+};
+
+__global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run_adaptive(const Problem P, const AdaptiveArgs a) {
+    extern __shared__ double smem_raw[];
+    const Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm);
+    __shared__ int nonfinite;
+    __shared__ double diff_s;
+    for (double* q = sm.xraw + threadIdx.x; q < sm.Gs + 272; q += kThreads) *q = 0.0;  // reflector buffers start finite
+    const int tid = threadIdx.x;
+    const int nu = P.n - 1;
+    const size_t msz = (size_t)P.D, csz = (size_t)P.D * P.D;
+    for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+        if (tid == 0) nonfinite = 0;
+        double t = a.t0, dt = a.dt0[b], diffsum = 0.0, difflast = 0.0;
+        int nsteps = 0, natt = 0, cur = 0, stat = 0;
+        double* err = a.err + (size_t)b * P.d;
+        double* ref = a.ref + (size_t)b * P.d;
+        __syncthreads();
+        while (t < a.tmax) {
+            if (natt >= a.max_attempts) { stat |= 2; break; }
+            if (!(dt >= 0.0)) { stat |= 1; break; }  // pdefilter.py:225 asserts dt >= 0 (a NaN proposal ends here too)
+            // Nordsieck preconditioner p_i = |dt|^(nu - i + 1/2) / (nu - i)!   (iwp.py:55-62)
+            if (tid < P.n) {
+                const int k = nu - tid;
+                double fact = 1.0;
+                for (int q = 2; q <= k; ++q) fact *= q;
+                const double pw = pow(fabs(dt), k + 0.5);
+                sm.pv[tid] = pw / fact;
+                sm.pinv[tid] = fact / pw;
+            }
+            __syncthreads();
+            const double* min_ = (cur ? a.mean_b : a.mean_a) + b * msz;
+            const double* cin_ = (cur ? a.chol_b : a.chol_a) + b * csz;
+            double* mout = (cur ? a.mean_a : a.mean_b) + b * msz;
+            double* cout = (cur ? a.chol_a : a.chol_b) + b * csz;
+            const int flags = (natt == 0 || nsteps == 0) ? a.flags : (a.flags & ~1);  // only a user-supplied factor may be dense
+            ek1_step(P, b, blockIdx.x, sm, dt, t + dt, min_, cin_, mout, cout, err, ref, &diff_s, flags, &nonfinite);
+            __syncthreads();
+            // scaled error norm (step.py:97-108 on dt * error_estimate, pdefilter.py:208-213)
+            double part = 0.0;
+            for (int i = tid; i < P.d; i += kThreads) {
+                const double r = dt * err[i] / (a.abstol + a.reltol * ref[i]);
+                part = fma(r, r, part);
+            }
+            const double norm = sqrt(block_sum(part, sm.red)) / sqrt((double)P.d);
+            double change = a.safety * pow(1.0 / norm, a.inv_rate);
+            change = fmax(a.change_min, fmin(change, a.change_max));
+            if (!(norm == norm)) change = norm;  // NaN propagates like jnp.minimum / jnp.maximum
+            const double suggested = change * dt;
+            ++natt;
+            if (norm < 1.0) {  // accepted: the proposal becomes the state
+                t = t + dt;
+                cur ^= 1;
+                ++nsteps;
+                difflast = diff_s;
+                diffsum += diff_s;
+                dt = fmin(suggested, a.tmax - t);
+                if (!(suggested == suggested)) dt = suggested;
+            } else {
+                dt = fmin(suggested, a.tmax - t);
+                if (!(suggested == suggested)) dt = suggested;
+                if (tid == 0) nonfinite = 0;  // a rejected proposal may be non-finite without harm
+            }
+            __syncthreads();
+        }
+        if (cur) {  // bring the final state home
+            const double* ms = a.mean_b + b * msz; const double* cs = a.chol_b + b * csz;
+            double* md = a.mean_a + b * msz; double* cd = a.chol_a + b * csz;
+            for (size_t k = tid; k < msz; k += kThreads) md[k] = ms[k];
+            for (size_t k = tid; k < csz; k += kThreads) cd[k] = cs[k];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            a.t_out[b] = t; a.dt_out[b] = dt; a.diff_sum[b] = diffsum; a.diff_last[b] = difflast;
+            a.nsteps[b] = nsteps; a.nattempts[b] = natt; a.status[b] = stat | (nonfinite ? 1 : 0);
+        }
+        if (nonfinite || stat) {
+            double* Wz = P.W + (size_t)blockIdx.x * P.ld * (P.m + P.D);
+            for (size_t k = tid; k < (size_t)P.ld * (P.m + P.D); k += kThreads) Wz[k] = 0.0;
+        }
+        __syncthreads();
+    }
+}
+
 // initialize(): two square-root updates on a Kronecker-structured prior factor.
 __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_init(const Problem P, const InitArgs a) {
     extern __shared__ double smem_raw[];

@@ -41,13 +41,23 @@ class EnsembleSolver:
     """Binds a solver (its kind, order, prior kernel, constant step) to an ensemble of one problem."""
 
     def __init__(self, solver, pde, *, y0=None, diff_scale=None, prior_scale=None, reaction_params=None, device=None):
-        if not isinstance(solver.steprule, _step.Constant):
-            raise NotImplementedError("ensembles run with constant steps (per-member adaptive steps are a next step)")
+        self.adaptive = isinstance(solver.steprule, _step.Adaptive)
+        if self.adaptive and (solver.family != "white" or getattr(pde, "is_semilinear", False)):
+            raise NotImplementedError("adaptive ensembles: linear white-noise solvers (per-member first_dt needs L y0)")
         y0 = np.asarray(pde.y0 if y0 is None else y0, dtype=np.float64)
         self.y0 = np.ascontiguousarray(y0.reshape(-1, pde.y0.shape[0]))
         self.batch = self.y0.shape[0]
         self.solver, self.pde = solver, pde
-        self.dts = _engine.constant_step_schedule(pde.t0, pde.tmax, solver.steprule.first_dt(pde))
+        if self.adaptive:
+            # Adaptive.first_dt per member (odetools/step.py:103-133): 0.01 ||y0|| / ||diff_scale L y0||
+            ds = np.ones((self.batch, 1)) if diff_scale is None else np.asarray(diff_scale, dtype=np.float64).reshape(self.batch, -1)
+            ncomp = getattr(pde, "num_components", 1)
+            rows = np.repeat(np.broadcast_to(ds, (self.batch, ncomp)), pde.L.shape[0] // ncomp, axis=1)
+            dy0 = rows * (self.y0 @ np.asarray(pde.L, dtype=np.float64).T)
+            self.dt0 = 0.01 * np.linalg.norm(self.y0, axis=1) / np.linalg.norm(dy0, axis=1)
+            self.dts = np.zeros(0)
+        else:
+            self.dts = _engine.constant_step_schedule(pde.t0, pde.tmax, solver.steprule.first_dt(pde))
         self.engine = _engine.Engine(pde, family=solver.family, num_derivatives=solver.num_derivatives,
                                      gram_sqrtm=solver._gram_sqrtm(pde), batch=self.batch, device=device,
                                      diff_scale=diff_scale, prior_scale=prior_scale, reaction_params=reaction_params)
@@ -66,6 +76,14 @@ class EnsembleSolver:
     def simulate_final_state(self, *, rescale=True, flags=0):
         """Device-resident route: returns CUDA tensors."""
         mean, chol, status0 = self.initialize()
+        if self.adaptive:  # every member with its own step sizes, accept/reject on the device
+            out = self.engine.run_adaptive(self.pde.t0, self.pde.tmax, self.dt0, self.solver.steprule, mean, chol, flags=flags)
+            cal = out["diff_sum"] / out["num_steps"]
+            if rescale:
+                self.engine.rescale(chol, cal, 1)
+            res = EnsembleResult(out["t"], mean, chol, cal, torch.maximum(status0, out["status"]), out["num_steps"])
+            self.last_adaptive = out
+            return res
         out = self.engine.run(self.pde.t0, self.dts, mean, chol, flags=flags)
         if rescale:
             cal = self.engine.rescale(chol, out["diff_sum"], len(self.dts))

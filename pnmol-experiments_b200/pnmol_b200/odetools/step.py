@@ -1,9 +1,10 @@
 """Step-size selection (src/pnmol/odetools/step.py).
 
 ``Constant`` (step.py:30-55) is what every configuration of the hot path uses.
-``Adaptive`` (step.py:58-119) is host-side scalar logic on top of the error estimate the
-white-noise step returns; it is kept for API parity and runs one ``attempt_step`` launch
-per trial step.
+``Adaptive`` (step.py:58-119): ``simulate_final_state`` of the white-noise solvers and adaptive
+ensembles evaluate it inside the persistent kernel (``pnmol_b200_run_adaptive``); ``solve`` and
+``solution_generator`` (variable-length trajectories) use the host-side scalar logic below, one
+``attempt_step`` launch per trial step.
 """
 import numpy as np
 

@@ -12,6 +12,8 @@ from abc import ABC, abstractmethod
 from collections import namedtuple
 from typing import Dict, Iterable
 
+import os
+
 import numpy as np
 import torch
 from tqdm import tqdm
@@ -97,6 +99,24 @@ class PDEFilter(ABC):
             return PDEFilterState(t=t, y=y, error_estimate=out["err"][0] if white else None,
                                   reference_state=out["ref"][0] if white else None,
                                   diffusion_squared_local=out["diff_last"][0]), info
+        if (isinstance(self.steprule, step.Adaptive) and self.family == "white" and stop_at is None and not progressbar
+                and os.environ.get("PNMOL_B200_HOST_ADAPTIVE") != "1"):
+            state0 = self.initialize(pde)
+            eng = self._engine
+            if eng.path == "single_cta":  # accept/reject and the step-size proposal run inside one kernel launch
+                mean = state0.y.mean[None].contiguous()
+                chol = state0.y.cov_sqrtm[None].contiguous()
+                out = eng.run_adaptive(pde.t0, pde.tmax, self.steprule.first_dt(pde), self.steprule, mean, chol)
+                status = int(out["status"][0])
+                if status & 2:
+                    raise RuntimeError("adaptive time loop: attempt limit reached before tmax")
+                nsteps, natt = int(out["num_steps"][0]), int(out["num_attempts"][0])
+                eng.rescale(chol, out["diff_sum"] / nsteps, 1)
+                info = _new_info()
+                info.update(num_f_evaluations=natt, num_df_evaluations=natt, num_steps=nsteps, num_attempted_steps=natt)
+                y = rv.MultivariateNormal(mean[0], _mark_tril(chol[0]))
+                return PDEFilterState(t=float(out["t"][0]), y=y, error_estimate=None, reference_state=None,
+                                      diffusion_squared_local=out["diff_last"][0]), info
         state, info, diffs = None, None, []
         for state, info in self.solution_generator(pde, stop_at=stop_at, progressbar=progressbar):
             if isinstance(state.diffusion_squared_local, list):

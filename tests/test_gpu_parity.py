@@ -248,6 +248,61 @@ def test_fused_marginal_readout(kind, name, path, monkeypatch):
     assert np.allclose(_np(marg.std)[big], ref_std[big], rtol=1e-6)
 
 
+def test_adaptive_time_loop_on_device(monkeypatch):
+    """simulate_final_state with step.Adaptive runs accept/reject and the step-size proposal inside
+    one kernel launch; same step counts and final state as the oracle's restatement of perform_full_step
+    (src/pnmol/pdefilter.py:192-227) and as the host loop over attempt_step."""
+    from pnmol_b200 import _lib, white
+    from pnmol_b200.odetools import step
+
+    case = cases.make_case("heat", num=9, bcond="neumann", tmax=0.5)
+    rule = dict(abstol=1e-3, reltol=1e-2)
+    mk = lambda: white.LinearWhiteNoiseEK1(num_derivatives=2, steprule=step.Adaptive(**rule), spatial_kernel=case["kernel"])
+    n0 = _lib.launch_count()
+    state, info = mk().simulate_final_state(case["pde"])
+    launches_device = _lib.launch_count() - n0
+    ref, cal, ref_info = ek1_np.simulate_final_state_adaptive("white_linear", case["opde"], 2, case["gram_sqrtm"], **rule)
+    assert state.t == pytest.approx(case["pde"].tmax) and state.t == ref.t
+    assert info == ref_info and info["num_attempted_steps"] >= info["num_steps"] >= 3
+    assert cases.mean_excess(_np(state.y.mean), ref.mean) < 1
+    # (unscaled covariance: the calibration factor is the QR-sign dependent quirk-Q1 quantity)
+    monkeypatch.setenv("PNMOL_B200_HOST_ADAPTIVE", "1")
+    n0 = _lib.launch_count()
+    state_h, info_h = mk().simulate_final_state(case["pde"])
+    launches_host = _lib.launch_count() - n0
+    assert info_h == info and state_h.t == state.t
+    assert torch.allclose(state_h.y.mean, state.y.mean, rtol=1e-9, atol=1e-14)
+    assert cases.cov_excess(_np(state.y.cov_sqrtm), _np(state_h.y.cov_sqrtm), 3) < 1
+    assert launches_device < launches_host and launches_device <= 4  # gram, init, adaptive loop, rescale
+
+
+def test_adaptive_ensemble_per_member_steps():
+    """Members with different diffusivities take different numbers of steps inside the same launch and match their
+    individual oracle solves."""
+    from oracle import setup_np
+    from pnmol_b200 import ensemble, white
+    from pnmol_b200.odetools import step
+
+    case = cases.make_case("heat", num=9, tmax=0.5)
+    pde, o = case["pde"], case["opde"]
+    B = 4
+    x = pde.mesh_spatial.points[:, 0]
+    y0 = np.stack([a * np.exp(-((x - 0.5) ** 2)) * np.sin(np.pi * x) for a in (0.05, 0.1, 0.15, 0.2)])
+    ds = np.array([0.3, 1.0, 2.0, 4.0])
+    rule = dict(abstol=1e-3, reltol=1e-2)
+    solver = white.LinearWhiteNoiseEK1(num_derivatives=2, steprule=step.Adaptive(**rule), spatial_kernel=case["kernel"])
+    res = ensemble.EnsembleSolver(solver, pde, y0=y0, diff_scale=ds).simulate_final_state(rescale=False)
+    assert int(res.status.max()) == 0
+    steps = res.num_steps.cpu().numpy()
+    for b in range(B):
+        member = setup_np.with_member(o, diff_scale=ds[b], y0=y0[b])
+        ref, cal, info = ek1_np.simulate_final_state_adaptive("white_linear", member, 2, case["gram_sqrtm"], **rule)
+        assert steps[b] == info["num_steps"] and float(res.t[b]) == ref.t
+        assert cases.mean_excess(_np(res.mean[b]), ref.mean) < 1
+        assert cases.cov_excess(_np(res.cov_sqrtm[b]), ref.cov_sqrtm / np.sqrt(cal), 3) < 1  # (unscaled factors)
+    assert len(set(steps.tolist())) > 1
+
+
 def test_dense_input_factor_and_adaptive_steps():
     from pnmol_b200 import pdefilter, white
     from pnmol_b200.base import rv
