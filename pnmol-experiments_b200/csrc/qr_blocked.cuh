@@ -293,7 +293,10 @@ __device__ __noinline__ void trailing_wy(double* __restrict__ W, int ld, int nco
 // Shared memory: Vs[refl][ldt] (ldt = 2 mod 8) feeds the B operand of the second product, Vr[row][kLdr] that of the
 // first, Ts[kNB][kLdr] holds T; the strides make every fragment load bank-conflict free.
 constexpr int kLdr = 18;
-constexpr int kCh = 8;  // 8-row tiles fetched per chunk
+#ifndef PNMOL_KCH
+#define PNMOL_KCH 8
+#endif
+constexpr int kCh = PNMOL_KCH;  // 8-row tiles fetched per chunk
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
