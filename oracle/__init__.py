@@ -15,20 +15,28 @@ PARITY PINNING STATUS
 ---------------------
 The reference is pure Python on top of JAX (jax/jaxlib <= 0.3.1, un-pinned in
 ``setup.cfg:16-17``) + tornadox.  Neither is installed in this image and nothing can be
-installed (no network), so the reference cannot be imported or executed here, and it
-ships no golden vectors for the EK1 path (``tests/test_pdefilter.py:143-146`` only checks
-for NaNs).  Consequently:
+installed (no network), and the reference ships no golden vectors for the EK1 path
+(``tests/test_pdefilter.py:143-146`` only checks for NaNs).  The oracle is pinned in two ways:
 
-* the square-root primitives and the IWP prior ARE pinned: the reference's own
-  known-answer tests (``tests/test_base/test_sqrt.py:37-109``,
+* the square-root primitives, the IWP prior, the FD weights and the step rules are pinned to
+  the reference's own known-answer tests (``tests/test_base/test_sqrt.py:37-109``,
   ``tests/test_base/test_iwp.py:20-62``, ``tests/test_discretize.py:64-71``,
-  ``tests/test_odetools/test_step.py:28-45``) are re-run against this oracle in
-  ``tests/test_oracle_*.py``;
-* EK1 step / trajectory VALUES are **parity unpinned** -- the oracle follows the
-  reference source line by line and uses the same LAPACK routines that jaxlib-CPU
-  dispatches to (``dgeqrf``/``dtrsm``/``dgetrf``/``dpotrf`` through NumPy/SciPy), but no
-  output of the real reference could be generated to anchor it.  ``tests/golden/`` holds
-  vectors produced by THIS oracle (script: ``tests/golden/make_golden.py``) so that later
-  changes to oracle or kernels are detected; they are regression anchors, not reference
-  outputs.
+  ``tests/test_odetools/test_step.py:28-45``), re-run against this oracle in
+  ``tests/test_oracle_primitives.py``;
+* EK1 step / trajectory VALUES are pinned to outputs of **the reference's own source**:
+  ``tests/golden/make_reference_golden.py`` executes the unmodified reference files
+  (``src/pnmol/white.py``, ``latent.py``, ``pdefilter.py``, ``base/{sqrt,iwp,stacked_ssm,rv}.py``,
+  ``odetools/step.py``) for all four solver classes -- ``solve``, ``solution_generator``,
+  ``simulate_final_state`` with ``Constant`` and ``Adaptive`` steps -- on a NumPy stand-in for the
+  used slice of the JAX API (``tests/golden/jax_numpy_shim``: ``jax.numpy`` -> NumPy,
+  ``jax.scipy.linalg`` -> SciPy, ``jit`` -> identity), i.e. on the same LAPACK routines that
+  jaxlib's CPU backend dispatches to.  ``tests/golden/reference_*.npz`` are those outputs;
+  ``tests/test_reference_golden.py`` checks the oracle against them (equal to rounding: means
+  1e-12, covariances 1e-11, all by-products and info counters) and the CUDA path at the
+  north-star tolerances.  What this does NOT cover: XLA's own float64 code generation (fusion,
+  FMA contraction) of the real jaxlib, which can differ from NumPy at the 1e-16 level; and the
+  problem set-up (discretisation, kernels), which needs JAX autodiff and is supplied by
+  ``oracle/setup_np.py`` (pinned to the reference's ``test_discretize`` known answers).
+  ``tests/golden/<config>.npz`` (without the ``reference_`` prefix) are older regression anchors
+  produced by this oracle itself (``tests/golden/make_golden.py``).
 """

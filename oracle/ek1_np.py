@@ -3,8 +3,8 @@
 Follows, line by line and in the reference's own dense formulation,
 ``src/pnmol/white.py:12-208`` (white-noise EK1), ``src/pnmol/latent.py:20-292``
 (latent-force EK1), ``src/pnmol/pdefilter.py:75-227`` (driver loop) and
-``src/pnmol/odetools/step.py:30-55`` (constant steps).  EK1 values are parity-unpinned
-(see ``oracle/__init__.py``).
+``src/pnmol/odetools/step.py:30-133`` (constant and adaptive steps).  Pinned to golden vectors produced
+by the reference's own source (``tests/golden/make_reference_golden.py``, see ``oracle/__init__.py``).
 
 A problem is any object with attributes ``L (d,d)``, ``E_sqrtm (d,d)``, ``B (nb,d)``,
 ``R_sqrtm (nb,nb)``, ``y0 (d,)``, ``t0``, ``tmax`` and, for semi-linear solvers,

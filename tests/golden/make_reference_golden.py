@@ -1,0 +1,124 @@
+"""Golden vectors produced by the REFERENCE'S OWN SOURCE for the EK1 path.
+
+    python tests/golden/make_reference_golden.py          # needs /root/reference (this container only)
+
+jax/jaxlib (<= 0.3.1) and tornadox cannot be installed here, so `import pnmol` fails on the stock interpreter.  This
+script puts a NumPy-backed stand-in for the used slice of the JAX API (tests/golden/jax_numpy_shim: jax.numpy ->
+numpy, jax.scipy.linalg -> scipy.linalg, jit -> identity, vmap -> loop) in front of the path and then executes the
+reference's unmodified files
+
+    src/pnmol/white.py, latent.py, pdefilter.py, base/sqrt.py, base/iwp.py, base/stacked_ssm.py, base/rv.py,
+    odetools/step.py
+
+on float64 NumPy: `Solver(...).solve(pde)` with `step.Constant`.  The shim has no autodiff, so the discretised
+problem (L, E_sqrtm, B, R_sqrtm, y0, f, df) and the spatial Gram matrix are supplied as arrays/callables (built by
+oracle/setup_np.py, which restates src/pnmol/{discretize,kernels,mesh}.py and pde/examples.py and is pinned to the
+reference's own known-answer tests in tests/test_oracle_primitives.py); everything from `initialize` on -- the hot
+path of SURVEY section 8 -- is the reference's code.  The linear-algebra kernels are the same LAPACK routines jaxlib's
+CPU backend dispatches to (geqrf, trtrs/trsm, potrf, getrf) through NumPy/SciPy.
+
+Output: tests/golden/reference_<config>.npz with the inputs and the reference's trajectory (t, mean, cov_sqrtm,
+calibrated diffusion, info counters).  tests/test_reference_golden.py pins the oracle (CPU) and the CUDA path (GPU)
+to them.
+"""
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFERENCE_SRC = os.environ.get("PNMOL_REFERENCE_SRC", "/root/reference/src")
+sys.path[:0] = [os.path.join(HERE, "jax_numpy_shim"), REFERENCE_SRC, ROOT]
+
+import pnmol  # noqa: E402  (the reference, running on the shim)
+from oracle import setup_np  # noqa: E402
+
+CONFIGS = {
+    "heat_dirichlet_white_linear": ("heat", "white_linear", dict(num=6, bcond="dirichlet")),
+    "heat_neumann_white_linear": ("heat", "white_linear", dict(num=6, bcond="neumann")),
+    "heat_dirichlet_latent_linear": ("heat", "latent_linear", dict(num=6, bcond="dirichlet")),
+    "heat_neumann_latent_linear": ("heat", "latent_linear", dict(num=6, bcond="neumann")),
+    "spruce_dirichlet_white_semilinear": ("spruce", "white_semilinear", dict(num=6, bcond="dirichlet")),
+    "spruce_neumann_white_semilinear": ("spruce", "white_semilinear", dict(num=6, bcond="neumann")),
+    "spruce_dirichlet_latent_semilinear": ("spruce", "latent_semilinear", dict(num=6, bcond="dirichlet")),
+    "sir_neumann_white_semilinear": ("sir", "white_semilinear", dict(num=5)),
+    "lv_neumann_white_semilinear": ("lv", "white_semilinear", dict(num=6)),
+    "heat_dirichlet_white_linear_N20": ("heat", "white_linear", dict(num=20, bcond="dirichlet")),
+}
+SOLVERS = {
+    "white_linear": pnmol.white.LinearWhiteNoiseEK1,
+    "white_semilinear": pnmol.white.SemiLinearWhiteNoiseEK1,
+    "latent_linear": pnmol.latent.LinearLatentForceEK1,
+    "latent_semilinear": pnmol.latent.SemiLinearLatentForceEK1,
+}
+DT, NU, TMAX = 2.0 ** -4, 2, 0.5
+
+
+def oracle_problem(prob, num, bcond="dirichlet"):
+    """Same recipes as tests/cases.py:make_case (oracle side)."""
+    if prob == "heat":
+        return setup_np.heat_1d(num=num, tmax=TMAX, diffusion_rate=0.05, bcond=bcond), 1
+    if prob == "spruce":
+        return setup_np.spruce_budworm_1d(num=num, tmax=TMAX, diffusion_rate=0.05, bcond=bcond), 1
+    if prob == "sir":
+        return setup_np.sir_1d(num=num, tmax=TMAX, diffusion_rates=(0.035,) * 3, n_bnd=min(5, num)), 3
+    if prob == "lv":
+        return setup_np.lotka_volterra_1d(num=num, tmax=TMAX), 2
+    raise KeyError(prob)
+
+
+def main():
+    for name, (prob, kind, kw) in CONFIGS.items():
+        o, copies = oracle_problem(prob, **kw)
+        gram = setup_np.gram(setup_np.Sum(setup_np.SE(), setup_np.White()), o.points, copies)
+        pde = SimpleNamespace(L=o.L, E_sqrtm=o.E_sqrtm, B=o.B, R_sqrtm=o.R_sqrtm, y0=o.y0, t0=o.t0, tmax=o.tmax, f=o.f,
+                              df=o.df, mesh_spatial=SimpleNamespace(points=o.points))
+        solver = SOLVERS[kind](num_derivatives=NU, steprule=pnmol.odetools.step.Constant(DT),
+                               spatial_kernel=lambda X, Y, g=gram: g)   # white.py:85 / latent.py:139: k(X, X.T)
+        sol = solver.solve(pde)
+        mean, chol = np.asarray(sol.mean), np.asarray(sol.cov_sqrtm)
+        assert np.isfinite(mean).all() and np.isfinite(chol).all()
+        info = {k: int(v) for k, v in sol.info.items()}
+        # per-step by-products through the reference's own generator (white: error estimate and reference state)
+        states = [st for st, _ in solver.solution_generator(pde)][1:]
+        diffs = np.array([float(st.diffusion_squared_local) for st in states])
+        extra = {}
+        if kind.startswith("white"):
+            extra = dict(error_estimate=np.stack([np.asarray(st.error_estimate) for st in states]),
+                         reference_state=np.stack([np.asarray(st.reference_state) for st in states]))
+        final, _ = solver.simulate_final_state(pde)  # pdefilter.py:105-116 (factor rescaled by the calibration)
+        extra["final_cov_sqrtm"] = np.asarray(final.y.cov_sqrtm)
+        np.savez_compressed(os.path.join(HERE, "reference_" + name + ".npz"), L=o.L, E_sqrtm=o.E_sqrtm, B=o.B,
+                            R_sqrtm=o.R_sqrtm, y0=o.y0, gram=gram, dt=DT, nu=NU, tmax=TMAX, t=np.asarray(sol.t), mean=mean,
+                            cov_sqrtm=chol, diffusion_squared_calibrated=float(sol.diffusion_squared_calibrated),
+                            kind=kind, problem=prob, num=kw["num"], bcond=kw.get("bcond", "neumann"),
+                            diffusion_squared_local=diffs, **extra,
+                            info_keys=np.array(sorted(info)), info_vals=np.array([info[k] for k in sorted(info)]))
+        print(f"{name:40s} t {np.asarray(sol.t).shape} mean {mean.shape} chol {chol.shape} "
+              f"sigma^2 {float(sol.diffusion_squared_calibrated):.6e} info {info}")
+
+
+def adaptive():
+    """simulate_final_state with step.Adaptive (pdefilter.py:105-227, odetools/step.py:58-133) on the heat problem."""
+    o, _ = oracle_problem("heat", 9, "neumann")
+    gram = setup_np.gram(setup_np.Sum(setup_np.SE(), setup_np.White()), o.points, 1)
+    pde = SimpleNamespace(L=o.L, E_sqrtm=o.E_sqrtm, B=o.B, R_sqrtm=o.R_sqrtm, y0=o.y0, t0=o.t0, tmax=o.tmax, f=o.f, df=o.df,
+                          mesh_spatial=SimpleNamespace(points=o.points))
+    rule = dict(abstol=1e-3, reltol=1e-2)
+    solver = pnmol.white.LinearWhiteNoiseEK1(num_derivatives=NU, steprule=pnmol.odetools.step.Adaptive(**rule),
+                                             spatial_kernel=lambda X, Y: gram)
+    final, info = solver.simulate_final_state(pde)
+    info = {k: int(v) for k, v in info.items()}
+    np.savez_compressed(os.path.join(HERE, "reference_adaptive_heat_neumann_white_linear.npz"), L=o.L, E_sqrtm=o.E_sqrtm,
+                        B=o.B, R_sqrtm=o.R_sqrtm, y0=o.y0, gram=gram, nu=NU, tmax=TMAX, num=9, abstol=rule["abstol"],
+                        reltol=rule["reltol"], t=float(final.t), mean=np.asarray(final.y.mean),
+                        cov_sqrtm=np.asarray(final.y.cov_sqrtm), info_keys=np.array(sorted(info)),
+                        info_vals=np.array([info[k] for k in sorted(info)]))
+    print("adaptive heat neumann N=9:", info, "t =", float(final.t))
+
+
+if __name__ == "__main__":
+    main()
+    adaptive()
