@@ -46,6 +46,11 @@ CONFIGS = {
     "sir_neumann_white_semilinear": ("sir", "white_semilinear", dict(num=5)),
     "lv_neumann_white_semilinear": ("lv", "white_semilinear", dict(num=6)),
     "heat_dirichlet_white_linear_N20": ("heat", "white_linear", dict(num=20, bcond="dirichlet")),
+    # BASELINE-sized members (C1/C5: heat N=50, D=150; SIR N=17, D=153), two steps; first-order prior (figure-3 style)
+    "heat_dirichlet_white_linear_N50": ("heat", "white_linear", dict(num=50, bcond="dirichlet", tmax=0.125)),
+    "sir_neumann_white_semilinear_N17": ("sir", "white_semilinear", dict(num=17, tmax=0.125)),
+    "heat_neumann_white_linear_nu1": ("heat", "white_linear", dict(num=8, bcond="neumann", nu=1)),
+    "spruce_dirichlet_latent_semilinear_nu1": ("spruce", "latent_semilinear", dict(num=6, bcond="dirichlet", nu=1)),
 }
 SOLVERS = {
     "white_linear": pnmol.white.LinearWhiteNoiseEK1,
@@ -56,16 +61,16 @@ SOLVERS = {
 DT, NU, TMAX = 2.0 ** -4, 2, 0.5
 
 
-def oracle_problem(prob, num, bcond="dirichlet"):
+def oracle_problem(prob, num, bcond="dirichlet", tmax=TMAX, nu=NU):
     """Same recipes as tests/cases.py:make_case (oracle side)."""
     if prob == "heat":
-        return setup_np.heat_1d(num=num, tmax=TMAX, diffusion_rate=0.05, bcond=bcond), 1
+        return setup_np.heat_1d(num=num, tmax=tmax, diffusion_rate=0.05, bcond=bcond), 1
     if prob == "spruce":
-        return setup_np.spruce_budworm_1d(num=num, tmax=TMAX, diffusion_rate=0.05, bcond=bcond), 1
+        return setup_np.spruce_budworm_1d(num=num, tmax=tmax, diffusion_rate=0.05, bcond=bcond), 1
     if prob == "sir":
-        return setup_np.sir_1d(num=num, tmax=TMAX, diffusion_rates=(0.035,) * 3, n_bnd=min(5, num)), 3
+        return setup_np.sir_1d(num=num, tmax=tmax, diffusion_rates=(0.035,) * 3, n_bnd=min(5, num)), 3
     if prob == "lv":
-        return setup_np.lotka_volterra_1d(num=num, tmax=TMAX), 2
+        return setup_np.lotka_volterra_1d(num=num, tmax=tmax), 2
     raise KeyError(prob)
 
 
@@ -75,7 +80,8 @@ def main():
         gram = setup_np.gram(setup_np.Sum(setup_np.SE(), setup_np.White()), o.points, copies)
         pde = SimpleNamespace(L=o.L, E_sqrtm=o.E_sqrtm, B=o.B, R_sqrtm=o.R_sqrtm, y0=o.y0, t0=o.t0, tmax=o.tmax, f=o.f,
                               df=o.df, mesh_spatial=SimpleNamespace(points=o.points))
-        solver = SOLVERS[kind](num_derivatives=NU, steprule=pnmol.odetools.step.Constant(DT),
+        nu = kw.get("nu", NU)
+        solver = SOLVERS[kind](num_derivatives=nu, steprule=pnmol.odetools.step.Constant(DT),
                                spatial_kernel=lambda X, Y, g=gram: g)   # white.py:85 / latent.py:139: k(X, X.T)
         sol = solver.solve(pde)
         mean, chol = np.asarray(sol.mean), np.asarray(sol.cov_sqrtm)
@@ -91,7 +97,7 @@ def main():
         final, _ = solver.simulate_final_state(pde)  # pdefilter.py:105-116 (factor rescaled by the calibration)
         extra["final_cov_sqrtm"] = np.asarray(final.y.cov_sqrtm)
         np.savez_compressed(os.path.join(HERE, "reference_" + name + ".npz"), L=o.L, E_sqrtm=o.E_sqrtm, B=o.B,
-                            R_sqrtm=o.R_sqrtm, y0=o.y0, gram=gram, dt=DT, nu=NU, tmax=TMAX, t=np.asarray(sol.t), mean=mean,
+                            R_sqrtm=o.R_sqrtm, y0=o.y0, gram=gram, dt=DT, nu=nu, tmax=o.tmax, t=np.asarray(sol.t), mean=mean,
                             cov_sqrtm=chol, diffusion_squared_calibrated=float(sol.diffusion_squared_calibrated),
                             kind=kind, problem=prob, num=kw["num"], bcond=kw.get("bcond", "neumann"),
                             diffusion_squared_local=diffs, **extra,

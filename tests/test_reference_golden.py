@@ -83,7 +83,7 @@ def test_oracle_adaptive_equals_reference_source():
 def _product_case(g):
     prob, num, bcond = str(g["problem"]), int(g["num"]), str(g["bcond"])
     kw = dict(bcond=bcond) if prob in ("heat", "spruce") else {}
-    return cases.make_case(prob, num=num, tmax=float(g["tmax"]), **kw)
+    return cases.make_case(prob, num=num, tmax=float(g["tmax"]), nu=int(g["nu"]), **kw)
 
 
 @pytest.mark.gpu
