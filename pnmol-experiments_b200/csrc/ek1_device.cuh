@@ -26,6 +26,13 @@ namespace pnmol {
 #ifndef PNMOL_MIN_CTAS
 #define PNMOL_MIN_CTAS 2
 #endif
+#ifdef PNMOL_PLAIN_STATE_IO   // tuning: plain instead of streaming (evict-first) accesses to the filter state
+#define PNMOL_STATE_LOAD(p) (*(p))
+#define PNMOL_STATE_STORE(p, v) (*(p) = (v))
+#else
+#define PNMOL_STATE_LOAD(p) __ldcs(p)
+#define PNMOL_STATE_STORE(p, v) __stcs(p, v)
+#endif
 constexpr int kThreads = PNMOL_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxN = 8;     // num_derivatives + 1
@@ -360,7 +367,7 @@ __device__ void build_predict(const Problem& P, int b, const Smem& sm, const dou
         const int tend = te[i];
         for (int k = lane; k <= tend; k += 32) {
             double acc = 0.0;
-            for (int s = 0; s < n; ++s) acc = fma(coef[s], sm.pinv[s] * __ldcs(Cl + (size_t)(blk * n + s) * D + k), acc);
+            for (int s = 0; s < n; ++s) acc = fma(coef[s], sm.pinv[s] * PNMOL_STATE_LOAD(Cl + (size_t)(blk * n + s) * D + k), acc);
             col[k] = acc;
         }
         // Ql^T column i = row i of Ql, entries 0..i
@@ -790,7 +797,7 @@ __device__ int update_output_factor(const Problem& P, const Smem& sm, const Upda
         for (int c = lane; c < D; c += 32) {
             double v = 0.0;
             if (c <= r && mcur + c < nrows) v = pr * col[c];
-            __stcs(orow + c, v);  // streaming: keep the workspaces, not the state, resident in L2
+            PNMOL_STATE_STORE(orow + c, v);  // streaming by default: keep the workspaces, not the state, resident in L2
             if (!isfinite(v)) bad = 1;
         }
     }
