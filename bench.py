@@ -340,8 +340,8 @@ def run_b200_arm(args):
 
 
 def other_configs_timing(dev, fp64_peak):
-    """BASELINE configs C2-C4 (single large solves, multi-CTA kernels): device-timed ms per EK1 step, not part of
-    `value`.  C4 needs ~0.5 GB of workspace and a few hundred ms; everything here stays below ~10 s."""
+    """BASELINE configs C2-C4 (single large solves, multi-CTA kernels): device-timed ms per EK1 step, and the other
+    C5 ensembles (SIR N=17, the N=6 probe): member-steps/s.  Not part of `value`; everything here stays below ~15 s."""
     import torch
 
     import cases
@@ -373,6 +373,53 @@ def other_configs_timing(dev, fp64_peak):
             del solver, eng, mean, chol, s0
             torch.cuda.empty_cache()
         except Exception as exc:  # never lose the headline line to a side measurement
+            out[name] = {"error": repr(exc)[:200]}
+    # the other ensemble members (SIR N=17: D=153, m=57; the HBM-bound probe N=6: D=18, m=8)
+    from pnmol_b200 import ensemble, kernels, white
+    from pnmol_b200.odetools import step
+    from pnmol_b200.pde import examples
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    for name in ("c5_sir_N17_ensemble_4096", "c5_heat_N6_probe_ensemble_4096"):
+        try:
+            M = 4096
+            rng = np.random.default_rng(SEED)
+            if "sir" in name:
+                pde = examples.sir_1d_discretized(num=17, tmax=TMAX, diffusion_rate_S=0.035, diffusion_rate_I=0.035,
+                                                  diffusion_rate_R=0.035)
+                solver = white.SemiLinearWhiteNoiseEK1(num_derivatives=NU, steprule=step.Constant(DT),
+                                                       spatial_kernel=kernels.duplicate(kernels.Matern52() + kernels.WhiteNoise(), 3))
+                es = ensemble.EnsembleSolver(solver, pde, y0=np.tile(pde.y0, (M, 1)) * rng.uniform(0.9, 1.1, (M, 1)),
+                                             diff_scale=np.exp(rng.uniform(np.log(0.3), np.log(3.0), (M, 3))), device=dev)
+            else:
+                pde = examples.heat_1d_discretized(num=6, tmax=TMAX, diffusion_rate=0.035)
+                solver = white.LinearWhiteNoiseEK1(num_derivatives=NU, steprule=step.Constant(DT),
+                                                   spatial_kernel=kernels.SquareExponential() + kernels.WhiteNoise())
+                y0, diff, prior = member_parameters(M, pde.mesh_spatial.points[:, 0], SEED)
+                es = ensemble.EnsembleSolver(solver, pde, y0=y0, diff_scale=diff, prior_scale=prior, device=dev)
+            eng = es.engine
+            mean0, chol0, _ = es.initialize()
+            mean, chol = mean0.clone(), chol0.clone()
+            eng.run(pde.t0, es.dts, mean, chol)
+            mean.copy_(mean0); chol.copy_(chol0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = eng.run(pde.t0, es.dts, mean, chol)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            b_alg, f_alg = work_model(eng.D, eng.m, eng.d)
+            rate = M * len(es.dts) / (ms * 1e-3)
+            out[name] = {"D": eng.D, "m": eng.m, "path": eng.path, "member_steps_per_sec": rate,
+                         "fp64_frac": rate * f_alg * 1e-12 / fp64_peak,
+                         "hbm_frac": rate * b_alg * 1e-9 / peaks.get("hbm_gbs", 6650.0), "status": int(res["status"].max())}
+            del es, eng, mean, chol, mean0, chol0
+            torch.cuda.empty_cache()
+        except Exception as exc:
             out[name] = {"error": repr(exc)[:200]}
     return out
 

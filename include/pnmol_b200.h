@@ -211,6 +211,14 @@ int pnmol_b200_sqrt_propagate(const double* S1, const double* S2, double* out, i
 int pnmol_b200_sqrt_update(const double* H, const double* C, const double* meascov, double* C_out,
                            double* K_out, double* S_out, int m, int D, int batch, int device, void* stream);
 
+/* Square-root RTS smoother step (src/pnmol/base/kalman.py:49-66 smoother_step_sqrt):
+ *   mean_out = m - sgain (mp - m_fut);  chol_out = (R[d:2d, d:])^T of the QR of [[x^T, sc^T], [sq^T, 0], [0, sc_fut^T sgain^T]].
+ * All arrays dev float64 row-major with a leading batch dimension: m, m_fut, mp, mean_out [batch, d]; sc, sc_fut, sgain,
+ * sq, x, chol_out [batch, d, d]. */
+int pnmol_b200_smoother_step(const double* m, const double* sc, const double* m_fut, const double* sc_fut, const double* sgain,
+                             const double* sq, const double* mp, const double* x, double* mean_out, double* chol_out, int d,
+                             int batch, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

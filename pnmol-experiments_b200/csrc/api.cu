@@ -714,4 +714,26 @@ int pnmol_b200_sqrt_update(const double* H, const double* C, const double* measc
     return 0;
 }
 
+int pnmol_b200_smoother_step(const double* m, const double* sc, const double* m_fut, const double* sc_fut, const double* sgain,
+                             const double* sq, const double* mp, const double* x, double* mean_out, double* chol_out, int d,
+                             int batch, int device, void* stream) {
+    if (!m || !sc || !m_fut || !sc_fut || !sgain || !sq || !mp || !x || !mean_out || !chol_out || d <= 0 || batch <= 0)
+        return fail(-1, "invalid argument");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(-3, "no such CUDA device (libpnmol_b200 has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const int grid = std::min(batch, 296);
+    double* W;
+    int rc = get_scratch(device, (size_t)grid * 3 * d * 2 * d, &W);
+    if (rc) return rc;
+    const size_t smem = sizeof(double) * (3 * d + 4 + 2 * kWarps);
+    CU(cudaFuncSetAttribute(k_smoother_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    k_smoother_step<<<grid, kThreads, smem, (cudaStream_t)stream>>>(m, sc, m_fut, sc_fut, sgain, sq, mp, x, mean_out, chol_out, d,
+                                                                    batch, W);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 }  // extern "C"

@@ -409,4 +409,55 @@ __global__ void __launch_bounds__(kThreads) k_sqrt_update(const double* H, const
     }
 }
 
+// Square-root RTS smoother step (src/pnmol/base/kalman.py:49-66): new_mean = m - G (mp - m_fut); the new factor is the
+// transpose of R[d:2d, d:] of the QR of the 3d x 2d matrix [[x^T, sc^T], [sq^T, 0], [0, sc_fut^T G^T]].
+// All inputs row-major [batch, ...]; one CTA per member, unblocked Householder QR on an L2-resident workspace.
+// (sc_fut may be any square root of the future covariance, not necessarily triangular.)
+__global__ void __launch_bounds__(kThreads) k_smoother_step(const double* m, const double* sc, const double* m_fut,
+                                                           const double* sc_fut, const double* sgain, const double* sq,
+                                                           const double* mp, const double* x, double* mean_out,
+                                                           double* chol_out, int d, int batch, double* Wall) {
+    extern __shared__ double smem_raw[];
+    double* vbuf = smem_raw;
+    double* red = smem_raw + 3 * d + 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rows = 3 * d, ld = rows, ncols = 2 * d;
+    double* W = Wall + (size_t)blockIdx.x * ld * ncols;
+    for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+        const size_t o1 = (size_t)b * d, o2 = (size_t)b * d * d;
+        for (int i = warp; i < d; i += kWarps) {  // new_mean[i] = m[i] - sum_k G[i][k] (mp[k] - m_fut[k])
+            double acc = 0.0;
+            for (int k = lane; k < d; k += 32) acc = fma(sgain[o2 + (size_t)i * d + k], mp[o1 + k] - m_fut[o1 + k], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) mean_out[o1 + i] = m[o1 + i] - acc;
+        }
+        for (int idx = tid; idx < rows * ncols; idx += kThreads) {
+            const int col = idx / rows, row = idx - col * rows;
+            double v = 0.0;
+            if (col < d) {
+                if (row < d) v = x[o2 + (size_t)col * d + row];               // x^T
+                else if (row < 2 * d) v = sq[o2 + (size_t)col * d + row - d];  // sq^T
+            } else {
+                const int c = col - d;
+                if (row < d) v = sc[o2 + (size_t)c * d + row];                 // sc^T
+                else if (row >= 2 * d) {  // (sc_fut^T G^T)[r][c] = sum_k sc_fut[k][r] G[c][k]
+                    const int r = row - 2 * d;
+                    double acc = 0.0;
+                    for (int k = 0; k < d; ++k) acc = fma(sc_fut[o2 + (size_t)k * d + r], sgain[o2 + (size_t)c * d + k], acc);
+                    v = acc;
+                }
+            }
+            W[(size_t)col * ld + row] = v;
+        }
+        __syncthreads();
+        Shape sh; sh.nt = rows; sh.nbot = 0; sh.ncols = ncols; sh.te = nullptr; sh.be = nullptr;
+        householder_qr(W, ld, sh, vbuf, red);
+        for (int idx = tid; idx < d * d; idx += kThreads) {  // out[i][j] = R[d + j][d + i], j <= i
+            const int i = idx / d, j = idx - i * d;
+            chol_out[o2 + idx] = j <= i ? W[(size_t)(d + i) * ld + d + j] : 0.0;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace pnmol

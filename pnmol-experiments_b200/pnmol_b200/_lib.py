@@ -36,6 +36,7 @@ SIGNATURES = {
     "pnmol_b200_simulate_final_state_host": (c_int, [c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                                      c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pnmol_b200_sqrt_propagate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "pnmol_b200_smoother_step": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_void_p]),
     "pnmol_b200_sqrt_update": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_void_p]),
 }
 

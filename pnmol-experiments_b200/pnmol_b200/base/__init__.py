@@ -1,2 +1,2 @@
 """State-space building blocks (API of src/pnmol/base)."""
-from . import iwp, rv, sqrt, stacked_ssm  # noqa: F401
+from . import iwp, kalman, rv, sqrt, stacked_ssm  # noqa: F401

@@ -125,6 +125,29 @@ def adaptive():
     print("adaptive heat neumann N=9:", info, "t =", float(final.t))
 
 
+def kalman():
+    """Filter step + square-root / covariance-form smoother step of src/pnmol/base/kalman.py on a random system
+    (the scenario of the reference's tests/test_base/test_kalman.py)."""
+    rng = np.random.default_rng(20261018)
+    out = {}
+    for d, k in ((4, 2), (12, 5), (33, 7)):
+        phi = rng.standard_normal((d, d)) / np.sqrt(d) + np.eye(d)
+        sq = np.tril(rng.standard_normal((d, d))) * 0.3 + 0.5 * np.eye(d)
+        h, b, data = rng.standard_normal((k, d)), rng.standard_normal(k), rng.standard_normal(k)
+        m, sc = rng.standard_normal(d), np.tril(rng.standard_normal((d, d))) + 2 * np.eye(d)
+        m1, sc1, sgain, mp, scp, x = pnmol.base.kalman.filter_step(m, sc, phi, sq, h, b, data)
+        m2, sc2, *_ = pnmol.base.kalman.filter_step(m1, sc1, phi, sq, h, b, data + 0.1)   # a "future" state
+        ms, scs = pnmol.base.kalman.smoother_step_sqrt(m, sc, m2, sc2, sgain, sq, mp, x)
+        mt, sct = pnmol.base.kalman.smoother_step_traditional(m, sc, m2, sc2, sgain, mp, scp)
+        assert np.allclose(ms, mt) and np.allclose(scs @ scs.T, sct @ sct.T)
+        for key, val in dict(phi=phi, sq=sq, h=h, b=b, data=data, m=m, sc=sc, m1=m1, sc1=sc1, sgain=sgain, mp=mp, scp=scp, x=x,
+                             m_fut=m2, sc_fut=sc2, m_smooth=ms, sc_smooth=scs, sc_smooth_traditional=sct).items():
+            out[f"d{d}_{key}"] = np.asarray(val)
+    np.savez_compressed(os.path.join(HERE, "reference_kalman.npz"), sizes=np.array([4, 12, 33]), **out)
+    print("kalman: filter_step + smoother_step_sqrt / traditional for d = 4, 12, 33")
+
+
 if __name__ == "__main__":
     main()
     adaptive()
+    kalman()

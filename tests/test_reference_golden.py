@@ -19,7 +19,8 @@ from oracle import ek1_np, setup_np
 import cases
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FILES = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "reference_*.npz")) if "adaptive" not in p)
+FILES = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "reference_*.npz")) if "adaptive" not in p and "kalman" not in p)
+KALMAN = os.path.join(HERE, "golden", "reference_kalman.npz")
 ADAPTIVE = os.path.join(HERE, "golden", "reference_adaptive_heat_neumann_white_linear.npz")
 IDS = [os.path.basename(p)[len("reference_"):-4] for p in FILES]
 
@@ -79,7 +80,55 @@ def test_oracle_adaptive_equals_reference_source():
     assert cases.block_rel(cases.cov(final.cov_sqrtm), cases.cov(g["cov_sqrtm"]), 3) <= 1e-10
 
 
+def test_oracle_kalman_equals_reference_source():
+    from oracle import kalman_np
+
+    g = np.load(KALMAN, allow_pickle=False)
+    for d in g["sizes"]:
+        v = {k[len(f"d{d}_"):]: g[k] for k in g.files if k.startswith(f"d{d}_")}
+        m1, sc1, sgain, mp, scp, x = kalman_np.filter_step(v["m"], v["sc"], v["phi"], v["sq"], v["h"], v["b"], v["data"])
+        assert np.allclose(m1, v["m1"], rtol=1e-12, atol=1e-13) and np.allclose(sgain, v["sgain"], rtol=1e-11, atol=1e-13)
+        assert np.allclose(sc1 @ sc1.T, v["sc1"] @ v["sc1"].T, rtol=1e-11, atol=1e-13)
+        ms, scs = kalman_np.smoother_step_sqrt(v["m"], v["sc"], v["m_fut"], v["sc_fut"], v["sgain"], v["sq"], v["mp"], v["x"])
+        assert np.allclose(ms, v["m_smooth"], rtol=1e-12, atol=1e-13) and np.allclose(scs, v["sc_smooth"], rtol=1e-9, atol=1e-11)
+        mt, sct = kalman_np.smoother_step_traditional(v["m"], v["sc"], v["m_fut"], v["sc_fut"], v["sgain"], v["mp"], v["scp"])
+        assert np.allclose(sct, v["sc_smooth_traditional"], rtol=1e-10, atol=1e-12)
+
+
 # ----------------------------------------------------------------------------------------------- CUDA path
+@pytest.mark.gpu
+def test_cuda_smoother_step_reproduces_reference_source():
+    """the square-root RTS smoother step (kalman.py:49-66) and the filter step it follows."""
+    import torch
+
+    import __graft_entry__
+
+    __graft_entry__.ensure_built()
+    from pnmol_b200.base import kalman
+
+    g = np.load(KALMAN, allow_pickle=False)
+    for d in g["sizes"]:
+        v = {k[len(f"d{d}_"):]: g[k] for k in g.files if k.startswith(f"d{d}_")}
+        ms, scs = kalman.smoother_step_sqrt(v["m"], v["sc"], v["m_fut"], v["sc_fut"], v["sgain"], v["sq"], v["mp"], v["x"])
+        ms, scs = ms.cpu().numpy(), scs.cpu().numpy()
+        assert np.allclose(ms, v["m_smooth"], rtol=1e-11, atol=1e-13)
+        assert np.array_equal(np.triu(scs, 1), np.zeros_like(scs))
+        assert np.allclose(scs @ scs.T, v["sc_smooth"] @ v["sc_smooth"].T, rtol=1e-9, atol=1e-12)
+        assert np.allclose(scs, v["sc_smooth"], rtol=1e-8, atol=1e-11)  # same signs as LAPACK (dlarfg convention)
+        mt, sct = kalman.smoother_step_traditional(v["m"], v["sc"], v["m_fut"], v["sc_fut"], v["sgain"], v["mp"], v["scp"])
+        assert np.allclose(scs @ scs.T, (sct @ sct.T).cpu().numpy(), rtol=1e-8, atol=1e-11)   # tests/test_base/test_kalman.py:131-135
+        out = kalman.filter_step(v["m"], v["sc"], v["phi"], v["sq"], v["h"], v["b"], v["data"])
+        assert np.allclose(out[0].cpu().numpy(), v["m1"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(out[2].cpu().numpy(), v["sgain"], rtol=1e-8, atol=1e-11)
+        L1 = out[1].cpu().numpy()
+        assert np.allclose(L1 @ L1.T, v["sc1"] @ v["sc1"].T, rtol=1e-8, atol=1e-11)
+        # batched call = stacked single calls
+        stack = lambda key: np.stack([v[key], v[key]])
+        mb, sb = kalman.smoother_step_sqrt(*[stack(k) for k in ("m", "sc", "m_fut", "sc_fut", "sgain", "sq", "mp", "x")])
+        assert torch.equal(mb[0], mb[1]) and np.allclose(sb[1].cpu().numpy(), scs)
+
+
+
 def _product_case(g):
     prob, num, bcond = str(g["problem"]), int(g["num"]), str(g["bcond"])
     kw = dict(bcond=bcond) if prob in ("heat", "spruce") else {}
