@@ -289,7 +289,7 @@ def run_b200_arm(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     ach_tf = f_alg * M * T / (kernel_ms * 1e-3) * 1e-12
     ach_gbs = b_alg * M * T / (kernel_ms * 1e-3) * 1e-9
-    roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+    roofline = {"bound": "tensor", "pipe": "fp64 (mma.sync DMMA + DFMA; tcgen05 has no FP64 MMA)", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
                 "traffic": NCU_DRAM_BYTES_PER_MEMBER_STEP * M * T,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per member-step "
                                   "(profiles/r01_ncu_k_run_full_summary_v6.csv) x member-steps per launch",
