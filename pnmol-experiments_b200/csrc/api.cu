@@ -132,6 +132,7 @@ struct pnmol_b200_handle {
     bool large = false;
     LargeQR q{};
     size_t smem_large = 0;
+    int cluster = 1;  // thread-block cluster size of the multi-CTA kernels (panel factorisation on cluster 0)
     // warp-per-member path (ek1_warp.cuh): every panel row list <= 256 rows; PNMOL_B200_PATH=cta|warp|large overrides
     bool warp = false;
     WarpGeom geo{};
@@ -196,12 +197,31 @@ int upload_steps(pnmol_b200_handle* h, int nsteps, double t0, const double* dts,
     return 0;
 }
 
+// Cooperative launch of a multi-CTA kernel, as thread-block clusters when h->cluster > 1.
+template <typename Kernel, typename Args>
+int launch_large(pnmol_b200_handle* h, Kernel kernel, Args& a, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(h->grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = h->smem_large;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = h->cluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = h->cluster > 1 ? 2 : 1;
+    CU(cudaLaunchKernelEx(&cfg, kernel, h->P, a, h->q));
+    return 0;
+}
+
 int launch_run(pnmol_b200_handle* h, RunArgs& a, cudaStream_t st) {
     if (h->warp) {
         k_run_warp<<<h->grid, 32 * h->geo.nwarps, h->smem_warp, st>>>(h->P, a, h->geo);
     } else if (h->large) {
-        void* args[] = {(void*)&h->P, (void*)&a, (void*)&h->q};
-        CU(cudaLaunchCooperativeKernel((const void*)k_run_large, dim3(h->grid), dim3(kThreads), args, h->smem_large, st));
+        int rc = launch_large(h, k_run_large, a, st);
+        if (rc) return rc;
     } else {
         k_run<<<h->grid, kThreads, h->smem_bytes, st>>>(h->P, a);
     }
@@ -387,6 +407,28 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
             if (std::min(occ, occ2) < 1) return fail(-1, "multi-CTA kernels do not fit on an SM");
             h->grid = h->num_sms;
             if (const char* e = std::getenv("PNMOL_B200_GRID")) h->grid = std::max(1, std::min(h->grid, std::atoi(e)));
+            // thread-block clusters: the panel factorisation runs on cluster 0 (rows split over its CTAs)
+            h->cluster = 1;
+            // (measured on B200: clusters of 8 make the C4 panel 2.5x and the C2/C3 panels ~1.15x faster; the trailing
+            // phases then run on the 120 CTAs that fit whole clusters instead of 148)
+            int want_cluster = 8;
+            if (const char* e = std::getenv("PNMOL_B200_CLUSTER")) want_cluster = std::atoi(e);
+            if (want_cluster > 1) {
+                for (auto fn : {(const void*)k_run_large, (const void*)k_init_large})
+                    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(want_cluster); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = h->smem_large;
+                cudaLaunchAttribute at[2];
+                at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+                at[1].id = cudaLaunchAttributeClusterDimension;
+                at[1].val.clusterDim.x = want_cluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 2;
+                int ncl = 0, ncl2 = 0;
+                CU(cudaOccupancyMaxActiveClusters(&ncl, k_run_large, &cfg));
+                CU(cudaOccupancyMaxActiveClusters(&ncl2, k_init_large, &cfg));
+                ncl = std::min(ncl, ncl2);
+                if (ncl >= 1) { h->cluster = want_cluster; h->grid = ncl * want_cluster; }
+            }
             const size_t wsz = (size_t)P.ld * (P.m + P.D);
             if ((rc = dev_alloc(h, &P.W, wsz))) return rc;
             if ((rc = dev_alloc(h, &P.Hcol, (size_t)P.m * P.wh))) return rc;
@@ -476,8 +518,8 @@ int pnmol_b200_initialize(pnmol_b200_handle* h, const double* y0, double t0, dou
     if (h->warp) {
         k_init_warp<<<h->grid, 32 * h->geo.nwarps, h->smem_warp, (cudaStream_t)stream>>>(h->P, a, h->geo);
     } else if (h->large) {
-        void* args[] = {(void*)&h->P, (void*)&a, (void*)&h->q};
-        CU(cudaLaunchCooperativeKernel((const void*)k_init_large, dim3(h->grid), dim3(kThreads), args, h->smem_large, (cudaStream_t)stream));
+        int rc2 = launch_large(h, k_init_large, a, (cudaStream_t)stream);
+        if (rc2) return rc2;
     } else {
         k_init<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
     }

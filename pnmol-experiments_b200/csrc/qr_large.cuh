@@ -280,6 +280,175 @@ __device__ void large_panel_factor(double* __restrict__ W, int ld, const Shape& 
     pc.mark(19);
 }
 
+// S1 on a thread-block cluster: the panel's compact row list is split over the CS CTAs of cluster 0 (CTA r keeps rows
+// [r Lc, (r+1) Lc) of all kNB columns in its shared memory), so the per-column work runs on CS SMs.  Per column one
+// round: every CTA reduces its partial dot products x_i . x_k (k >= i; k = i is the norm) over its rows, all CTAs
+// exchange them through distributed shared memory (CTA 0 adds the row-i entries x_k[i]), one cluster barrier, then every
+// CTA sums the partials in the same fixed order, derives the dlarfg scalars redundantly and updates its own rows.
+// Requires Lc >= kNB (the diagonal block lives in CTA 0) -- the caller falls back to large_panel_factor otherwise.
+constexpr int kGath = 2 * kNB;  // doubles per CTA and column round: kNB partial dots + kNB row-i entries
+
+__device__ void large_panel_factor_cluster(cg::cluster_group& cluster, double* __restrict__ W, int ld, const Shape& s, int j0,
+                                           int nbk, const RowMap rm, const LargeQR& q, const LargeSmem& ls, int Lc) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int CS = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+    const int L = rm.len, nt = s.nt;
+    const int c_lo = r * Lc, c_hi = L < (r + 1) * Lc ? L : (r + 1) * Lc;  // this CTA's rows of the compact list
+    const int nloc = c_hi > c_lo ? c_hi - c_lo : 0;
+    double* PB = ls.PB;                       // [kNB][Lc] local slice, column-major
+    double* gath = PB + (size_t)kNB * Lc;     // [2][CS][kGath] gathered partials (double buffered)
+    double* part = gath + 2 * CS * kGath;     // [kGath] this CTA's contribution
+    double* sc = ls.sc;                       // [3 i] tau, [3 i + 1] beta, [3 i + 2] scale
+    __shared__ int envc[2 * kNB];
+    if (tid < nbk) { envc[tid] = env_top(s, j0 + tid); envc[kNB + tid] = env_bot(s, j0 + tid); }
+    __syncthreads();
+    // ---- load the slice (entries outside a column's own envelope are zero)
+    for (int cc = 0; cc < kNB; ++cc) {
+        const bool hc = cc < nbk;
+        const int et = hc ? envc[cc] : -1, eb = hc ? envc[kNB + cc] : -1;
+        const double* src = W + (size_t)(j0 + (hc ? cc : 0)) * ld;
+        double* dstc = PB + (size_t)cc * Lc;
+        for (int cl = tid; cl < Lc; cl += kThreads) {
+            const int c = c_lo + cl;
+            const int row = rm.row(c);
+            if (hc && c < L && (row < nt ? row <= et : row <= eb)) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(dstc + cl);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src + row) : "memory");
+            } else {
+                dstc[cl] = 0.0;
+            }
+        }
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncthreads();
+    for (int i = 0; i < nbk; ++i) {
+        const double* xi = PB + (size_t)i * Lc;
+        const int lo = (i + 1 > c_lo ? i + 1 : c_lo) - c_lo;  // first local row below the diagonal
+        // ---- partial dot products: warp w takes columns w and w + 8 (both in one pass over the pivot column)
+        {
+            const int k0 = warp, k1 = warp + kWarps;
+            const bool u0 = k0 >= i && k0 < nbk, u1 = k1 >= i && k1 < nbk;
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            if (u0 || u1) {
+                const double* xa = PB + (size_t)(u0 ? k0 : k1) * Lc;
+                const double* xb = PB + (size_t)(u1 ? k1 : k0) * Lc;
+                int cl = lo + lane;
+                for (; cl + 32 < nloc; cl += 64) {
+                    const double p0 = xi[cl], p1 = xi[cl + 32];
+                    a0 = fma(p0, xa[cl], a0); a1 = fma(p1, xa[cl + 32], a1);
+                    b0 = fma(p0, xb[cl], b0); b1 = fma(p1, xb[cl + 32], b1);
+                }
+                if (cl < nloc) { a0 = fma(xi[cl], xa[cl], a0); b0 = fma(xi[cl], xb[cl], b0); }
+                a0 += a1; b0 += b1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ta = __shfl_xor_sync(0xffffffffu, a0, o), tb = __shfl_xor_sync(0xffffffffu, b0, o);
+                    a0 += ta; b0 += tb;
+                }
+            }
+            if (lane == 0) {
+                part[k0] = u0 ? a0 : 0.0;
+                part[k1] = u1 ? (u0 ? b0 : a0) : 0.0;
+                part[kNB + k0] = (r == 0 && k0 < nbk) ? PB[(size_t)k0 * Lc + i] : 0.0;  // row i of column k lives in CTA 0
+                part[kNB + k1] = (r == 0 && k1 < nbk) ? PB[(size_t)k1 * Lc + i] : 0.0;
+            }
+        }
+        __syncthreads();
+        // ---- all-gather through distributed shared memory
+        double* gbuf = gath + (i & 1) * CS * kGath;
+        for (int idx = tid; idx < CS * kGath; idx += kThreads) {
+            const int dst = idx / kGath, e = idx - dst * kGath;
+            double* remote = cluster.map_shared_rank(gbuf, dst);
+            remote[r * kGath + e] = part[e];
+        }
+        cluster.sync();
+        // ---- totals (same order everywhere; the warp's two columns summed alongside the norm), scalars, local update
+        const int k0 = warp, k1 = warp + kWarps;
+        const bool v0 = k0 > i && k0 < nbk, v1 = k1 > i && k1 < nbk;
+        double ss = 0.0, d0 = 0.0, d1 = 0.0;
+        for (int q2 = 0; q2 < CS; ++q2) {
+            const double* gq = gbuf + q2 * kGath;
+            ss += gq[i]; d0 += gq[k0]; d1 += gq[k1];
+        }
+        const double al = gbuf[kNB + i], e0 = gbuf[kNB + k0], e1 = gbuf[kNB + k1];
+        double tau = 0.0, beta = al, scale = 0.0;
+        if (ss != 0.0) {  // dlarfg: xnorm == 0 -> H = I
+            const double nrm = sqrt(fma(al, al, ss));
+            beta = -copysign(nrm, al);  // Fortran SIGN semantics of dlarfg
+            tau = (beta - al) / beta;
+            scale = 1.0 / (al - beta);
+        }
+        if (tid == 0) { sc[3 * i] = tau; sc[3 * i + 1] = beta; sc[3 * i + 2] = scale; }
+        if (tau != 0.0 && (v0 || v1)) {
+            const double g0 = v0 ? -tau * fma(scale, d0, e0) : 0.0, g1 = v1 ? -tau * fma(scale, d1, e1) : 0.0;
+            const double gs0 = g0 * scale, gs1 = g1 * scale;
+            double* xa = PB + (size_t)(v0 ? k0 : k1) * Lc;
+            double* xb = PB + (size_t)k1 * Lc;
+            const double ga = v0 ? gs0 : gs1;
+            int cl = lo + lane;
+            for (; cl + 32 < nloc; cl += 64) {
+                const double p0 = xi[cl], p1 = xi[cl + 32];
+                const double y0 = xa[cl], y1 = xa[cl + 32];
+                xa[cl] = fma(ga, p0, y0); xa[cl + 32] = fma(ga, p1, y1);
+                if (v0 && v1) {
+                    const double z0 = xb[cl], z1 = xb[cl + 32];
+                    xb[cl] = fma(gs1, p0, z0); xb[cl + 32] = fma(gs1, p1, z1);
+                }
+            }
+            if (cl < nloc) {
+                xa[cl] = fma(ga, xi[cl], xa[cl]);
+                if (v0 && v1) xb[cl] = fma(gs1, xi[cl], xb[cl]);
+            }
+            if (r == 0 && lane == 0) {  // v = 1 at row i
+                if (v0) PB[(size_t)k0 * Lc + i] += g0;
+                if (v1) PB[(size_t)k1 * Lc + i] += g1;
+            }
+        }
+        __syncthreads();
+    }
+    // ---- write R back, export V (v = scale x below the diagonal, 1 on it, 0 above) to Vg and keep it in the slice
+    for (int cc = 0; cc < kNB; ++cc) {
+        const bool hc = cc < nbk;
+        const double tau = hc ? sc[3 * cc] : 0.0, beta = hc ? sc[3 * cc + 1] : 0.0, scale = hc ? sc[3 * cc + 2] : 0.0;
+        const int et = hc ? envc[cc] : -1, eb = hc ? envc[kNB + cc] : -1;
+        double* colp = PB + (size_t)cc * Lc;
+        double* wj = W + (size_t)(j0 + (hc ? cc : 0)) * ld;
+        double* vg = q.Vg + (size_t)cc * q.lv;
+        for (int cl = tid; cl < Lc; cl += kThreads) {
+            const int c = c_lo + cl;
+            const double xv = colp[cl];
+            double vv = 0.0;
+            if (hc && c < L) {
+                const int row = rm.row(c);
+                if (row < nt ? row <= et : row <= eb) wj[row] = c < cc ? xv : (c == cc ? beta : 0.0);
+                if (tau != 0.0) vv = c > cc ? xv * scale : (c == cc ? 1.0 : 0.0);
+            }
+            colp[cl] = vv;
+            if (c < ((L + 7) & ~7)) vg[c] = vv;
+        }
+    }
+    __syncthreads();
+    // ---- T factor: local Gram blocks (tensor pipe), summed on CTA 0 in a fixed order
+    large_gram(PB, Lc, nloc, ls.Gs, ls.scratch);   // rows beyond nloc of the slice are zero; Gs = this CTA's partial
+    double* gram_all = gath;                        // [CS][kNB * 17] on CTA 0 (the gather buffers are free now)
+    {
+        double* remote = cluster.map_shared_rank(gram_all, 0);
+        for (int e = tid; e < kNB * 17; e += kThreads) remote[r * kNB * 17 + e] = ls.Gs[e];
+    }
+    cluster.sync();
+    if (r == 0) {
+        for (int e = tid; e < kNB * 17; e += kThreads) {
+            double sum = 0.0;
+            for (int q2 = 0; q2 < CS; ++q2) sum += gram_all[q2 * kNB * 17 + e];
+            ls.Gs[e] = sum;
+        }
+        __syncthreads();
+        if (warp == 0) panel_t_factor(ls.Gs, sc, nbk, ls.Ts);
+        __syncthreads();
+        for (int idx = tid; idx < kNB * kLdr; idx += kThreads) q.Tg[idx] = ls.Ts[idx];
+    }
+}
+
 // S2: partial Y^T = C^T V per (row chunk, column group) item.
 __device__ void large_trailing_y(const double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
                                  const LargeQR& q, int RC, double* __restrict__ Vr) {
@@ -439,7 +608,16 @@ __device__ void householder_qr_large(cg::grid_group& grid, double* __restrict__ 
     for (int j0 = 0; j0 < nref; j0 += kNB) {
         const int nbk = nref - j0 < kNB ? nref - j0 : kNB;
         const RowMap rm = panel_rows(s, j0, j0 + nbk - 1);
-        if (blockIdx.x == 0) large_panel_factor(W, ld, s, j0, nbk, rm, q, ls, pc);
+        // panel on the cluster when it has at least kNB rows per CTA and the slice + exchange buffers fit
+        cg::cluster_group cluster = cg::this_cluster();
+        const int CS = (int)cluster.num_blocks();
+        const int Lc = ((rm.len + CS - 1) / CS + 7) & ~7;
+        const bool on_cluster = CS > 1 && Lc >= kNB && (size_t)kNB * Lc + 2 * CS * kGath + kGath + (size_t)CS * kNB * 17 <= (size_t)q.cap;
+        if (on_cluster) {
+            if (blockIdx.x < CS) large_panel_factor_cluster(cluster, W, ld, s, j0, nbk, rm, q, ls, Lc);
+        } else if (blockIdx.x == 0) {
+            large_panel_factor(W, ld, s, j0, nbk, rm, q, ls, pc);
+        }
         pc.mark(8);
         grid.sync();
         pc.mark(9);
