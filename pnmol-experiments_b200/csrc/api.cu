@@ -388,13 +388,23 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
         if (h->large) {
             // one member at a time on the whole grid: one workspace, vectors in global scratch
             LargeQR& q = h->q;
-            int cap = (int)(h->smem_optin / sizeof(double)) - kLargeFixed - 64;
+            // Panel buffer: half of the SM's shared memory when the problem allows it (two CTAs per SM: the trailing
+            // phases are latency-bound and the cluster panel only needs a row slice per CTA), else all of it.
+            const int lp = (maxlen + 7) & ~7;
+            const int cap_full = ((int)(h->smem_optin / sizeof(double)) - kLargeFixed - 64) & ~15;
+            const int cap_half = ((int)((h->smem_optin + 1024) / 2 / sizeof(double)) - 128 - kLargeFixed - 64) & ~15;
+            auto cb_for = [&](int c) { return (size_t)P.m * 17 <= (size_t)c ? 16 : (size_t)P.m * 9 <= (size_t)c ? 8 : (size_t)P.m * 5 <= (size_t)c ? 4 : 0; };
+            // (measured: two CTAs per SM speed the trailing phases up by 1.6x at C4 but slow the panel team down, whose
+            // SMs then also host a CTA spinning in the grid barrier: a gain only where the trailing update dominates)
+            bool two = PNMOL_LARGE_CTAS >= 2 && maxlen >= 2048 && lp <= cap_half && cb_for(cap_half) > 0;
+            if (const char* e = std::getenv("PNMOL_B200_LARGE_CTAS")) two = std::atoi(e) >= 2 && lp <= cap_half && cb_for(cap_half) > 0;
+            int cap = two ? cap_half : cap_full;
             if (const char* e = std::getenv("PNMOL_B200_LARGE_CAP")) cap = std::max(1280, std::min(cap, std::atoi(e)));  // >= one 64-row V chunk (64 x kLdr)
             cap &= ~15;
-            const int lp = (maxlen + 7) & ~7;
-            if (lp > cap || (size_t)P.m * 17 > (size_t)cap)
+            if (lp > cap || cb_for(cap) == 0)
                 return fail(-1, "state dimension too large: one panel column does not fit in shared memory");
             q.cap = cap;
+            q.cb = cb_for(cap);
             q.lv = lp + 8;
             q.ycols = P.m + P.D;
             h->smem_large = (size_t)(kLargeFixed + cap) * sizeof(double);
@@ -405,7 +415,7 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_large, kThreads, h->smem_large));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_init_large, kThreads, h->smem_large));
             if (std::min(occ, occ2) < 1) return fail(-1, "multi-CTA kernels do not fit on an SM");
-            h->grid = h->num_sms;
+            h->grid = h->num_sms * std::min(std::min(occ, occ2), PNMOL_LARGE_CTAS);
             if (const char* e = std::getenv("PNMOL_B200_GRID")) h->grid = std::max(1, std::min(h->grid, std::atoi(e)));
             // thread-block clusters: the panel factorisation runs on cluster 0 (rows split over its CTAs)
             h->cluster = 1;

@@ -6,6 +6,9 @@
 #include "ek1_kernels.cuh"
 #include "qr_large.cuh"
 
+#ifndef PNMOL_LARGE_CTAS
+#define PNMOL_LARGE_CTAS 2   // CTAs per SM the multi-CTA kernels are compiled for (128 registers per thread)
+#endif
 namespace pnmol {
 
 __device__ __forceinline__ Smem large_vectors(const Problem& P, const LargeQR& q, const LargeSmem& ls) {
@@ -71,14 +74,15 @@ __device__ void error_estimate_large(cg::grid_group& grid, const Problem& P, int
     // Right-looking blocked Cholesky of the lower triangle (row-major), panels of kCB columns staged in shared memory
     // (leading dimension kCB + 1): CTA 0 factors the (m - k0) x kCB panel there and writes L back (its diagonal also to
     // q.Ld), then every CTA stages the panel and applies the rank-kCB update to its share of the rows below.
-    constexpr int kCB = 16, kCL = kCB + 1;
+    constexpr int kCB = 16;         // widest panel; q.cb (16, 8 or 4) is what fits the panel buffer
+    const int cbw = q.cb, kCL = q.cb + 1;
     double* Lp = ls.PB;
-    for (int k0 = 0; k0 < m; k0 += kCB) {
-        const int kb = m - k0 < kCB ? m - k0 : kCB;
+    for (int k0 = 0; k0 < m; k0 += cbw) {
+        const int kb = m - k0 < cbw ? m - k0 : cbw;
         const int pr = m - k0;  // panel rows
         if (blockIdx.x == 0) {
-            for (int idx = tid; idx < pr * kCB; idx += kThreads) {
-                const int r = idx / kCB, kk = idx - r * kCB;
+            for (int idx = tid; idx < pr * cbw; idx += kThreads) {
+                const int r = idx / cbw, kk = idx - r * cbw;
                 Lp[r * kCL + kk] = (kk < kb && kk <= r) ? S[(size_t)(k0 + r) * m + k0 + kk] : 0.0;
             }
             __syncthreads();
@@ -95,8 +99,8 @@ __device__ void error_estimate_large(cg::grid_group& grid, const Problem& P, int
                 }
                 __syncthreads();
             }
-            for (int idx = tid; idx < pr * kCB; idx += kThreads) {
-                const int r = idx / kCB, kk = idx - r * kCB;
+            for (int idx = tid; idx < pr * cbw; idx += kThreads) {
+                const int r = idx / cbw, kk = idx - r * cbw;
                 if (kk < kb && kk <= r) S[(size_t)(k0 + r) * m + k0 + kk] = Lp[r * kCL + kk];
             }
             if (tid < kb) q.Ld[k0 + tid] = Lp[tid * kCL + tid];
@@ -106,8 +110,8 @@ __device__ void error_estimate_large(cg::grid_group& grid, const Problem& P, int
         if (c0 < m) {
             const int tr = m - c0;  // rows below the panel
             if (blockIdx.x != 0) {  // (CTA 0 still holds the panel: rows c0.. start at local row kb)
-                for (int idx = tid; idx < tr * kCB; idx += kThreads) {
-                    const int r = idx / kCB, kk = idx - r * kCB;
+                for (int idx = tid; idx < tr * cbw; idx += kThreads) {
+                    const int r = idx / cbw, kk = idx - r * cbw;
                     Lp[(kb + r) * kCL + kk] = kk < kb ? S[(size_t)(c0 + r) * m + k0 + kk] : 0.0;
                 }
             }
@@ -115,12 +119,14 @@ __device__ void error_estimate_large(cg::grid_group& grid, const Problem& P, int
             for (int r = c0 + gw; r < m; r += gnw) {  // S[r][c] -= sum_k L[r][k] L[c][k],  c0 <= c <= r
                 double lr[kCB];
 #pragma unroll
-                for (int kk = 0; kk < kCB; ++kk) lr[kk] = kk < kb ? Lp[(r - k0) * kCL + kk] : 0.0;
+                for (int kk = 0; kk < kCB; ++kk) lr[kk] = kk < kb ? Lp[(r - k0) * kCL + kk] : 0.0;  // (zero beyond the panel width)
                 for (int c = c0 + lane; c <= r; c += 32) {
                     const double* lc = Lp + (c - k0) * kCL;
                     double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-                    for (int kk = 0; kk < kCB; kk += 2) { a0 = fma(lr[kk], lc[kk], a0); a1 = fma(lr[kk + 1], lc[kk + 1], a1); }
+                    for (int kk = 0; kk < kCB; kk += 2) {
+                        if (kk < cbw) { a0 = fma(lr[kk], lc[kk], a0); a1 = fma(lr[kk + 1], lc[kk + 1], a1); }
+                    }
                     S[(size_t)r * m + c] -= a0 + a1;
                 }
             }
@@ -185,7 +191,7 @@ __device__ void update_stage_large(cg::grid_group& grid, const Problem& P, int b
     pc.mark(7);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_run_large(const Problem P, const RunArgs a, const LargeQR q) {
+__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const Problem P, const RunArgs a, const LargeQR q) {
     extern __shared__ double smem_raw[];
     cg::grid_group grid = cg::this_grid();
     const LargeSmem ls = carve_large(smem_raw);
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_run_large(const Problem P, cons
 }
 
 // initialize() (white.py:12-80, latent.py:20-134) on the grid.
-__global__ void __launch_bounds__(kThreads, 1) k_init_large(const Problem P, const InitArgs a, const LargeQR q) {
+__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_init_large(const Problem P, const InitArgs a, const LargeQR q) {
     extern __shared__ double smem_raw[];
     cg::grid_group grid = cg::this_grid();
     const LargeSmem ls = carve_large(smem_raw);

@@ -32,6 +32,7 @@ struct LargeQR {   // global scratch of the multi-CTA path (one set per handle)
     double* Ld;    // [m] diagonal of the Cholesky factor of S (error estimate)
     int32_t* nf;   // non-finite flag of the member in flight
     int lv, ycols, cap;  // cap: panel buffer capacity (doubles of shared memory)
+    int cb;              // panel width of the blocked Cholesky in the error estimate (16, 8 or 4)
 };
 
 struct LargeSmem {
