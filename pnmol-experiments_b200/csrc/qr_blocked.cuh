@@ -609,18 +609,30 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
     // ---- load this group's panel column (entries outside the column's own envelope are zero)
     // round-robin ownership (column p -> warp p % kWarps, group p / kWarps): consecutive reflectors are owned by
     // different warps, so the owner's post-work overlaps with the next owner's critical chain
+    // For G = 32 (one group per warp) a group holds a SECOND panel column in x1 (column p0 + kWarps), so that panels
+    // stay kNB = 16 columns wide for row lists of 129 .. 256 rows as well.
+    constexpr bool kTwo = G == 32;
     const int p0 = warp + kWarps * g;
     const bool hp = p0 < nbk && g < PPW;
     const int jp = j0 + (hp ? p0 : 0);
     const int etp = hp ? env_top(s, jp) : -1, ebp = hp ? env_bot(s, jp) : -1;
+    const int p1 = p0 + kWarps * PPW;
+    const bool hq = kTwo && p1 < nbk && g < PPW;
+    const int jq = j0 + (hq ? p1 : 0);
+    const int etq = hq ? env_top(s, jq) : -1, ebq = hq ? env_bot(s, jq) : -1;
     {
         const double* c0 = W + (size_t)jp * ld;
+        const double* c1 = W + (size_t)jq * ld;
 #pragma unroll
         for (int r = 0; r < kRPL; ++r) {
             const int c = sl + G * r;
             const int row = rm.row(c);
             const bool ok = c < rm.len && (row < nt ? row <= etp : row <= ebp);
             x0[r] = ok ? c0[row] : 0.0;
+            if (kTwo) {
+                const bool ok1 = hq && c < rm.len && (row < nt ? row <= etq : row <= ebq);
+                x1[r] = ok1 ? c1[row] : 0.0;
+            }
         }
     }
     pc.mark(8);
@@ -630,24 +642,26 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
     // that still holds a live column reduces x_i . x_k and derives the reflector scalars (dlarfg) redundantly.
     int wlast = -1;  // last panel column held by this warp
 #pragma unroll
-    for (int gg = 0; gg < PPW; ++gg)
+    for (int gg = 0; gg < PPW * (kTwo ? 2 : 1); ++gg)
         if (warp + kWarps * gg < nbk) wlast = warp + kWarps * gg;
     for (int i = 0; i < nbk; ++i) {
-        const bool own = hp && p0 == i;
+        const bool own1 = hq && p1 == i;  // (the pivot column is this group's second column)
+        const bool own = (hp && p0 == i) || own1;
         const int ri = G >= kNB ? 0 : i / G, si = G >= kNB ? i : i % G;  // register slot and lane that hold row i (slot 0 for G >= 16: compile time)
         double* xr = xraw + (i & 1) * vld;  // double buffered: the next owner may publish while others still read
         if (own) {
 #pragma unroll
             for (int r = 0; r < kRPL; ++r) {
                 const bool gt = r > ri || (r == ri && sl > si);
-                xr[sl + G * r] = gt ? x0[r] : 0.0;
-                if (r == ri && sl == si) sc[3 * i + 1] = x0[r];
+                const double xo = (kTwo && own1) ? x1[r] : x0[r];
+                xr[sl + G * r] = gt ? xo : 0.0;
+                if (r == ri && sl == si) sc[3 * i + 1] = xo;
             }
         }
         __syncthreads();
         if (wlast < i) continue;  // no live panel column in this warp: only keep the barrier
         const double al = sc[3 * i + 1];
-        double d0 = 0.0, ss = 0.0, d0b = 0.0, ssb = 0.0;
+        double d0 = 0.0, ss = 0.0, d0b = 0.0, ssb = 0.0, d1 = 0.0, d1b = 0.0;
 #pragma unroll
         for (int q = 0; q < kQ; ++q) {
             if (q < nq) {
@@ -659,17 +673,24 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
                     ss = fma(t, t, ss);
                     d0b = fma(u, x0[r + 1], d0b);
                     ssb = fma(u, u, ssb);
+                    if (kTwo) { d1 = fma(t, x1[r], d1); d1b = fma(u, x1[r + 1], d1b); }
                 }
             }
         }
-        d0 += d0b; ss += ssb;
+        d0 += d0b; ss += ssb; d1 += d1b;
         // entry of this group's column at row i: slot ri of lane si
         double e0 = x0[0];
         if (G < 16 && ri == 1) e0 = x0[1];
         if (G < 8 && ri == 2) e0 = x0[2];
         if (G < 8 && ri == 3) e0 = x0[3];
         e0 = __shfl_sync(0xffffffffu, e0, (lane & ~(G - 1)) | si);
-        group_sum2<G>(d0, ss);
+        double e1 = 0.0;
+        if (kTwo) {
+            e1 = __shfl_sync(0xffffffffu, x1[0], si);  // (G = 32: row i is slot 0 of lane i)
+            group_sum3<G>(d0, ss, d1);
+        } else {
+            group_sum2<G>(d0, ss);
+        }
         // dlarfg on (alpha, ||x||^2): beta = -sign(alpha) ||(alpha, x)||, tau = (beta - alpha) / beta, v = x / (alpha - beta)
         double tau = 0.0, beta = al, scale = 0.0;
         if (ss != 0.0) {  // zero sub-column -> H = I
@@ -688,16 +709,21 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
         if (tau != 0.0) {
             const double f0 = p0 > i && hp ? -tau * fma(scale, d0, e0) : 0.0;
             const double g0 = f0 * scale;
+            const double f1 = (kTwo && p1 > i && hq) ? -tau * fma(scale, d1, e1) : 0.0;
+            const double g1 = f1 * scale;
 #pragma unroll
             for (int q = 0; q < kQ; ++q) {
                 if (q < nq) {
 #pragma unroll
                     for (int rr = 0; rr < 4; ++rr) {
                         const int r = 4 * q + rr;
-                        x0[r] = fma(g0, xr[sl + G * r], x0[r]);
+                        const double t = xr[sl + G * r];
+                        x0[r] = fma(g0, t, x0[r]);
+                        if (kTwo) x1[r] = fma(g1, t, x1[r]);
                     }
                 }
             }
+            if (kTwo && sl == si) x1[0] += f1;  // (ri = 0 for G = 32)
             if (sl == si) {  // v = 1 at row i
                 x0[0] += ri == 0 ? f0 : 0.0;
                 if (G < 16) x0[1] += ri == 1 ? f0 : 0.0;
@@ -711,7 +737,10 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
                     const double vv = eq ? 1.0 : scale * xr[sl + G * r];
                     Vs[i * ldt + sl + G * r] = vv;
                     Vr[(sl + G * r) * kLdr + i] = vv;
-                    if (ge) x0[r] = eq ? beta : 0.0;
+                    if (ge) {
+                        if (kTwo && own1) x1[r] = eq ? beta : 0.0;
+                        else x0[r] = eq ? beta : 0.0;
+                    }
                 }
             }
         }
@@ -726,6 +755,15 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
             const int c = sl + G * r;
             const int row = rm.row(c);
             if (c < rm.len && (row < nt ? row <= etp : row <= ebp)) c0[row] = x0[r];
+        }
+    }
+    if (kTwo && hq) {
+        double* c1 = W + (size_t)jq * ld;
+#pragma unroll
+        for (int r = 0; r < kRPL; ++r) {
+            const int c = sl + G * r;
+            const int row = rm.row(c);
+            if (c < rm.len && (row < nt ? row <= etq : row <= ebq)) c1[row] = x1[r];
         }
     }
     __syncthreads();  // all of Vs / sc written
@@ -804,11 +842,14 @@ __device__ void householder_qr_blocked(double* __restrict__ W, int ld, const Sha
     const int nref = nrows < s.ncols ? nrows : s.ncols;
     int j0 = 0;
     while (j0 < nref) {
-        int nbk = nref - j0 < kNB ? nref - j0 : kNB;
+#ifndef PNMOL_PANEL_CAP
+#define PNMOL_PANEL_CAP kNB
+#endif
+        int nbk = nref - j0 < PNMOL_PANEL_CAP ? nref - j0 : PNMOL_PANEL_CAP;  // (tuning: narrower panels)
         RowMap rm = panel_rows(s, j0, j0 + nbk - 1);
         // lanes per column: the smallest group that holds the row list in kRPL rows per lane
         const int G = rm.len <= 4 * kRPL ? 4 : rm.len <= 8 * kRPL ? 8 : rm.len <= 16 * kRPL ? 16 : 32;
-        const int cap = kWarps * (32 / G);  // panel columns the CTA can hold in registers (one per lane group)
+        const int cap = kWarps * (32 / G) * (G == 32 ? 2 : 1);  // panel columns the CTA can hold in registers (one per lane group, two for G = 32)
         if (nbk > cap) {
             nbk = cap;
             rm = panel_rows(s, j0, j0 + nbk - 1);
