@@ -603,7 +603,9 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / G, sl = lane % G;
     const int nt = s.nt;
-    const int nq = (rm.len + 4 * G - 1) / (4 * G);  // row chunks (of 4 per lane) that hold data
+    // row chunks (of 4 per lane) that hold data; the driver picks the smallest G with kRPL * G >= len, so for G >= 8 more
+    // than half of the kRPL rows per lane are in use and all kQ chunks are live (compile time: no guards in the loops)
+    const int nq = (G >= 8 && kRPL == 8) ? kQ : (rm.len + 4 * G - 1) / (4 * G);
     double x0[kRPL], x1[kRPL];
 
     // ---- load this group's panel column (entries outside the column's own envelope are zero)
