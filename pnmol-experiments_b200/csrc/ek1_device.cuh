@@ -370,19 +370,24 @@ __device__ void build_predict(const Problem& P, int b, const Smem& sm, const dou
             for (int s = 0; s < n; ++s) acc = fma(coef[s], sm.pinv[s] * PNMOL_STATE_LOAD(Cl + (size_t)(blk * n + s) * D + k), acc);
             col[k] = acc;
         }
-        // Ql^T column i = row i of Ql, entries 0..i
+        // Ql^T column i = row i of Ql, entries 0..i  (lanes over the n x n blocks: no integer divisions per entry)
         if (i < nd) {
-            for (int k = lane; k <= i; k += 32) {
-                const int kb = k / n, kk = k - kb * n;
-                col[D + k] = (ps * P.Lk[(size_t)blk * P.d + kb]) * P.LQ1d[ii * n + kk];
+            for (int kb = lane; kb <= blk; kb += 32) {
+                const double lk = ps * P.Lk[(size_t)blk * P.d + kb];
+                for (int kk = 0; kk < n; ++kk) {
+                    const int k = kb * n + kk;
+                    if (k <= i) col[D + k] = lk * P.LQ1d[ii * n + kk];
+                }
             }
         } else {
             const int comp = (blk - P.d) / P.npts;
             const double ds = P.diffscale ? P.diffscale[(size_t)b * P.ncomp + comp] : 1.0;
             const double eb = ds * P.Ediag[blk - P.d];
-            for (int k = lane; k <= i; k += 32) {
-                const int kb = k / n, kk = k - kb * n;
-                col[D + k] = kb == blk ? eb * P.LQ1d[ii * n + kk] : 0.0;
+            for (int kb = lane; kb <= blk; kb += 32) {
+                for (int kk = 0; kk < n; ++kk) {
+                    const int k = kb * n + kk;
+                    if (k <= i) col[D + k] = kb == blk ? eb * P.LQ1d[ii * n + kk] : 0.0;
+                }
             }
         }
     }
@@ -552,10 +557,9 @@ __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, dou
         for (int r = k + 1 + tid; r < m; r += T::size) S[r * ldm + k] *= rinv;
         if (tid == 0) sm.xw[k] = skk * rinv;
         T::sync();
-        const int rem = m - k - 1;
-        for (int idx = tid; idx < rem * rem; idx += T::size) {
-            const int r = k + 1 + idx / rem, c = k + 1 + idx % rem;
-            if (c <= r) S[r * ldm + c] = fma(-S[r * ldm + k], S[c * ldm + k], S[r * ldm + c]);
+        for (int r = k + 1 + warp; r < m; r += T::nwarps) {  // (warp per row, lanes over the columns: no divisions)
+            const double lrk = S[r * ldm + k];
+            for (int c = k + 1 + lane; c <= r; c += 32) S[r * ldm + c] = fma(-lrk, S[c * ldm + k], S[r * ldm + c]);
         }
     }
     T::sync();
