@@ -703,46 +703,42 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
             tau = (beta - al) * -copysign(rn, al);
             scale = __drcp_rn(al - beta);
         }
-        if (own && sl == 0) sc[3 * i] = tau;
-        if (own && tau == 0.0) {
+        // (tau == 0: H = I; f, g and scale are then zero, the update below adds zeros and v is stored as zero)
+        const double f0 = p0 > i && hp ? -tau * fma(scale, d0, e0) : 0.0;
+        const double g0 = f0 * scale;
+        const double f1 = (kTwo && p1 > i && hq) ? -tau * fma(scale, d1, e1) : 0.0;
+        const double g1 = f1 * scale;
 #pragma unroll
-            for (int r = 0; r < kRPL; ++r) { Vs[i * ldt + sl + G * r] = 0.0; Vr[(sl + G * r) * kLdr + i] = 0.0; }
-        }
-        if (tau != 0.0) {
-            const double f0 = p0 > i && hp ? -tau * fma(scale, d0, e0) : 0.0;
-            const double g0 = f0 * scale;
-            const double f1 = (kTwo && p1 > i && hq) ? -tau * fma(scale, d1, e1) : 0.0;
-            const double g1 = f1 * scale;
+        for (int q = 0; q < kQ; ++q) {
+            if (q < nq) {
 #pragma unroll
-            for (int q = 0; q < kQ; ++q) {
-                if (q < nq) {
-#pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
-                        const int r = 4 * q + rr;
-                        const double t = xr[sl + G * r];
-                        x0[r] = fma(g0, t, x0[r]);
-                        if (kTwo) x1[r] = fma(g1, t, x1[r]);
-                    }
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int r = 4 * q + rr;
+                    const double t = xr[sl + G * r];
+                    x0[r] = fma(g0, t, x0[r]);
+                    if (kTwo) x1[r] = fma(g1, t, x1[r]);
                 }
             }
-            if (kTwo && sl == si) x1[0] += f1;  // (ri = 0 for G = 32)
-            if (sl == si) {  // v = 1 at row i
-                x0[0] += ri == 0 ? f0 : 0.0;
-                if (G < 16) x0[1] += ri == 1 ? f0 : 0.0;
-                if (G < 8) { x0[2] += ri == 2 ? f0 : 0.0; x0[3] += ri == 3 ? f0 : 0.0; }
-            }
-            if (own) {  // reflector into Vs; the column itself becomes (R entries, beta, zeros)
+        }
+        if (kTwo && sl == si) x1[0] += f1;  // (ri = 0 for G = 32)
+        if (sl == si) {  // v = 1 at row i
+            x0[0] += ri == 0 ? f0 : 0.0;
+            if (G < 16) x0[1] += ri == 1 ? f0 : 0.0;
+            if (G < 8) { x0[2] += ri == 2 ? f0 : 0.0; x0[3] += ri == 3 ? f0 : 0.0; }
+        }
+        if (own) {  // reflector into Vs; the column itself becomes (R entries, beta, zeros)
+            if (sl == 0) sc[3 * i] = tau;
+            const double one = tau != 0.0 ? 1.0 : 0.0;
 #pragma unroll
-                for (int r = 0; r < kRPL; ++r) {
-                    const bool eq = r == ri && sl == si;
-                    const bool ge = r > ri || (r == ri && sl >= si);
-                    const double vv = eq ? 1.0 : scale * xr[sl + G * r];
-                    Vs[i * ldt + sl + G * r] = vv;
-                    Vr[(sl + G * r) * kLdr + i] = vv;
-                    if (ge) {
-                        if (kTwo && own1) x1[r] = eq ? beta : 0.0;
-                        else x0[r] = eq ? beta : 0.0;
-                    }
+            for (int r = 0; r < kRPL; ++r) {
+                const bool eq = r == ri && sl == si;
+                const bool ge = r > ri || (r == ri && sl >= si);
+                const double vv = eq ? one : scale * xr[sl + G * r];
+                Vs[i * ldt + sl + G * r] = vv;
+                Vr[(sl + G * r) * kLdr + i] = vv;
+                if (ge) {
+                    if (kTwo && own1) x1[r] = eq ? beta : 0.0;
+                    else x0[r] = eq ? beta : 0.0;
                 }
             }
         }
