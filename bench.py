@@ -52,9 +52,9 @@ def member_parameters(num_members, x, seed):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of pnmol::k_run per member-step, from the committed `ncu --set full`
-# capture profiles/r01_ncu_k_run_full_summary_v7.csv (296 members x 8 steps per launch: 779 MB read + 2960 MB written).
+# capture profiles/r01_ncu_k_run_full_summary_v8.csv (296 members x 8 steps per launch: 727 MB read + 2777 MB written).
 # Four times the algorithmic 363 KB: the L2-resident per-CTA workspaces are written back to HBM as dirty lines.
-NCU_DRAM_BYTES_PER_MEMBER_STEP = (779.428096e6 + 2959.760e6) / (296 * 8)
+NCU_DRAM_BYTES_PER_MEMBER_STEP = (726.918400e6 + 2776.589e6) / (296 * 8)
 
 
 def work_model(D, m, d):
@@ -292,7 +292,7 @@ def run_b200_arm(args):
     roofline = {"bound": "tensor", "pipe": "fp64 (mma.sync DMMA + DFMA; tcgen05 has no FP64 MMA)", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
                 "traffic": NCU_DRAM_BYTES_PER_MEMBER_STEP * M * T,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per member-step "
-                                  "(profiles/r01_ncu_k_run_full_summary_v7.csv) x member-steps per launch",
+                                  "(profiles/r01_ncu_k_run_full_summary_v8.csv) x member-steps per launch",
                 "kernel": "pnmol::k_run", "kernel_ms_per_launch": kernel_ms,
                 "algorithmic_flops_per_member_step": f_alg, "algorithmic_bytes_per_member_step": b_alg,
                 "peak_source": "measured in this run: cuBLAS DGEMM 4096^3 via torch.matmul(float64), best of 5 "
