@@ -614,11 +614,14 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
     // For G = 32 (one group per warp) a group holds a SECOND panel column in x1 (column p0 + kWarps), so that panels
     // stay kNB = 16 columns wide for row lists of 129 .. 256 rows as well.
     constexpr bool kTwo = G == 32;
-    const int p0 = warp + kWarps * g;
-    const bool hp = p0 < nbk && g < PPW;
+    // Only as many warps as the kNB columns need take part (8 for G >= 16, 4 for G = 8, 2 for G = 4): the others just
+    // keep the barriers, which removes their share of the (redundant) per-column instructions.
+    constexpr int NWU = kNB / PPW < kWarps ? (kNB / PPW > 0 ? kNB / PPW : 1) : kWarps;
+    const int p0 = warp + NWU * g;
+    const bool hp = p0 < nbk && g < PPW && warp < NWU;
     const int jp = j0 + (hp ? p0 : 0);
     const int etp = hp ? env_top(s, jp) : -1, ebp = hp ? env_bot(s, jp) : -1;
-    const int p1 = p0 + kWarps * PPW;
+    const int p1 = p0 + NWU * PPW;
     const bool hq = kTwo && p1 < nbk && g < PPW;
     const int jq = j0 + (hq ? p1 : 0);
     const int etq = hq ? env_top(s, jq) : -1, ebq = hq ? env_bot(s, jq) : -1;
@@ -645,7 +648,7 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
     int wlast = -1;  // last panel column held by this warp
 #pragma unroll
     for (int gg = 0; gg < PPW * (kTwo ? 2 : 1); ++gg)
-        if (warp + kWarps * gg < nbk) wlast = warp + kWarps * gg;
+        if (warp < NWU && warp + NWU * gg < nbk) wlast = warp + NWU * gg;
     for (int i = 0; i < nbk; ++i) {
         const bool own1 = hq && p1 == i;  // (the pivot column is this group's second column)
         const bool own = (hp && p0 == i) || own1;
