@@ -339,7 +339,7 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
         maxlen = std::max(maxlen, max_panel_len(P.D, P.d, P.d + P.D, nullptr, nullptr, P.ld));   // initialisation updates
         maxlen = std::max(maxlen, max_panel_len(P.D, P.m, P.m + P.D, nullptr, nullptr, P.ld));
         const int G = maxlen <= 4 * kRPL ? 4 : maxlen <= 8 * kRPL ? 8 : maxlen <= 16 * kRPL ? 16 : 32;
-        P.vld = kRPL * G;
+        P.vld = std::max(64, kRPL * G);  // rows of the panel buffers of the blocked QR (LP: 64, 128 or 256)
         P.ldm = P.m <= 96 ? (P.m | 1) : 0;  // odd leading dimension: conflict-free rows and columns
         h->smem_bytes = smem_doubles(P.D, P.m, P.dd, P.vld, P.ldm) * sizeof(double);
         const char* force = std::getenv("PNMOL_B200_FORCE_LARGE");

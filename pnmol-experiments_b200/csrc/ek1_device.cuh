@@ -80,8 +80,20 @@ struct Shape {  // QR row structure: rows [0,nt) top, [nt, nt+nbot) bottom
     int ldr = 0;  // > 0: rows that exist in every workspace column; panel row lists are then aligned to 8-row tiles
 };
 
+struct FastQR {       // shared-memory buffers of the blocked QR (qr_fast.cuh), as offsets in doubles from the base of the
+    unsigned buf[2];   // dynamic shared memory: 2 x (16 x LP) panel / reflector buffers, XOR-swizzled reflector-major
+    unsigned Ts[2];    // 2 x (16 x 18): T factors
+    unsigned Gs;       // 16 x 17 Gram matrix V^T V (upper triangle)
+    unsigned scratch;  // 4 x 192 per-warp Gram partials
+    unsigned tau;      // 2 x 16
+    unsigned t4;       // 4 x 4 T factor of the current sub-panel
+    int LP;            // rows of a buffer: 64, 128 or 256, >= every panel row list
+};
+
 struct Smem {
     double *vbuf, *mp, *z, *y, *xw, *xat, *red, *pv, *pinv, *Vs, *xraw, *sc, *msq, *Vr, *Ts, *Gs;
+    FastQR fq;
+    double *fqbase, *fqend;
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -118,13 +130,18 @@ struct WarpTeam {
     static __device__ __forceinline__ double sum(double v, double*) { return warp_sum(v); }
 };
 
+__host__ __device__ __forceinline__ size_t fastqr_doubles(int LP) {
+    return 2 * (size_t)16 * LP + 2 * (size_t)16 * 18 + 16 * 17 + 4 * 192 + 2 * 16 + 16;
+}
+
+// vld = rows of a panel buffer (LP of the blocked QR: 64, 128 or 256)
 __host__ __device__ __forceinline__ size_t smem_doubles(int D, int m, int dd, int vld, int ldm) {
-    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 80 + 2 * (size_t)vld + 16 * ((size_t)vld + 2) + 18 * (size_t)vld + 288 + 272 +
-           (size_t)m * ldm + 8;
+    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 80 + fastqr_doubles(vld) + (size_t)m * ldm + 8;
 }
 
 __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vld, int ldm) {
     Smem s;
+    double* const base0 = base;
     s.vbuf = base;              base += 2 * D + 4;
     s.mp = base;                base += D;
     s.z = base;                 base += m;
@@ -135,11 +152,18 @@ __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vl
     s.pv = base;                base += kMaxN;
     s.pinv = base;              base += kMaxN;
     s.sc = base;                base += 80;
-    s.xraw = base;              base += 2 * vld;
-    s.Vs = base;                base += 16 * (vld + 2);
-    s.Vr = base;                base += 18 * vld;
-    s.Ts = base;                base += 288;
-    s.Gs = base;                base += 272;
+    s.xraw = nullptr; s.Vs = nullptr; s.Vr = nullptr; s.Ts = nullptr; s.Gs = nullptr;
+    s.fq.LP = vld;
+    s.fqbase = base;            // (zeroed at kernel start: reflector buffers start finite)
+    s.fq.buf[0] = (unsigned)(base - base0); base += (size_t)16 * vld;
+    s.fq.buf[1] = (unsigned)(base - base0); base += (size_t)16 * vld;
+    s.fq.Ts[0] = (unsigned)(base - base0);  base += 16 * 18;
+    s.fq.Ts[1] = (unsigned)(base - base0);  base += 16 * 18;
+    s.fq.Gs = (unsigned)(base - base0);     base += 16 * 17;
+    s.fq.scratch = (unsigned)(base - base0); base += 4 * 192;
+    s.fq.tau = (unsigned)(base - base0);    base += 2 * 16;
+    s.fq.t4 = (unsigned)(base - base0);     base += 16;
+    s.fqend = base;
     s.msq = ldm > 0 ? base : nullptr;
     return s;
 }
@@ -232,6 +256,7 @@ __device__ __forceinline__ double* qr_scratch(const Problem& P, const Smem& sm) 
 }  // namespace pnmol
 
 #include "qr_blocked.cuh"
+#include "qr_fast.cuh"
 
 namespace pnmol {
 
@@ -831,7 +856,7 @@ __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, 
     pc.mark(4);
     Shape sh;
     sh.nt = D; sh.nbot = nbot; sh.ncols = ncols; sh.te = te; sh.be = be; sh.ldr = ld;
-    householder_qr_blocked(Wl, ld, sh, sm.Vs, P.vld, sm.xraw, sm.sc, sm.Vr, sm.Ts, sm.Gs, qr_scratch(P, sm), sm.vbuf, sm.red, pc);
+    householder_qr_fast(Wl, ld, sh, sm.fq, pc);
     pc.mark(5);
 
     const double diff = update_solve(P, sm, mcur, Wl, Wr);

@@ -63,7 +63,7 @@ __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, doub
     pc.mark(1);
     Shape sp;
     sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p; sp.ldr = P.ld;
-    householder_qr_blocked(W + (size_t)P.m * P.ld, P.ld, sp, sm.Vs, P.vld, sm.xraw, sm.sc, sm.Vr, sm.Ts, sm.Gs, qr_scratch(P, sm), sm.vbuf, sm.red, pc);
+    householder_qr_fast(W + (size_t)P.m * P.ld, P.ld, sp, sm.fq, pc);
     pc.mark(2);
     if (!P.latent && !(flags & 2)) {
         error_estimate(P, b, sm, sm.pv[1], dt, E_STEP_WHITE, 0.0, Hcol, Hval, P.F + (size_t)slot * P.m * P.d,
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem 
     const Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm);
     __shared__ int nonfinite;
     __shared__ double diff_s;
-    for (double* q = sm.xraw + threadIdx.x; q < sm.Gs + 272; q += kThreads) *q = 0.0;  // reflector buffers start finite
+    for (double* q = sm.fqbase + threadIdx.x; q < sm.fqend; q += kThreads) *q = 0.0;  // reflector buffers start finite
     const int tid = threadIdx.x;
     const size_t msz = (size_t)P.D, csz = (size_t)P.D * P.D;
     for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run_adaptive(const
     const Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm);
     __shared__ int nonfinite;
     __shared__ double diff_s;
-    for (double* q = sm.xraw + threadIdx.x; q < sm.Gs + 272; q += kThreads) *q = 0.0;  // reflector buffers start finite
+    for (double* q = sm.fqbase + threadIdx.x; q < sm.fqend; q += kThreads) *q = 0.0;  // reflector buffers start finite
     const int tid = threadIdx.x;
     const int nu = P.n - 1;
     const size_t msz = (size_t)P.D, csz = (size_t)P.D * P.D;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_init(const Problem
     extern __shared__ double smem_raw[];
     const Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm);
     __shared__ int nonfinite;
-    for (double* q = sm.xraw + threadIdx.x; q < sm.Gs + 272; q += kThreads) *q = 0.0;  // reflector buffers start finite
+    for (double* q = sm.fqbase + threadIdx.x; q < sm.fqend; q += kThreads) *q = 0.0;  // reflector buffers start finite
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = P.n, d = P.d, D = P.D, nd = P.n * P.d;
     const int slot = blockIdx.x;
