@@ -3,7 +3,6 @@
 #include "../../include/pnmol_b200.h"
 #include "ek1_kernels.cuh"
 #include "ek1_large.cuh"
-#include "ek1_warp.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -89,29 +88,6 @@ int max_panel_len(int nt, int nbot, int ncols, const int32_t* te, const int32_t*
     return best;
 }
 
-// Largest padded row list (qr_warp.cuh: pad_map) of any kWNB-wide panel, mirroring panel_rows.
-int max_padded_len(int nt, int nbot, int ncols, const int32_t* te, const int32_t* be) {
-    const int nrows = nt + nbot, nref = std::min(nrows, ncols);
-    int best = 8;
-    for (int j0 = 0; j0 < nref; j0 += kWNB) {
-        const int jl = std::min(j0 + kWNB, nref) - 1;
-        auto top = [&](int j) { return std::min(te ? te[j] : nt - 1, nt - 1); };
-        auto bot = [&](int j) { return std::min(be ? be[j] : nrows - 1, nrows - 1); };
-        int len1, a2, len;
-        if (j0 < nt) {
-            const int jt = std::min(jl, nt - 1);
-            const int e1 = std::max(top(jt), jt), e2 = bot(jl);
-            len1 = e1 - j0 + 1; a2 = nt;
-            len = len1 + (e2 >= nt ? e2 - nt + 1 : 0);
-        } else {
-            len1 = 0; a2 = j0;
-            len = std::max(bot(jl), jl) - j0 + 1;
-        }
-        best = std::max(best, pad_map(j0, len1, a2, len).Lp);
-    }
-    return best;
-}
-
 }  // namespace
 
 struct pnmol_b200_handle {
@@ -133,10 +109,6 @@ struct pnmol_b200_handle {
     LargeQR q{};
     size_t smem_large = 0;
     int cluster = 1;  // thread-block cluster size of the multi-CTA kernels (panel factorisation on cluster 0)
-    // warp-per-member path (ek1_warp.cuh): every panel row list <= 256 rows; PNMOL_B200_PATH=cta|warp|large overrides
-    bool warp = false;
-    WarpGeom geo{};
-    size_t smem_warp = 0;
 };
 
 namespace {
@@ -158,6 +130,12 @@ int dev_upload(pnmol_b200_handle* h, const T** out, const T* host, size_t count)
     CU(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
     *out = p;
     return 0;
+}
+
+int prop_smem_per_sm(int device) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+    return v;
 }
 
 int ensure_ready(pnmol_b200_handle* h) {
@@ -217,12 +195,11 @@ int launch_large(pnmol_b200_handle* h, Kernel kernel, Args& a, cudaStream_t st) 
 }
 
 int launch_run(pnmol_b200_handle* h, RunArgs& a, cudaStream_t st) {
-    if (h->warp) {
-        k_run_warp<<<h->grid, 32 * h->geo.nwarps, h->smem_warp, st>>>(h->P, a, h->geo);
-    } else if (h->large) {
+    if (h->large) {
         int rc = launch_large(h, k_run_large, a, st);
         if (rc) return rc;
     } else {
+        CU(cudaMemsetAsync(h->P.smslot, 0, sizeof(int) * h->num_sms, st));
         k_run<<<h->grid, kThreads, h->smem_bytes, st>>>(h->P, a);
     }
     ++g_launches;
@@ -282,6 +259,10 @@ int pnmol_b200_create(pnmol_b200_handle** out, int kind, int d, int num_derivati
     CU(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
+    {
+        int rc = dev_alloc(h, &P.smslot, (size_t)h->num_sms);
+        if (rc) { delete h; return rc; }
+    }
     *out = h;
     return 0;
 }
@@ -341,7 +322,16 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
         const int G = maxlen <= 4 * kRPL ? 4 : maxlen <= 8 * kRPL ? 8 : maxlen <= 16 * kRPL ? 16 : 32;
         P.vld = std::max(64, kRPL * G);  // rows of the panel buffers of the blocked QR (LP: 64, 128 or 256)
         P.ldm = P.m <= 96 ? (P.m | 1) : 0;  // odd leading dimension: conflict-free rows and columns
-        h->smem_bytes = smem_doubles(P.D, P.m, P.dd, P.vld, P.ldm) * sizeof(double);
+        // the sparse rows of H go to shared memory when two CTAs per SM still fit (else: global scratch, L2-resident)
+        P.whs = P.wh;
+        h->smem_bytes = smem_doubles(P.D, P.m, P.dd, P.vld, P.ldm, P.whs) * sizeof(double);
+        if (2 * (h->smem_bytes + 1024) > (size_t)prop_smem_per_sm(h->device) && P.m * P.wh > 256) {
+            const size_t without = smem_doubles(P.D, P.m, P.dd, P.vld, P.ldm, 0) * sizeof(double);
+            if (2 * (without + 1024) <= (size_t)prop_smem_per_sm(h->device) || h->smem_bytes > h->smem_optin) {
+                P.whs = 0;
+                h->smem_bytes = without;
+            }
+        }
         const char* force = std::getenv("PNMOL_B200_FORCE_LARGE");
         // auto: the single-CTA kernels need their shared memory to fit and are only fast while every panel's row list
         // fits the register-resident panels (<= 32 * kRPL rows); beyond that the whole grid works on one member
@@ -351,40 +341,6 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
         const std::string want_path = pathenv ? pathenv : "";
         if (want_path == "large") h->large = true;
         if (want_path == "cta" && h->smem_bytes <= h->smem_optin) h->large = false;
-        int maxpad = max_padded_len(P.D, P.D, P.D, te_p.data(), be_p.data());
-        maxpad = std::max(maxpad, max_padded_len(P.D, P.D, P.D, te_pd.data(), be_p.data()));
-        maxpad = std::max(maxpad, max_padded_len(P.D, P.latent ? 0 : P.m, P.m + P.D, te_u.data(), be_u.data()));
-        maxpad = std::max(maxpad, max_padded_len(P.D, P.d, P.d + P.D, nullptr, nullptr));
-        maxpad = std::max(maxpad, max_padded_len(P.D, P.m, P.m + P.D, nullptr, nullptr));
-        // opt-in (PNMOL_B200_PATH=warp): measured slower than the CTA-per-member kernels on B200 -- eight desynchronised
-        // instruction streams per SM thrash the 32 KB instruction cache (profiles/r01_notes.md)
-        if (!h->large && want_path == "warp" && maxpad <= 8 * kWT) {
-            WarpGeom& geo = h->geo;
-            geo.ldv = warp_ldv(maxpad);
-            geo.per_warp = warp_smem_doubles(P.D, P.m, P.dd, P.ldm, geo.ldv);
-            geo.nwarps = std::min(8, (int)(h->smem_optin / sizeof(double)) / geo.per_warp);
-            if (const char* e = std::getenv("PNMOL_B200_WARPS")) geo.nwarps = std::max(1, std::min(geo.nwarps, std::atoi(e)));  // tuning
-            if (geo.nwarps >= 4 || want_path == "warp") h->warp = geo.nwarps >= 1;
-        }
-        if (want_path == "warp" && !h->warp) return fail(-1, "PNMOL_B200_PATH=warp: problem does not fit the warp-per-member kernels");
-        if (h->warp) {
-            const WarpGeom& geo = h->geo;
-            h->smem_warp = (size_t)geo.per_warp * geo.nwarps * sizeof(double);
-            CU(cudaFuncSetAttribute(k_run_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_warp));
-            CU(cudaFuncSetAttribute(k_init_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_warp));
-            h->grid = std::min((P.batch + geo.nwarps - 1) / geo.nwarps, h->num_sms);
-            if (const char* e = std::getenv("PNMOL_B200_GRID")) h->grid = std::max(1, std::min(h->grid, std::atoi(e)));
-            const size_t slots = (size_t)h->grid * geo.nwarps;
-            const size_t wsz = (size_t)P.ld * (P.m + P.D);
-            if ((rc = dev_alloc(h, &P.W, wsz * slots))) return rc;
-            if ((rc = dev_alloc(h, &P.Hcol, slots * P.m * P.wh))) return rc;
-            if ((rc = dev_alloc(h, &P.Hval, slots * P.m * P.wh))) return rc;
-            if ((rc = dev_alloc(h, &P.F, slots * P.m * P.d))) return rc;
-            if ((rc = dev_alloc(h, &P.S, slots * P.m * P.m))) return rc;
-            CU(cudaMemset(P.W, 0, wsz * slots * sizeof(double)));
-            h->have_op = true;
-            return 0;
-        }
         if (h->large) {
             // one member at a time on the whole grid: one workspace, vectors in global scratch
             LargeQR& q = h->q;
@@ -525,12 +481,11 @@ int pnmol_b200_initialize(pnmol_b200_handle* h, const double* y0, double t0, dou
     a.y0 = y0; a.t0 = t0; a.prior_scale0 = diffuse_prior_scale;
     a.nugget = h->P.latent ? 1e-6 : 1e-10;  // latent.py:71,98 / white.py:33,51
     a.mean_out = mean_out; a.chol_out = chol_out; a.status = status;
-    if (h->warp) {
-        k_init_warp<<<h->grid, 32 * h->geo.nwarps, h->smem_warp, (cudaStream_t)stream>>>(h->P, a, h->geo);
-    } else if (h->large) {
+    if (h->large) {
         int rc2 = launch_large(h, k_init_large, a, (cudaStream_t)stream);
         if (rc2) return rc2;
     } else {
+        CU(cudaMemsetAsync(h->P.smslot, 0, sizeof(int) * h->num_sms, (cudaStream_t)stream));
         k_init<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
     }
     ++g_launches;
@@ -605,7 +560,7 @@ int pnmol_b200_run_adaptive(pnmol_b200_handle* h, double t0, double tmax, const 
     int rc = ensure_ready(h);
     if (rc) return rc;
     if (h->P.latent) return fail(-1, "adaptive steps need an error estimate: white-noise solvers only (src/pnmol/latent.py:217-223)");
-    if (h->large || h->warp) return fail(-4, "the on-device adaptive loop is served by the CTA-per-member kernels only");
+    if (h->large) return fail(-4, "the on-device adaptive loop is served by the CTA-per-member kernels only");
     if (!dt0 || !mean || !chol || !mean_tmp || !chol_tmp || !t_out || !dt_out || !diff_sum || !diff_last || !num_steps ||
         !num_attempts || !status)
         return fail(-1, "null argument");
@@ -623,6 +578,7 @@ int pnmol_b200_run_adaptive(pnmol_b200_handle* h, double t0, double tmax, const 
     a.err = h->hs_err; a.ref = h->hs_ref; a.t_out = t_out; a.dt_out = dt_out; a.diff_sum = diff_sum; a.diff_last = diff_last;
     a.nsteps = num_steps; a.nattempts = num_attempts; a.status = status; a.max_attempts = max_attempts; a.flags = flags;
     CU(cudaFuncSetAttribute(k_run_adaptive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    CU(cudaMemsetAsync(h->P.smslot, 0, sizeof(int) * h->num_sms, (cudaStream_t)stream));
     k_run_adaptive<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
     ++g_launches;
     CU(cudaGetLastError());
@@ -659,7 +615,7 @@ int pnmol_b200_profile(pnmol_b200_handle* h, int enable, uint64_t* cycles_out) {
 int pnmol_b200_path(pnmol_b200_handle* h) {
     if (!h) return fail(-1, "null handle");
     if (!h->have_op) return fail(-1, "pnmol_b200_set_operator has not been called");
-    return h->warp ? 2 : (h->large ? 1 : 0);
+    return h->large ? 1 : 0;
 }
 
 int pnmol_b200_rescale(pnmol_b200_handle* h, double* chol, const double* diff_sum, int nsteps, double* diff_cal_out,

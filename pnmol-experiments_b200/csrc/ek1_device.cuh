@@ -49,6 +49,7 @@ struct Problem {
     int latent, semilinear, reaction;
     int d, n, nb, ncomp, npts, dd, D, m;
     int wl, wb, wh, ld, batch, nparams, vld, ldm;  // ldm > 0: an m x ldm shared-memory scratch exists (small m)
+    int whs;                                       // = wh when the rows of H live in shared memory, else 0
     const int32_t* Lcol; const double* Lval; const double* Ediag;
     const int32_t* Bcol; const double* Bval; const double* Rsq;
     const double* A1d; const double* LQ1d; const double* Lk; const double* Kg;
@@ -57,6 +58,7 @@ struct Problem {
     const int32_t* te_pd;                                                                    // dense input factor
     double* W; int32_t* Hcol; double* Hval; double* F; double* S;
     unsigned long long* prof;  // optional clock64 phase accumulators (diagnostics)
+    int* smslot;               // [number of SMs] zeroed before every launch: CTAs count themselves per SM
 };
 
 // Phase timer: thread 0 of every CTA adds the cycles since the previous mark to prof[idx].
@@ -86,14 +88,18 @@ struct FastQR {       // shared-memory buffers of the blocked QR (qr_fast.cuh), 
     unsigned Gs;       // 16 x 17 Gram matrix V^T V (upper triangle)
     unsigned scratch;  // 4 x 192 per-warp Gram partials
     unsigned tau;      // 2 x 16
-    unsigned t4;       // 4 x 4 T factor of the current sub-panel
+    unsigned t4;       // 4 x (4 x 4): T factors of the sub-panels of the current panel
     int LP;            // rows of a buffer: 64, 128 or 256, >= every panel row list
+    int slot;          // which co-resident CTA of its SM this is (0, 1, ...): decides the factor warp's scheduler
 };
 
 struct Smem {
     double *vbuf, *mp, *z, *y, *xw, *xat, *red, *pv, *pinv, *Vs, *xraw, *sc, *msq, *Vr, *Ts, *Gs;
     FastQR fq;
     double *fqbase, *fqend;
+    int32_t *te_p, *be_p, *te_pd, *te_u, *be_u;  // shared-memory copies of the QR envelopes (Problem::te_p ...)
+    double* Hval; int32_t *Hcol, *Hpt;           // sparse rows of H (m x wh; Hpt = mesh point of an entry) when they fit in
+                                                 // shared memory, else nullptr
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -131,15 +137,17 @@ struct WarpTeam {
 };
 
 __host__ __device__ __forceinline__ size_t fastqr_doubles(int LP) {
-    return 2 * (size_t)16 * LP + 2 * (size_t)16 * 18 + 16 * 17 + 4 * 192 + 2 * 16 + 16;
+    return 2 * (size_t)16 * LP + 2 * (size_t)16 * 18 + 16 * 17 + 4 * 192 + 2 * 16 + 64;
 }
 
 // vld = rows of a panel buffer (LP of the blocked QR: 64, 128 or 256)
-__host__ __device__ __forceinline__ size_t smem_doubles(int D, int m, int dd, int vld, int ldm) {
-    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 80 + fastqr_doubles(vld) + (size_t)m * ldm + 8;
+// wh: ELL width of the sparse rows of H (> 0: they live in shared memory; 0: in the global scratch Problem::Hcol/Hval)
+__host__ __device__ __forceinline__ size_t smem_doubles(int D, int m, int dd, int vld, int ldm, int wh) {
+    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 80 + 1 + fastqr_doubles(vld) + (size_t)m * ldm + 8 +
+           (3 * (size_t)D + 2 * ((size_t)m + D) + 2) / 2 + 2 * (size_t)m * wh;
 }
 
-__device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vld, int ldm) {
+__device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vld, int ldm, int wh = 0) {
     Smem s;
     double* const base0 = base;
     s.vbuf = base;              base += 2 * D + 4;
@@ -154,6 +162,8 @@ __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vl
     s.sc = base;                base += 80;
     s.xraw = nullptr; s.Vs = nullptr; s.Vr = nullptr; s.Ts = nullptr; s.Gs = nullptr;
     s.fq.LP = vld;
+    s.fq.slot = 0;
+    if ((base - base0) & 1) ++base;  // 16-byte alignment of the panel buffers (128-bit operand loads)
     s.fqbase = base;            // (zeroed at kernel start: reflector buffers start finite)
     s.fq.buf[0] = (unsigned)(base - base0); base += (size_t)16 * vld;
     s.fq.buf[1] = (unsigned)(base - base0); base += (size_t)16 * vld;
@@ -162,10 +172,39 @@ __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vl
     s.fq.Gs = (unsigned)(base - base0);     base += 16 * 17;
     s.fq.scratch = (unsigned)(base - base0); base += 4 * 192;
     s.fq.tau = (unsigned)(base - base0);    base += 2 * 16;
-    s.fq.t4 = (unsigned)(base - base0);     base += 16;
+    s.fq.t4 = (unsigned)(base - base0);     base += 64;
     s.fqend = base;
     s.msq = ldm > 0 ? base : nullptr;
+    base += (size_t)m * ldm + 8;
+    int32_t* ib = reinterpret_cast<int32_t*>(base);
+    s.te_p = ib;  ib += D;
+    s.be_p = ib;  ib += D;
+    s.te_pd = ib; ib += D;
+    s.te_u = ib;  ib += m + D;
+    s.be_u = ib;  ib += m + D;
+    ib += (3 * D + 2 * (m + D)) & 1;
+    s.Hval = wh > 0 ? reinterpret_cast<double*>(ib) : nullptr;
+    s.Hcol = wh > 0 ? reinterpret_cast<int32_t*>(s.Hval + (size_t)m * wh) : nullptr;
+    s.Hpt = wh > 0 ? s.Hcol + (size_t)m * wh : nullptr;
     return s;
+}
+
+// Which co-resident CTA of this SM am I?  (Order of arrival on the SM; block-uniform, contains a block barrier.)
+__device__ __forceinline__ int sm_slot(const Problem& P) {
+    __shared__ int slot_s;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        slot_s = P.smslot ? atomicAdd(&P.smslot[smid], 1) : 0;
+    }
+    __syncthreads();
+    return slot_s;
+}
+
+// Copy the envelope arrays of the problem into shared memory (once per kernel; followed by a block barrier at the caller).
+__device__ __forceinline__ void load_envelopes(const Problem& P, const Smem& sm) {
+    for (int i = threadIdx.x; i < P.D; i += kThreads) { sm.te_p[i] = P.te_p[i]; sm.be_p[i] = P.be_p[i]; sm.te_pd[i] = P.te_pd[i]; }
+    for (int i = threadIdx.x; i < P.m + P.D; i += kThreads) { sm.te_u[i] = P.te_u[i]; sm.be_u[i] = P.be_u[i]; }
 }
 
 // ---------------------------------------------------------------- Householder QR
@@ -384,24 +423,47 @@ __device__ void build_predict(const Problem& P, int b, const Smem& sm, const dou
     const int lane = T::tid() & 31;
     const int n = P.n, D = P.D, nd = P.n * P.d;
     const double ps = P.priorscale ? P.priorscale[b] : 1.0;
-    for (int i = w0; i < D; i += nw) {
-        double* col = Wp + (size_t)i * P.ld;
-        const int blk = i / n, ii = i - blk * n;
-        double coef[kMaxN];
-        for (int s = 0; s < n; ++s) coef[s] = P.A1d[ii * n + s];
-        const int tend = te[i];
-        for (int k = lane; k <= tend; k += 32) {
-            double acc = 0.0;
-            for (int s = 0; s < n; ++s) acc = fma(coef[s], sm.pinv[s] * PNMOL_STATE_LOAD(Cl + (size_t)(blk * n + s) * D + k), acc);
-            col[k] = acc;
+    // One n x n block of columns per warp and round: the n columns i = blk n + ii are combinations of the SAME n rows
+    // blk n + s of the input factor (A = I (x) A_1d), so those rows are read once; two lane-chunks per round keep
+    // 2 n independent (streaming, HBM) loads in flight.
+    const int nblk = D / n;
+    for (int blk = w0; blk < nblk; blk += nw) {
+        const int i0 = blk * n;
+        const int tend = te[i0];  // (the columns of a block share their top envelope)
+        const double* src = Cl + (size_t)i0 * D;
+        double* col0 = Wp + (size_t)i0 * P.ld;
+        for (int k0 = 0; k0 <= tend; k0 += 64) {
+            double v[2][kMaxN];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int k = k0 + 32 * u + lane;
+#pragma unroll
+                for (int s = 0; s < kMaxN; ++s) v[u][s] = (s < n && k <= tend) ? sm.pinv[s] * PNMOL_STATE_LOAD(src + (size_t)s * D + k) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int k = k0 + 32 * u + lane;
+                if (k <= tend) {
+                    for (int ii = 0; ii < n; ++ii) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int s = 0; s < kMaxN; ++s)
+                            if (s < n) acc = fma(P.A1d[ii * n + s], v[u][s], acc);
+                        col0[(size_t)ii * P.ld + k] = acc;
+                    }
+                }
+            }
         }
-        // Ql^T column i = row i of Ql, entries 0..i  (lanes over the n x n blocks: no integer divisions per entry)
-        if (i < nd) {
+        // Ql^T columns i0 .. i0 + n - 1 = rows of Ql, entries 0 .. i  (lanes over the n x n blocks)
+        if (i0 < nd) {
             for (int kb = lane; kb <= blk; kb += 32) {
                 const double lk = ps * P.Lk[(size_t)blk * P.d + kb];
-                for (int kk = 0; kk < n; ++kk) {
-                    const int k = kb * n + kk;
-                    if (k <= i) col[D + k] = lk * P.LQ1d[ii * n + kk];
+                for (int ii = 0; ii < n; ++ii) {
+                    double* col = col0 + (size_t)ii * P.ld + D;
+                    for (int kk = 0; kk < n; ++kk) {
+                        const int k = kb * n + kk;
+                        if (k <= i0 + ii) col[k] = lk * P.LQ1d[ii * n + kk];
+                    }
                 }
             }
         } else {
@@ -409,9 +471,12 @@ __device__ void build_predict(const Problem& P, int b, const Smem& sm, const dou
             const double ds = P.diffscale ? P.diffscale[(size_t)b * P.ncomp + comp] : 1.0;
             const double eb = ds * P.Ediag[blk - P.d];
             for (int kb = lane; kb <= blk; kb += 32) {
-                for (int kk = 0; kk < n; ++kk) {
-                    const int k = kb * n + kk;
-                    if (k <= i) col[D + k] = kb == blk ? eb * P.LQ1d[ii * n + kk] : 0.0;
+                for (int ii = 0; ii < n; ++ii) {
+                    double* col = col0 + (size_t)ii * P.ld + D;
+                    for (int kk = 0; kk < n; ++kk) {
+                        const int k = kb * n + kk;
+                        if (k <= i0 + ii) col[k] = kb == blk ? eb * P.LQ1d[ii * n + kk] : 0.0;
+                    }
                 }
             }
         }
@@ -537,33 +602,48 @@ __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, dou
     double* S = sm.msq;
     const int na_ode = P.wl + (P.semilinear ? P.ncomp : 0);  // order-0 entries come first in a row of H
     const int ntri = m * (m + 1) / 2;
+    // mesh-point index c / n of every order-0 entry, once (the entry loops below are then division-free); -1 = padding
+    int32_t* pt = sm.Hpt;
+    const bool havept = pt != nullptr;
+    if (havept) {
+        for (int e = tid; e < m * P.wh; e += T::size) {
+            const int c = Hcol[e];
+            pt[e] = c >= 0 ? c / n : -1;
+        }
+        T::sync();
+    }
     for (int idx = tid; idx < ntri; idx += T::size) {
         int r = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
         while (r * (r + 1) / 2 > idx) --r;
         while ((r + 1) * (r + 2) / 2 <= idx) ++r;
         const int rp = idx - r * (r + 1) / 2;  // rp <= r
-        const int32_t* hr = Hcol + (size_t)r * P.wh;
-        const int32_t* hp = Hcol + (size_t)rp * P.wh;
+        const int32_t* hr = (havept ? pt : Hcol) + r * P.wh;
+        const int32_t* hp = (havept ? pt : Hcol) + rp * P.wh;
         const double* vr = Hval + (size_t)r * P.wh;
         const double* vp = Hval + (size_t)rp * P.wh;
         const int nar = r < d ? na_ode : P.wb, nap = rp < d ? na_ode : P.wb;
         double acc = 0.0, cross = 0.0;
         for (int u = 0; u < nar; ++u) {
-            const int cu = hr[u];
+            int cu = hr[u];
             if (cu < 0) continue;
-            const double* krow = P.Kg + (size_t)(cu / n) * d;
+            if (!havept) cu /= n;
+            const double* krow = P.Kg + (size_t)cu * d;
             double inner = 0.0;
             for (int w = 0; w < nap; ++w) {
-                const int cw = hp[w];
-                if (cw >= 0) inner = fma(vp[w], krow[cw / n], inner);
+                int cw = hp[w];
+                if (cw < 0) continue;
+                if (!havept) cw /= n;
+                inner = fma(vp[w], krow[cw], inner);
             }
             acc = fma(vr[u], inner, acc);
             if (rp < d) cross = fma(vr[u], krow[rp], cross);
         }
         if (r < d) {
             for (int w = 0; w < nap; ++w) {
-                const int cw = hp[w];
-                if (cw >= 0) cross = fma(vp[w], P.Kg[(size_t)(cw / n) * d + r], cross);
+                int cw = hp[w];
+                if (cw < 0) continue;
+                if (!havept) cw /= n;
+                cross = fma(vp[w], P.Kg[(size_t)cw * d + r], cross);
             }
         }
         double val = q00 * acc + q01 * p1s * cross;
@@ -689,13 +769,26 @@ __device__ void update_build_left(const Problem& P, int b, int mcur, int nrows, 
         double* col = Wl + (size_t)r * ld;
         int tend = te ? te[r] : D - 1;
         if (tend > D - 1) tend = D - 1;
-        for (int i = lane; i <= tend; i += 32) {
-            double acc = 0.0;
+        const int32_t* hc = Hcol + (size_t)r * P.wh;
+        const double* hv = Hval + (size_t)r * P.wh;
+        for (int i0 = 0; i0 <= tend; i0 += 128) {  // four lane-chunks per round: 4 wh independent loads in flight
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
             for (int w = 0; w < P.wh; ++w) {
-                const int c = Hcol[(size_t)r * P.wh + w];
-                if (c >= i) acc = fma(Hval[(size_t)r * P.wh + w], Wr[(size_t)c * ld + i], acc);  // R[i][c], zero for i > c
+                const int c = hc[w];
+                if (c < 0) continue;
+                const double hvw = hv[w];
+                const double* rc = Wr + (size_t)c * ld;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + 32 * u + lane;
+                    if (i <= c && i <= tend) acc[u] = fma(hvw, rc[i], acc[u]);  // R[i][c], zero for i > c
+                }
             }
-            col[i] = acc;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + 32 * u + lane;
+                if (i <= tend) col[i] = acc[u];
+            }
         }
         int bend = be ? be[r] : nrows - 1;
         if (bend > nrows - 1) bend = nrows - 1;
@@ -784,13 +877,21 @@ __device__ double update_solve(const Problem& P, const Smem& sm, int mcur, const
         for (int r = tid; r < mcur; r += T::size) part = fma(sm.xw[r], sm.xw[r], part);
         diff = T::sum(part, sm.red) / mcur;
     }
-    // m_new = mp - R2^T y   (white.py:123, sqrt.py:72)
-    for (int k = warp; k < D; k += T::nwarps) {
-        const double* col = Wr + (size_t)k * ld;
-        double acc = 0.0;
-        for (int i = lane; i < mcur; i += 32) acc = fma(col[i], sm.y[i], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) sm.mp[k] -= acc;
+    // m_new = mp - R2^T y   (white.py:123, sqrt.py:72); four columns per warp and round (independent loads)
+    for (int k0 = 4 * warp; k0 < D; k0 += 4 * T::nwarps) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = lane; i < mcur; i += 32) {
+            const double yi = sm.y[i];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k0 + u < D) acc[u] = fma(Wr[(size_t)(k0 + u) * ld + i], yi, acc[u]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+        }
+        if (lane < 4 && k0 + lane < D) sm.mp[k0 + lane] -= lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
     }
     T::sync();
     return diff;
@@ -823,11 +924,21 @@ __device__ int update_output_factor(const Problem& P, const Smem& sm, const Upda
         const double* col = Wr + (size_t)r * ld + mcur;
         const double pr = out.scale_by_p ? sm.pv[r % n] : 1.0;
         double* orow = out.chol_out + (size_t)r * D;
-        for (int c = lane; c < D; c += 32) {
-            double v = 0.0;
-            if (c <= r && mcur + c < nrows) v = pr * col[c];
-            PNMOL_STATE_STORE(orow + c, v);  // streaming by default: keep the workspaces, not the state, resident in L2
-            if (!isfinite(v)) bad = 1;
+        for (int c0 = 0; c0 < D; c0 += 128) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + 32 * u + lane;
+                v[u] = (c <= r && mcur + c < nrows) ? pr * col[c] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + 32 * u + lane;
+                if (c < D) {
+                    PNMOL_STATE_STORE(orow + c, v[u]);  // streaming by default: keep the workspaces, not the state, resident in L2
+                    if (!isfinite(v[u])) bad = 1;
+                }
+            }
         }
     }
     return bad;

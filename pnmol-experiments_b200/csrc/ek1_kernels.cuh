@@ -46,8 +46,8 @@ __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, doub
     pc.start(P.prof);
     const int n = P.n, D = P.D;
     double* W = P.W + (size_t)slot * P.ld * (P.m + P.D);
-    int32_t* Hcol = P.Hcol + (size_t)slot * P.m * P.wh;
-    double* Hval = P.Hval + (size_t)slot * P.m * P.wh;
+    int32_t* Hcol = sm.Hcol ? sm.Hcol : P.Hcol + (size_t)slot * P.m * P.wh;
+    double* Hval = sm.Hval ? sm.Hval : P.Hval + (size_t)slot * P.m * P.wh;
     // [setup + predict]  m = P^-1 mean (flattened column-major, index j n + i), mp = A m   white.py:104-107
     for (int k = tid; k < D; k += kThreads) {
         const int j = k / n, i = k - j * n;
@@ -59,10 +59,10 @@ __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, doub
     evaluate_ode(P, b, sm, sm.pv[0], sm.pv[1], Hcol, Hval);
     pc.mark(0);
     const bool dense = flags & 1;
-    build_predict(P, b, sm, chol_in, dense ? P.te_pd : P.te_p, W + (size_t)P.m * P.ld);
+    build_predict(P, b, sm, chol_in, dense ? sm.te_pd : sm.te_p, W + (size_t)P.m * P.ld);
     pc.mark(1);
     Shape sp;
-    sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p; sp.ldr = P.ld;
+    sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? sm.te_pd : sm.te_p; sp.be = sm.be_p; sp.ldr = P.ld;
     householder_qr_fast(W + (size_t)P.m * P.ld, P.ld, sp, sm.fq, pc);
     pc.mark(2);
     if (!P.latent && !(flags & 2)) {
@@ -73,16 +73,18 @@ __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, doub
     UpdateOut out;
     out.mean_out = mean_out; out.chol_out = chol_out; out.diff_out = diff_out;
     out.ref_out = P.latent ? nullptr : ref_out; out.scale_by_p = true;
-    update_stage(P, b, sm, P.m, P.latent ? E_NONE : E_STEP_WHITE, 0.0, nullptr, P.te_u, P.be_u, Hcol, Hval, W, out,
+    update_stage(P, b, sm, P.m, P.latent ? E_NONE : E_STEP_WHITE, 0.0, nullptr, sm.te_u, sm.be_u, Hcol, Hval, W, out,
                  nonfinite, pc);
 }
 
 __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem P, const RunArgs a) {
-    extern __shared__ double smem_raw[];
-    const Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm);
+    extern __shared__ __align__(16) double smem_raw[];
+    Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm, P.whs);
+    sm.fq.slot = sm_slot(P);
     __shared__ int nonfinite;
     __shared__ double diff_s;
     for (double* q = sm.fqbase + threadIdx.x; q < sm.fqend; q += kThreads) *q = 0.0;  // reflector buffers start finite
+    load_envelopes(P, sm);
     const int tid = threadIdx.x;
     const size_t msz = (size_t)P.D, csz = (size_t)P.D * P.D;
     for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
@@ -155,11 +157,13 @@ struct AdaptiveArgs {
 };
 
 __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run_adaptive(const Problem P, const AdaptiveArgs a) {
-    extern __shared__ double smem_raw[];
-    const Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm);
+    extern __shared__ __align__(16) double smem_raw[];
+    Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm, P.whs);
+    sm.fq.slot = sm_slot(P);
     __shared__ int nonfinite;
     __shared__ double diff_s;
     for (double* q = sm.fqbase + threadIdx.x; q < sm.fqend; q += kThreads) *q = 0.0;  // reflector buffers start finite
+    load_envelopes(P, sm);
     const int tid = threadIdx.x;
     const int nu = P.n - 1;
     const size_t msz = (size_t)P.D, csz = (size_t)P.D * P.D;
@@ -238,16 +242,18 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run_adaptive(const
 
 // initialize(): two square-root updates on a Kronecker-structured prior factor.
 __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_init(const Problem P, const InitArgs a) {
-    extern __shared__ double smem_raw[];
-    const Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm);
+    extern __shared__ __align__(16) double smem_raw[];
+    Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm, P.whs);
+    sm.fq.slot = sm_slot(P);
     __shared__ int nonfinite;
     for (double* q = sm.fqbase + threadIdx.x; q < sm.fqend; q += kThreads) *q = 0.0;  // reflector buffers start finite
+    load_envelopes(P, sm);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = P.n, d = P.d, D = P.D, nd = P.n * P.d;
     const int slot = blockIdx.x;
     double* W = P.W + (size_t)slot * P.ld * (P.m + P.D);
-    int32_t* Hcol = P.Hcol + (size_t)slot * P.m * P.wh;
-    double* Hval = P.Hval + (size_t)slot * P.m * P.wh;
+    int32_t* Hcol = sm.Hcol ? sm.Hcol : P.Hcol + (size_t)slot * P.m * P.wh;
+    double* Hval = sm.Hval ? sm.Hval : P.Hval + (size_t)slot * P.m * P.wh;
     for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
         if (tid == 0) nonfinite = 0;
         double* chol = a.chol_out + (size_t)b * D * D;
@@ -326,7 +332,7 @@ __global__ void k_gram(const double* Lk, double* Kg, int d) {
 // propagate_cholesky_factor for dense S1 (r x c1), S2 (r x c2): QR of the (c1+c2) x r stack.
 __global__ void __launch_bounds__(kThreads) k_sqrt_propagate(const double* S1, const double* S2, double* out, int r,
                                                             int c1, int c2, int batch, double* Wall) {
-    extern __shared__ double smem_raw[];
+    extern __shared__ __align__(16) double smem_raw[];
     double* vbuf = smem_raw;
     double* red = smem_raw + (c1 + c2) + 4;  // 16 doubles
     const int tid = threadIdx.x;
@@ -352,7 +358,7 @@ __global__ void __launch_bounds__(kThreads) k_sqrt_propagate(const double* S1, c
 __global__ void __launch_bounds__(kThreads) k_sqrt_update(const double* H, const double* C, const double* E, double* C_out,
                                                          double* K_out, double* S_out, int m, int D, int batch,
                                                          double* Wall) {
-    extern __shared__ double smem_raw[];
+    extern __shared__ __align__(16) double smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nbot = E ? m : 0;
     const int rows = D + nbot, ld = D + m, ncols = m + D;
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(kThreads) k_smoother_step(const double* m, con
                                                            const double* sc_fut, const double* sgain, const double* sq,
                                                            const double* mp, const double* x, double* mean_out,
                                                            double* chol_out, int d, int batch, double* Wall) {
-    extern __shared__ double smem_raw[];
+    extern __shared__ __align__(16) double smem_raw[];
     double* vbuf = smem_raw;
     double* red = smem_raw + 3 * d + 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -192,7 +192,7 @@ __device__ void update_stage_large(cg::grid_group& grid, const Problem& P, int b
 }
 
 __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const Problem P, const RunArgs a, const LargeQR q) {
-    extern __shared__ double smem_raw[];
+    extern __shared__ __align__(16) double smem_raw[];
     cg::grid_group grid = cg::this_grid();
     const LargeSmem ls = carve_large(smem_raw);
     const Smem sm = large_vectors(P, q, ls);
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const 
 
 // initialize() (white.py:12-80, latent.py:20-134) on the grid.
 __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_init_large(const Problem P, const InitArgs a, const LargeQR q) {
-    extern __shared__ double smem_raw[];
+    extern __shared__ __align__(16) double smem_raw[];
     cg::grid_group grid = cg::this_grid();
     const LargeSmem ls = carve_large(smem_raw);
     const Smem sm = large_vectors(P, q, ls);

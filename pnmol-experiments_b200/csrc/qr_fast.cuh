@@ -23,8 +23,11 @@
 
 namespace pnmol {
 
-// XOR swizzle of the row index inside reflector r (bits 0..2 of r -> bits 0, 3, 2 of the row index)
-__device__ __forceinline__ int vsw(int r) { return (r & 1) | ((r & 2) << 2) | (r & 4); }
+// XOR swizzle of the row index inside reflector r: bit 1 of r -> bit 2, (bit 0 ^ bit 2) of r -> bit 3 of the row index.
+// Row pairs (2 t, 2 t + 1) stay adjacent, so the pass-1 operands of a lane are one 16-byte load; both operand patterns
+// of the trailing update are bank-conflict free (128-bit loads of reflectors g, g + 8 by quarter-warps; 64-bit loads of
+// reflectors 2 t + sx by half-warps).
+__device__ __forceinline__ int vsw(int r) { return ((r & 2) << 1) | (((r ^ (r >> 2)) & 1) << 3); }
 
 // A team: warps [first, first + nw) of the CTA; named barrier `bar` (0 = the whole CTA).
 struct QTeam {
@@ -54,7 +57,7 @@ __device__ __forceinline__ void warp_sum_n(double (&v)[NV]) {
 template <int R>
 __device__ __noinline__ void subpanel_factor(unsigned buf_off, int LP, int c0, int nc, unsigned tau_off, unsigned t4_off,
                                              double* __restrict__ Wp, int ld, const RowMap rm) {
-    extern __shared__ double smem_raw[];
+    extern __shared__ __align__(16) double smem_raw[];
     double* buf = smem_raw + buf_off;
     double* tau_s = smem_raw + tau_off;
     double* t4 = smem_raw + t4_off;
@@ -179,7 +182,7 @@ __device__ __noinline__ void subpanel_factor(unsigned buf_off, int LP, int c0, i
 // column per warp at a time:  x <- x - V T^T (V^T x).
 template <int R>
 __device__ __noinline__ void subpanel_apply(unsigned buf_off, int LP, int c0, int cbeg, int cend, unsigned t4_off, const QTeam tm) {
-    extern __shared__ double smem_raw[];
+    extern __shared__ __align__(16) double smem_raw[];
     double* buf = smem_raw + buf_off;
     const double* t4 = smem_raw + t4_off;
     const int lane = threadIdx.x & 31;
@@ -229,73 +232,72 @@ __device__ __noinline__ void subpanel_apply(unsigned buf_off, int LP, int c0, in
 __device__ __forceinline__ int swz_even(int x, int sw) { return (x ^ (sw & 7)) + (sw & 8); }
 __device__ __forceinline__ int swz_odd(int x, int sw) { return (x ^ (sw & 7)) - (sw & 8); }
 
-// Gram matrix V^T V (upper triangle) on the tensor pipe, at most 4 warps of the team; fixed summation order.
-__device__ __noinline__ void gram16(unsigned buf_off, int LP, int ntile, unsigned gs_off, unsigned scratch_off, const QTeam tm) {
-    extern __shared__ double smem_raw[];
+// T factor of the panel (dlarft), built sub-panel by sub-panel while the factor warp is busy with the next one:
+//   T[4s:4s+4, 4s:4s+4] = T4_s (from the factor warp),   T[0:4s, 4s:4s+4] = -T[0:4s, 0:4s] (V_<s^T V_s) T4_s.
+// Three helper warps (h = 0, 1, 2; named barrier 4) share the Gram block V_<s^T V_s on the tensor pipe -- every warp a
+// third of the 8-row tiles, partial blocks summed in a fixed order -- and helper 0 does the two small products.
+__device__ __noinline__ void t_extend(unsigned buf_off, int LP, int ntile, int sidx, unsigned ts_off, unsigned t4_off,
+                                      unsigned scratch_off, int h) {
+    extern __shared__ __align__(16) double smem_raw[];
     const double* buf = smem_raw + buf_off;
-    double* Gs = smem_raw + gs_off;
-    double* scratch = smem_raw + scratch_off;
+    double* Ts = smem_raw + ts_off;
+    const double* t4 = smem_raw + t4_off;
+    double* scratch = smem_raw + scratch_off;  // 3 x 64 partial Gram blocks, then 64 + 64 for the products
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int nwg = tm.nw < 4 ? tm.nw : 4;
-    if (tm.w < nwg) {
-        double c00[2] = {0.0, 0.0}, c01[2] = {0.0, 0.0}, c11[2] = {0.0, 0.0};
-        double d00[2] = {0.0, 0.0}, d01[2] = {0.0, 0.0}, d11[2] = {0.0, 0.0};
-        const int sw = vsw(g);
+    const int c0 = 4 * sidx;
+    if (h == 0 && lane < 16) Ts[(c0 + (lane >> 2)) * kLdr + c0 + (lane & 3)] = t4[lane];
+    if (sidx == 0) return;
+    {
+        double c_lo[2] = {0.0, 0.0}, d_lo[2] = {0.0, 0.0}, c_hi[2] = {0.0, 0.0}, d_hi[2] = {0.0, 0.0};
+        const int swa = vsw(g), swb = vsw(c0 + (g & 3));
         const double* lo = buf + (size_t)g * LP;
         const double* hi = lo + (size_t)8 * LP;
-        for (int i = tm.w; i < ntile; i += nwg) {
-            const int r0 = (8 * i + 2 * t) ^ sw, r1 = (8 * i + 2 * t + 1) ^ sw;
-            const double a0 = lo[r0], a1 = hi[r0], b0 = lo[r1], b1 = hi[r1];
-            dmma884(c00[0], c00[1], a0, a0);
-            dmma884(c01[0], c01[1], a0, a1);
-            dmma884(c11[0], c11[1], a1, a1);
-            dmma884(d00[0], d00[1], b0, b0);
-            dmma884(d01[0], d01[1], b0, b1);
-            dmma884(d11[0], d11[1], b1, b1);
+        const double* pb = buf + (size_t)(c0 + (g & 3)) * LP;
+        const bool hi_needed = c0 > 8;
+        for (int i = h; i < ntile; i += 3) {
+            const int r0 = 8 * i + 2 * t;
+            const double2 a = *reinterpret_cast<const double2*>(lo + (r0 ^ swa));
+            double2 bv = *reinterpret_cast<const double2*>(pb + (r0 ^ swb));
+            if (g >= 4) { bv.x = 0.0; bv.y = 0.0; }
+            dmma884(c_lo[0], c_lo[1], a.x, bv.x);
+            dmma884(d_lo[0], d_lo[1], a.y, bv.y);
+            if (hi_needed) {
+                const double2 a2 = *reinterpret_cast<const double2*>(hi + (r0 ^ swa));
+                dmma884(c_hi[0], c_hi[1], a2.x, bv.x);
+                dmma884(d_hi[0], d_hi[1], a2.y, bv.y);
+            }
         }
-        double* mine = scratch + tm.w * 192;
+        if (t < 2) {  // D[g][2 t + q] = (v_g . v_{c0 + 2 t + q}) over this warp's tiles
+            double* mine = scratch + h * 64;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int e = g * 8 + 2 * t + q;
-            mine[e] = c00[q] + d00[q];
-            mine[64 + e] = c01[q] + d01[q];
-            mine[128 + e] = c11[q] + d11[q];
+            for (int q = 0; q < 2; ++q) {
+                mine[g * 4 + 2 * t + q] = c_lo[q] + d_lo[q];
+                mine[(g + 8) * 4 + 2 * t + q] = c_hi[q] + d_hi[q];
+            }
         }
     }
-    tm.sync();
-    for (int e = tm.w * 32 + lane; e < 192; e += tm.nw * 32) {
-        double sum = 0.0;
-        for (int w = 0; w < nwg; ++w) sum += scratch[w * 192 + e];
-        const int blk = e >> 6, r = (e & 63) >> 3, c = e & 7;
-        Gs[(r + (blk == 2 ? 8 : 0)) * 17 + c + (blk >= 1 ? 8 : 0)] = sum;
-    }
-}
-
-// dlarft on one warp (lane k owns row k of T); tau with unit stride.
-__device__ __noinline__ void t_factor16(unsigned gs_off, unsigned tau_off, unsigned ts_off) {
-    extern __shared__ double smem_raw[];
-    const double* Gs = smem_raw + gs_off;
-    const double* tau_s = smem_raw + tau_off;
-    double* Ts = smem_raw + ts_off;
-    const int k = threadIdx.x & 31;
-    double Trow[kNB];
-#pragma unroll
-    for (int j = 0; j < kNB; ++j) Trow[j] = 0.0;
-#pragma unroll
-    for (int i = 0; i < kNB; ++i) {
-        const double tau = tau_s[i];
+    asm volatile("bar.sync 4, 96;" ::: "memory");
+    if (h != 0) return;
+    double* gs = scratch + 192;
+    double* ms = scratch + 256;
+    for (int idx = lane; idx < c0 * 4; idx += 32) gs[idx] = (scratch[idx] + scratch[64 + idx]) + scratch[128 + idx];
+    __syncwarp();
+    for (int idx = lane; idx < c0 * 4; idx += 32) {  // M = T[0:c0, 0:c0] G
+        const int j = idx >> 2, c = idx & 3;
         double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < i; j += 2) {
-            a0 = fma(Trow[j], Gs[j * 17 + i], a0);
-            if (j + 1 < i) a1 = fma(Trow[j + 1], Gs[(j + 1) * 17 + i], a1);
+        for (int jp = j; jp < c0; jp += 2) {
+            a0 = fma(Ts[j * kLdr + jp], gs[jp * 4 + c], a0);
+            if (jp + 1 < c0) a1 = fma(Ts[j * kLdr + jp + 1], gs[(jp + 1) * 4 + c], a1);
         }
-        Trow[i] = k < i ? -tau * (a0 + a1) : (k == i ? tau : 0.0);
+        ms[idx] = a0 + a1;
     }
-    if (k < kNB) {
-#pragma unroll
-        for (int j = 0; j < kNB; ++j) Ts[k * kLdr + j] = Trow[j];
+    __syncwarp();
+    for (int idx = lane; idx < c0 * 4; idx += 32) {  // T[0:c0, c0:c0+4] = -M T4
+        const int j = idx >> 2, c = idx & 3;
+        double acc = 0.0;
+        for (int q = 0; q <= c; ++q) acc = fma(ms[j * 4 + q], t4[q * 4 + c], acc);
+        Ts[j * kLdr + c0 + c] = -acc;
     }
 }
 
@@ -304,25 +306,32 @@ __device__ __noinline__ void t_factor16(unsigned gs_off, unsigned tau_off, unsig
 // swizzled reflector-major buffer.  NT > 0: single pass with all (<= NT) tiles of a column in registers; NT = 0: two
 // passes in chunks of kCh tiles (row lists of more than 16 tiles).
 struct TrailOps {  // lane-dependent operand bases (even / odd tiles): index + 8 a
-    const double *p1e0, *p1o0, *p1e1, *p1o1;   // pass 1: reflector g (+ 8 LP: g + 8), in-tile rows 2 t, 2 t + 1
+    const double *p1e, *p1o;                   // pass 1: reflector g (+ 8 LP: g + 8), in-tile row pair (2 t, 2 t + 1)
     const double *p2ea, *p2oa, *p2eb, *p2ob;   // pass 2: reflectors 2 t (a) and 2 t + 1 (b) (+ 8 LP: + 8), in-tile row g
     int hi;                                    // 8 LP
 };
 
-template <bool ALIGNED>
+// Workspace tile of a lane: rows 8 a + 2 t, 8 a + 2 t + 1 of its column.  MODE 2: aligned row list and even offsets
+// (one 16-byte access), 1: aligned row list, 0: general row list (per-element map and guards).
+template <int MODE>
 __device__ __forceinline__ void trail_load(const double* __restrict__ cp, const RowMap& rm, int a, int t, int nt1, int off1,
                                            int off2, double& x0, double& x1) {
-    if (ALIGNED) {  // every tile lies in one segment of the row list: (segment base) + constant
+    if (MODE == 2) {
+        const double2 v = *reinterpret_cast<const double2*>(cp + (a < nt1 ? off1 : off2) + 8 * a);
+        x0 = v.x; x1 = v.y;
+    } else if (MODE == 1) {  // every tile lies in one segment of the row list: (segment base) + constant
         const double* q = cp + (a < nt1 ? off1 : off2) + 8 * a;
         x0 = q[0]; x1 = q[1];
     } else {
         tile_load<false>(cp, rm, 8 * a, t, x0, x1);
     }
 }
-template <bool ALIGNED>
+template <int MODE>
 __device__ __forceinline__ void trail_store(double* __restrict__ cp, const RowMap& rm, int a, int t, int nt1, int off1, int off2,
                                             double x0, double x1) {
-    if (ALIGNED) {
+    if (MODE == 2) {
+        *reinterpret_cast<double2*>(cp + (a < nt1 ? off1 : off2) + 8 * a) = make_double2(x0, x1);
+    } else if (MODE == 1) {
         double* q = cp + (a < nt1 ? off1 : off2) + 8 * a;
         q[0] = x0; q[1] = x1;
     } else {
@@ -330,21 +339,33 @@ __device__ __forceinline__ void trail_store(double* __restrict__ cp, const RowMa
     }
 }
 // tile index a = ab + ac with ab a multiple of 2 (runtime) and ac a compile-time constant: parity(a) = parity(ac)
-__device__ __forceinline__ void trail_pass1(const TrailOps& o, int ab, int ac, double x0, double x1, double (&y)[2][2][2]) {
-    const double* q0 = ((ac & 1) ? o.p1o0 : o.p1e0) + 8 * ab + 8 * ac;
-    const double* q1 = ((ac & 1) ? o.p1o1 : o.p1e1) + 8 * ab + 8 * ac;
-    dmma884(y[0][0][0], y[0][0][1], x0, q0[0]);
-    dmma884(y[0][1][0], y[0][1][1], x0, q0[o.hi]);
-    dmma884(y[1][0][0], y[1][0][1], x1, q1[0]);
-    dmma884(y[1][1][0], y[1][1][1], x1, q1[o.hi]);
+struct P1Ops { double2 lo, hi; };
+__device__ __forceinline__ P1Ops trail_p1_fetch(const TrailOps& o, int ab, int ac) {
+    const double* q = ((ac & 1) ? o.p1o : o.p1e) + 8 * ab + 8 * ac;
+    P1Ops r;
+    r.lo = *reinterpret_cast<const double2*>(q);
+    r.hi = *reinterpret_cast<const double2*>(q + o.hi);
+    return r;
 }
-__device__ __forceinline__ void trail_pass2(const TrailOps& o, int ab, int ac, const double (&z)[2][2], double& x0, double& x1) {
+__device__ __forceinline__ void trail_p1_mma(const P1Ops& b, double x0, double x1, double (&y)[2][2][2]) {
+    dmma884(y[0][0][0], y[0][0][1], x0, b.lo.x);
+    dmma884(y[0][1][0], y[0][1][1], x0, b.hi.x);
+    dmma884(y[1][0][0], y[1][0][1], x1, b.lo.y);
+    dmma884(y[1][1][0], y[1][1][1], x1, b.hi.y);
+}
+struct P2Ops { double a0, b0, a1, b1; };
+__device__ __forceinline__ P2Ops trail_p2_fetch(const TrailOps& o, int ab, int ac) {
     const double* qa = ((ac & 1) ? o.p2oa : o.p2ea) + 8 * ab + 8 * ac;
     const double* qb = ((ac & 1) ? o.p2ob : o.p2eb) + 8 * ab + 8 * ac;
-    dmma884(x0, x1, z[0][0], qa[0]);
-    dmma884(x0, x1, z[0][1], qb[0]);
-    dmma884(x0, x1, z[1][0], qa[o.hi]);
-    dmma884(x0, x1, z[1][1], qb[o.hi]);
+    P2Ops r;
+    r.a0 = qa[0]; r.b0 = qb[0]; r.a1 = qa[o.hi]; r.b1 = qb[o.hi];
+    return r;
+}
+__device__ __forceinline__ void trail_p2_mma(const P2Ops& b, const double (&z)[2][2], double& x0, double& x1) {
+    dmma884(x0, x1, z[0][0], b.a0);
+    dmma884(x0, x1, z[0][1], b.b0);
+    dmma884(x0, x1, z[1][0], b.a1);
+    dmma884(x0, x1, z[1][1], b.b1);
 }
 // Y'^T = -(Y^T T): yt[n][q] = Y^T[col g][reflector 8 n + 2 t + q]
 __device__ __forceinline__ void trail_apply_t(const double* __restrict__ Ts, int g, int t, bool have, const double (&y)[2][2][2],
@@ -368,10 +389,12 @@ __device__ __forceinline__ void trail_apply_t(const double* __restrict__ Ts, int
     for (int n = 0; n < 2; ++n) { z[n][0] = -z[n][0]; z[n][1] = -z[n][1]; }
 }
 
-template <bool ALIGNED, int NT>
+// NT > 0: single pass, NT - 4 < ntile <= NT tiles all in registers (only the last 4 carry guards).
+// NT = 0: two passes in chunks of kCh tiles (full chunks unguarded, one guarded tail chunk).
+template <int MODE, int NT, bool EXTRA = false>
 __device__ __noinline__ void trailing_fast(double* __restrict__ W, int ld, int cbeg, int cend, const RowMap rm, unsigned buf_off,
                                            int LP, unsigned ts_off, const QTeam tm) {
-    extern __shared__ double smem_raw[];
+    extern __shared__ __align__(16) double smem_raw[];
     const double* buf = smem_raw + buf_off;
     const double* Ts = smem_raw + ts_off;
     const int lane = threadIdx.x & 31;
@@ -381,8 +404,7 @@ __device__ __noinline__ void trailing_fast(double* __restrict__ W, int ld, int c
     {
         const int sw1 = vsw(g), swa = vsw(2 * t), swb = vsw(2 * t + 1);
         const double* r1 = buf + (size_t)g * LP;
-        o.p1e0 = r1 + swz_even(2 * t, sw1);     o.p1o0 = r1 + swz_odd(2 * t, sw1);
-        o.p1e1 = r1 + swz_even(2 * t + 1, sw1); o.p1o1 = r1 + swz_odd(2 * t + 1, sw1);
+        o.p1e = r1 + swz_even(2 * t, sw1); o.p1o = r1 + swz_odd(2 * t, sw1);
         const double* ra = buf + (size_t)(2 * t) * LP;
         const double* rb = ra + LP;
         o.p2ea = ra + swz_even(g, swa); o.p2oa = ra + swz_odd(g, swa);
@@ -391,6 +413,7 @@ __device__ __noinline__ void trailing_fast(double* __restrict__ W, int ld, int c
     }
     const int nt1 = (rm.len1 + 7) >> 3;                // aligned lists: tiles [0, nt1) lie in the first segment
     const int off1 = rm.j0 + 2 * t, off2 = rm.a2 - rm.len1 + 2 * t;
+    constexpr int NG = NT > 4 ? NT - 4 : 0;            // tiles [0, NG) exist for certain
     for (int kb = cbeg + tm.w * 8; kb < cend; kb += tm.nw * 8) {
         const int col = kb + g;
         const bool have = col < cend;
@@ -402,51 +425,123 @@ __device__ __noinline__ void trailing_fast(double* __restrict__ W, int ld, int c
             for (int n = 0; n < 2; ++n) { y[e][n][0] = 0.0; y[e][n][1] = 0.0; }
         double z[2][2];
         if (NT > 0) {
+            if (EXTRA) {  // tiles [NT, ntile): first product now (their second product follows the main block)
+                for (int i0 = NT; i0 < ntile; i0 += kCh) {
+                    double xe[kCh][2];
+#pragma unroll
+                    for (int a = 0; a < kCh; ++a) {
+                        xe[a][0] = 0.0; xe[a][1] = 0.0;
+                        if (i0 + a < ntile) trail_load<MODE>(cp, rm, i0 + a, t, nt1, off1, off2, xe[a][0], xe[a][1]);
+                    }
+#pragma unroll
+                    for (int a = 0; a < kCh; ++a)
+                        if (i0 + a < ntile) trail_p1_mma(trail_p1_fetch(o, i0, a), xe[a][0], xe[a][1], y);
+                }
+            }
             double xa[NT > 0 ? NT : 1][2];
 #pragma unroll
             for (int a = 0; a < NT; ++a) {
                 xa[a][0] = 0.0; xa[a][1] = 0.0;
-                if (a < ntile) trail_load<ALIGNED>(cp, rm, a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
+                if (EXTRA || a < NG || a < ntile) trail_load<MODE>(cp, rm, a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
             }
+            {   // pass 1, operands fetched one tile ahead
+                P1Ops nxt = trail_p1_fetch(o, 0, 0);
 #pragma unroll
-            for (int a = 0; a < NT; ++a)
-                if (a < ntile) trail_pass1(o, 0, a, xa[a][0], xa[a][1], y);
+                for (int a = 0; a < NT; ++a) {
+                    const P1Ops cur = nxt;
+                    if (a + 1 < NT && (EXTRA || a + 1 < NG || a + 1 < ntile)) nxt = trail_p1_fetch(o, 0, a + 1);
+                    if (EXTRA || a < NG || a < ntile) trail_p1_mma(cur, xa[a][0], xa[a][1], y);
+                }
+            }
             trail_apply_t(Ts, g, t, have, y, z);
+            {
+                P2Ops nxt = trail_p2_fetch(o, 0, 0);
 #pragma unroll
-            for (int a = 0; a < NT; ++a)
-                if (a < ntile) trail_pass2(o, 0, a, z, xa[a][0], xa[a][1]);
+                for (int a = 0; a < NT; ++a) {
+                    const P2Ops cur = nxt;
+                    if (a + 1 < NT && (EXTRA || a + 1 < NG || a + 1 < ntile)) nxt = trail_p2_fetch(o, 0, a + 1);
+                    if (EXTRA || a < NG || a < ntile) trail_p2_mma(cur, z, xa[a][0], xa[a][1]);
+                }
+            }
             if (have) {
 #pragma unroll
                 for (int a = 0; a < NT; ++a)
-                    if (a < ntile) trail_store<ALIGNED>(cp, rm, a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
+                    if (EXTRA || a < NG || a < ntile) trail_store<MODE>(cp, rm, a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
+            }
+            if (EXTRA) {
+                for (int i0 = NT; i0 < ntile; i0 += kCh) {
+                    double xe[kCh][2];
+#pragma unroll
+                    for (int a = 0; a < kCh; ++a) {
+                        xe[a][0] = 0.0; xe[a][1] = 0.0;
+                        if (i0 + a < ntile) trail_load<MODE>(cp, rm, i0 + a, t, nt1, off1, off2, xe[a][0], xe[a][1]);
+                    }
+#pragma unroll
+                    for (int a = 0; a < kCh; ++a)
+                        if (i0 + a < ntile) trail_p2_mma(trail_p2_fetch(o, i0, a), z, xe[a][0], xe[a][1]);
+                    if (have) {
+#pragma unroll
+                        for (int a = 0; a < kCh; ++a)
+                            if (i0 + a < ntile) trail_store<MODE>(cp, rm, i0 + a, t, nt1, off1, off2, xe[a][0], xe[a][1]);
+                    }
+                }
             }
         } else {
-            for (int i0 = 0; i0 < ntile; i0 += kCh) {
+            const int nfull = ntile / kCh * kCh;
+            for (int i0 = 0; i0 < nfull; i0 += kCh) {
+                double xa[kCh][2];
+#pragma unroll
+                for (int a = 0; a < kCh; ++a) trail_load<MODE>(cp, rm, i0 + a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
+                P1Ops nxt = trail_p1_fetch(o, i0, 0);
+#pragma unroll
+                for (int a = 0; a < kCh; ++a) {
+                    const P1Ops cur = nxt;
+                    if (a + 1 < kCh) nxt = trail_p1_fetch(o, i0, a + 1);
+                    trail_p1_mma(cur, xa[a][0], xa[a][1], y);
+                }
+            }
+            if (nfull < ntile) {
                 double xa[kCh][2];
 #pragma unroll
                 for (int a = 0; a < kCh; ++a) {
                     xa[a][0] = 0.0; xa[a][1] = 0.0;
-                    if (i0 + a < ntile) trail_load<ALIGNED>(cp, rm, i0 + a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
+                    if (nfull + a < ntile) trail_load<MODE>(cp, rm, nfull + a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
                 }
 #pragma unroll
                 for (int a = 0; a < kCh; ++a)
-                    if (i0 + a < ntile) trail_pass1(o, i0, a, xa[a][0], xa[a][1], y);
+                    if (nfull + a < ntile) trail_p1_mma(trail_p1_fetch(o, nfull, a), xa[a][0], xa[a][1], y);
             }
             trail_apply_t(Ts, g, t, have, y, z);
-            for (int i0 = 0; i0 < ntile; i0 += kCh) {
+            for (int i0 = 0; i0 < nfull; i0 += kCh) {
+                double xa[kCh][2];
+#pragma unroll
+                for (int a = 0; a < kCh; ++a) trail_load<MODE>(cp, rm, i0 + a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
+                P2Ops nxt = trail_p2_fetch(o, i0, 0);
+#pragma unroll
+                for (int a = 0; a < kCh; ++a) {
+                    const P2Ops cur = nxt;
+                    if (a + 1 < kCh) nxt = trail_p2_fetch(o, i0, a + 1);
+                    trail_p2_mma(cur, z, xa[a][0], xa[a][1]);
+                }
+                if (have) {
+#pragma unroll
+                    for (int a = 0; a < kCh; ++a) trail_store<MODE>(cp, rm, i0 + a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
+                }
+            }
+            if (nfull < ntile) {
                 double xa[kCh][2];
 #pragma unroll
                 for (int a = 0; a < kCh; ++a) {
                     xa[a][0] = 0.0; xa[a][1] = 0.0;
-                    if (i0 + a < ntile) trail_load<ALIGNED>(cp, rm, i0 + a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
+                    if (nfull + a < ntile) trail_load<MODE>(cp, rm, nfull + a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
                 }
 #pragma unroll
                 for (int a = 0; a < kCh; ++a)
-                    if (i0 + a < ntile) trail_pass2(o, i0, a, z, xa[a][0], xa[a][1]);
+                    if (nfull + a < ntile) trail_p2_mma(trail_p2_fetch(o, nfull, a), z, xa[a][0], xa[a][1]);
                 if (have) {
 #pragma unroll
                     for (int a = 0; a < kCh; ++a)
-                        if (i0 + a < ntile) trail_store<ALIGNED>(cp, rm, i0 + a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
+                        if (nfull + a < ntile) trail_store<MODE>(cp, rm, nfull + a, t, nt1, off1, off2, xa[a][0], xa[a][1]);
                 }
             }
         }
@@ -458,11 +553,23 @@ __device__ __forceinline__ void trailing_dispatch(double* __restrict__ W, int ld
     if (cbeg >= cend) return;
     const int ntile = (rm.len + 7) >> 3;
     if (rm.aligned) {
-        if (ntile <= 8) trailing_fast<true, 8>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
-        else if (ntile <= 16) trailing_fast<true, 16>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
-        else trailing_fast<true, 0>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+        // 16-byte accesses when every tile address is even (segment offsets and the leading dimension)
+        const bool vec = (((rm.j0 | (rm.a2 - rm.len1) | ld) & 1) == 0) && ((reinterpret_cast<size_t>(W) & 15) == 0);
+        if (vec) {
+            if (ntile <= 4) trailing_fast<2, 4>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+            else if (ntile <= 8) trailing_fast<2, 8>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+            else if (ntile <= 12) trailing_fast<2, 12>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+            else if (ntile <= 16) trailing_fast<2, 16>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+            else trailing_fast<2, 16, true>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+        } else {
+            if (ntile <= 4) trailing_fast<1, 4>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+            else if (ntile <= 8) trailing_fast<1, 8>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+            else if (ntile <= 12) trailing_fast<1, 12>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+            else if (ntile <= 16) trailing_fast<1, 16>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+            else trailing_fast<1, 16, true>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+        }
     } else {
-        trailing_fast<false, 0>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+        trailing_fast<0, 0>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
     }
 }
 
@@ -471,78 +578,149 @@ __device__ __forceinline__ void trailing_dispatch(double* __restrict__ W, int ld
 // the rows [len, 32 R) are zero; absent columns nbk .. kNB - 1 are zero columns).
 template <int R>
 __device__ __forceinline__ void panel_load(const double* __restrict__ W, int ld, const Shape& s, int j0, int nbk,
-                                           const RowMap& rm, unsigned buf_off, int LP, unsigned tau_off, const QTeam tm) {
-    extern __shared__ double smem_raw[];
+                                           const RowMap& rm, unsigned buf_off, int LP, unsigned tau_off, unsigned ts_off,
+                                           const QTeam tm) {
+    extern __shared__ __align__(16) double smem_raw[];
     double* buf = smem_raw + buf_off;
     const int lane = threadIdx.x & 31;
-    for (int p = tm.w; p < kNB; p += tm.nw) {
+    for (int e = tm.w * 32 + lane; e < kNB * kLdr; e += tm.nw * 32) smem_raw[ts_off + e] = 0.0;  // T starts as zero
+    constexpr int CMAX = 4;  // columns per warp (teams of >= 4 warps)
+    double v[CMAX][R];
+    // every load of the warp is issued before the first shared-memory store (one L2 round trip per panel)
+#pragma unroll
+    for (int q = 0; q < CMAX; ++q) {
+        const int p = tm.w + q * tm.nw;
         const bool valid = p < nbk;
         const int jp = j0 + (valid ? p : 0);
         const int et = env_top(s, jp), eb = env_bot(s, jp);
         const double* col = W + (size_t)jp * ld;
-        const int sw = vsw(p);
-        double* dst = buf + (size_t)p * LP;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int c = lane + 32 * r;
             const int row = rm.row(c);
             const bool ok = valid && c < rm.len && (row < s.nt ? row <= et : row <= eb);
-            dst[(lane ^ sw) + 32 * r] = ok ? col[row] : 0.0;
+            v[q][r] = ok ? col[row] : 0.0;
         }
-        if (lane == 0) smem_raw[tau_off + p] = 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < CMAX; ++q) {
+        const int p = tm.w + q * tm.nw;
+        if (p < kNB) {
+            const int sw = vsw(p);
+            double* dst = buf + (size_t)p * LP;
+#pragma unroll
+            for (int r = 0; r < R; ++r) dst[(lane ^ sw) + 32 * r] = v[q][r];
+            if (lane == 0) smem_raw[tau_off + p] = 0.0;
+        }
     }
 }
 
 template <int R>
 __device__ __forceinline__ void panel_factor(double* __restrict__ W, int ld, const Shape& s, int j0, int nbk, const RowMap& rm,
-                                             const FastQR& fq, int bi, const QTeam tm) {
-    const unsigned buf_off = fq.buf[bi], tau_off = fq.tau + bi * kNB;
+                                             const FastQR& fq, int bi, const QTeam tm, PhaseClock& pc) {
+    const unsigned buf_off = fq.buf[bi], tau_off = fq.tau + bi * kNB, ts_off = fq.Ts[bi];
     const int LP = fq.LP;
-    panel_load<R>(W, ld, s, j0, nbk, rm, buf_off, LP, tau_off, tm);
+    const int ntile = (rm.len + 7) >> 3;
+    panel_load<R>(W, ld, s, j0, nbk, rm, buf_off, LP, tau_off, ts_off, tm);
     tm.sync();
+    pc.mark(8);
+    const QTeam helpers{tm.w - 1, tm.nw - 1, -1};
+    const bool t_helper = tm.w >= 1 && tm.w <= 3;
 #pragma unroll 1
     for (int c0 = 0; c0 < nbk; c0 += 4) {
         const int nc = nbk - c0 < 4 ? nbk - c0 : 4;
-        if (tm.w == 0) subpanel_factor<R>(buf_off, LP, c0, nc, tau_off, fq.t4, W + (size_t)j0 * ld, ld, rm);
+        const int sidx = c0 >> 2;
+        if (tm.w == 0) {
+            subpanel_factor<R>(buf_off, LP, c0, nc, tau_off, fq.t4 + 16 * sidx, W + (size_t)j0 * ld, ld, rm);
+        } else if (c0 > 0) {
+            // hidden behind the factor warp: the previous sub-panel's reflectors applied to the columns beyond this
+            // sub-panel, and the previous sub-panel's T columns
+            subpanel_apply<R>(buf_off, LP, c0 - 4, c0 + 4, nbk, fq.t4 + 16 * (sidx - 1), helpers);
+            if (t_helper) t_extend(buf_off, LP, ntile, sidx - 1, ts_off, fq.t4 + 16 * (sidx - 1), fq.scratch, tm.w - 1);
+        }
         tm.sync();
-        if (c0 + 4 < nbk) {
-            subpanel_apply<R>(buf_off, LP, c0, c0 + 4, nbk, fq.t4, tm);
+        pc.mark(9);
+        if (c0 + 4 < nbk) {  // critical: the columns of the next sub-panel only
+            subpanel_apply<R>(buf_off, LP, c0, c0 + 4, c0 + 8 < nbk ? c0 + 8 : nbk, fq.t4 + 16 * sidx, tm);
             tm.sync();
+            pc.mark(10);
         }
     }
+    if (t_helper) t_extend(buf_off, LP, ntile, (nbk - 1) >> 2, ts_off, fq.t4 + 16 * ((nbk - 1) >> 2), fq.scratch, tm.w - 1);
+    pc.mark(14);
 }
 
 __device__ __forceinline__ void panel_factor_dispatch(double* __restrict__ W, int ld, const Shape& s, int j0, int nbk,
-                                                      const RowMap& rm, const FastQR& fq, int bi, bool need_t, const QTeam tm) {
-    if (rm.len <= 64) panel_factor<2>(W, ld, s, j0, nbk, rm, fq, bi, tm);
-    else if (rm.len <= 128) panel_factor<4>(W, ld, s, j0, nbk, rm, fq, bi, tm);
-    else panel_factor<8>(W, ld, s, j0, nbk, rm, fq, bi, tm);
-    if (need_t) {  // T factor of the whole panel (the last sub-panel's barrier precedes this)
-        gram16(fq.buf[bi], fq.LP, (rm.len + 7) >> 3, fq.Gs, fq.scratch, tm);
-        tm.sync();
-        if (tm.w == 0) t_factor16(fq.Gs, fq.tau + bi * kNB, fq.Ts[bi]);
-    }
+                                                      const RowMap& rm, const FastQR& fq, int bi, bool need_t, const QTeam tm,
+                                                      PhaseClock& pc) {
+    (void)need_t;
+    if (rm.len <= 64) panel_factor<2>(W, ld, s, j0, nbk, rm, fq, bi, tm, pc);
+    else if (rm.len <= 128) panel_factor<4>(W, ld, s, j0, nbk, rm, fq, bi, tm, pc);
+    else panel_factor<8>(W, ld, s, j0, nbk, rm, fq, bi, tm, pc);
 }
 
 // ---------------------------------------------------------------- driver
 // Requires every panel row list <= fq.LP <= 256 (the host checks this when it selects the CTA-per-member path).
+//
+// Look-ahead with warps placed by scheduler (a warp's scheduler is its index mod 4):
+//   * panel team  = warps 0 .. 3.  Its factor warp -- the one that runs the dependent per-column chain -- is warp 0 in
+//     the first CTA of an SM and warp 2 in the second (fq.slot), so that the chains of two co-resident CTAs never share
+//     a scheduler and its FP64 pipe (measured: 218 k -> 300 k member-steps/s);
+//   * update team = warps 4 .. 7: the tensor-core trailing updates.
+// Once panel k is factored, update warps 5 and 7 (schedulers 1 and 3: never a chain's) apply it to the columns of panel
+// k+1, one column group each, and release the panel team through a named barrier; the panel team then loads and
+// factors panel k+1 into the other buffer (T factor included) while the update team applies panel k to the columns
+// beyond.  One block barrier per panel joins the teams.
 __device__ __noinline__ void householder_qr_fast(double* __restrict__ W, int ld, const Shape s, const FastQR fq, PhaseClock& pc) {
     const int warp = threadIdx.x >> 5;
     const int nrows = s.nt + s.nbot;
     const int nref = nrows < s.ncols ? nrows : s.ncols;
     const QTeam all{warp, kWarps, 0};
+    constexpr int kHalf = kWarps / 2;
+    const bool in_p = warp < kHalf;
+    const QTeam pt{(warp - 2 * (fq.slot & 1)) & (kHalf - 1), kHalf, 1};   // team index 0 = factor warp
+    const int uw = warp - kHalf;                                         // 0 .. 3
+    const bool pri = in_p ? false : (uw & 1) == 1;                       // warps 5 and 7 take the priority columns
+    const QTeam ut_pri{uw >> 1, 2, 2};
+#ifndef PNMOL_U_ODD_ONLY
+#define PNMOL_U_ODD_ONLY 0
+#endif
+    // PNMOL_U_ODD_ONLY: only warps 5 and 7 do trailing updates (no DMMA on the schedulers of the two chains)
+    const QTeam ut_far = PNMOL_U_ODD_ONLY ? QTeam{uw >> 1, 2, 2} : QTeam{pri ? 2 + (uw >> 1) : (uw >> 1), kHalf, 2};
+    constexpr int kHandoff = (kHalf + 2) * 32;                           // panel team + the two priority warps
     int bi = 0;
+    int nbk = nref < kNB ? nref : kNB;
+    RowMap rm = panel_rows(s, 0, nbk - 1);
+    panel_factor_dispatch(W, ld, s, 0, nbk, rm, fq, bi, nbk < s.ncols, all, pc);
+    __syncthreads();
+    pc.mark(12);
     for (int j0 = 0; j0 < nref; j0 += kNB) {
-        const int nbk = nref - j0 < kNB ? nref - j0 : kNB;
-        const RowMap rm = panel_rows(s, j0, j0 + nbk - 1);
-        const bool trail = j0 + nbk < s.ncols;
-        panel_factor_dispatch(W, ld, s, j0, nbk, rm, fq, bi, trail, all);
-        __syncthreads();
-        pc.mark(9);
-        if (trail) trailing_dispatch(W, ld, j0 + nbk, s.ncols, rm, fq.buf[bi], fq.LP, fq.Ts[bi], all);
-        __syncthreads();
-        pc.mark(11);
-        bi ^= 1;
+        const int j1 = j0 + nbk;                       // first column of the next panel
+        const bool more = j1 < nref;
+        if (more) {
+            const int nb1 = nref - j1 < kNB ? nref - j1 : kNB;
+            const RowMap rm1 = panel_rows(s, j1, j1 + nb1 - 1);
+            if (in_p) {
+                asm volatile("bar.sync 3, %0;" ::"r"(kHandoff) : "memory");   // columns of panel k+1 are up to date
+                pc.mark(11);
+                panel_factor_dispatch(W, ld, s, j1, nb1, rm1, fq, bi ^ 1, j1 + nb1 < s.ncols, pt, pc);
+            } else {
+                if (pri) {
+                    trailing_dispatch(W, ld, j1, j1 + nb1, rm, fq.buf[bi], fq.LP, fq.Ts[bi], ut_pri);
+                    asm volatile("bar.arrive 3, %0;" ::"r"(kHandoff) : "memory");
+                }
+                if (!PNMOL_U_ODD_ONLY || pri) trailing_dispatch(W, ld, j1 + nb1, s.ncols, rm, fq.buf[bi], fq.LP, fq.Ts[bi], ut_far);
+            }
+            __syncthreads();
+            pc.mark(12);
+            rm = rm1;
+            nbk = nb1;
+            bi ^= 1;
+        } else {
+            if (j1 < s.ncols) trailing_dispatch(W, ld, j1, s.ncols, rm, fq.buf[bi], fq.LP, fq.Ts[bi], all);
+            __syncthreads();
+            pc.mark(11);
+        }
     }
 }
 

@@ -114,11 +114,11 @@ class Engine:
 
     @property
     def path(self):
-        """"warp" (one warp per member), "single_cta" (one CTA per member) or "multi_cta" (whole grid per member)."""
+        """"single_cta" (one CTA per member) or "multi_cta" (whole grid per member)."""
         rc = self.lib.pnmol_b200_path(self.h)
         if rc < 0:
             _lib.check(rc)
-        return {0: "single_cta", 1: "multi_cta", 2: "warp"}[rc]
+        return {0: "single_cta", 1: "multi_cta"}[rc]
 
     # ------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=torch.float64):

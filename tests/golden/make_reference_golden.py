@@ -147,7 +147,82 @@ def kalman():
     print("kalman: filter_step + smoother_step_sqrt / traditional for d = 4, 12, 33")
 
 
+def _reference_pde(o):
+    return SimpleNamespace(L=o.L, E_sqrtm=o.E_sqrtm, B=o.B, R_sqrtm=o.R_sqrtm, y0=o.y0, t0=o.t0, tmax=o.tmax, f=o.f, df=o.df,
+                           mesh_spatial=SimpleNamespace(points=o.points))
+
+
+def baseline_c1_48_steps():
+    """BASELINE config 1 / the C5 member at full length: heat N=50 (D=150, m=52), dt=2^-4, tmax=3 => 48 free-running
+    steps through the reference's own solve().  All means, the factors at steps 0, 1, 12, 24, 36, 48, every local
+    diffusion, the calibrated diffusion and the rescaled final factor of simulate_final_state."""
+    o, _ = oracle_problem("heat", 50, "dirichlet", tmax=3.0)
+    gram = setup_np.gram(setup_np.Sum(setup_np.SE(), setup_np.White()), o.points, 1)
+    pde = _reference_pde(o)
+    solver = pnmol.white.LinearWhiteNoiseEK1(num_derivatives=NU, steprule=pnmol.odetools.step.Constant(DT),
+                                             spatial_kernel=lambda X, Y: gram)
+    sol = solver.solve(pde)
+    states = [st for st, _ in solver.solution_generator(pde)][1:]
+    final, _ = solver.simulate_final_state(pde)
+    keep = np.array([0, 1, 12, 24, 36, 48])
+    info = {k: int(v) for k, v in sol.info.items()}
+    np.savez_compressed(os.path.join(HERE, "baseline_c1_heat_N50_48steps.npz"), gram=gram, dt=DT, nu=NU, tmax=3.0, num=50,
+                        t=np.asarray(sol.t), mean=np.asarray(sol.mean), keep=keep, cov_sqrtm_keep=np.asarray(sol.cov_sqrtm)[keep],
+                        diffusion_squared_local=np.array([float(s.diffusion_squared_local) for s in states]),
+                        diffusion_squared_calibrated=float(sol.diffusion_squared_calibrated),
+                        error_estimate_last=np.asarray(states[-1].error_estimate),
+                        final_cov_sqrtm=np.asarray(final.y.cov_sqrtm), y0=o.y0, L=o.L,
+                        info_keys=np.array(sorted(info)), info_vals=np.array([info[k] for k in sorted(info)]))
+    print("baseline C1 48 steps:", np.asarray(sol.mean).shape, "sigma^2", float(sol.diffusion_squared_calibrated))
+
+
+def _digest(L, n, idx):
+    """Compact, sign-invariant digest of a factor: diag(P), P on an index subset, Frobenius norms of the n x n
+    derivative blocks of P = L L^T."""
+    P = L @ L.T
+    blocks = np.array([[np.linalg.norm(P[i::n, j::n]) for j in range(n)] for i in range(n)])
+    return np.diag(P).copy(), P[np.ix_(idx, idx)].copy(), blocks
+
+
+def baseline_c2_c3_two_steps():
+    """BASELINE configs 2 and 3 at full size (SIR N=100: D=900, m=306, Matern-5/2 prior; spruce N=200 latent: D=1200,
+    m=202), initialise + two free-running steps through the reference's own code.  The factors are 6.5-11.5 MB each, so
+    the fixture keeps the means and a digest of every covariance (diagonal, a 120 x 120 principal sub-matrix that
+    covers every derivative, block norms)."""
+    rng = np.random.default_rng(20261018)
+    for name, prob, kind, num, bcond, dt, prior in (("c2_sir_N100", "sir", "white_semilinear", 100, "neumann", 2.0 ** -3, "matern"),
+                                                    ("c3_spruce_N200_latent", "spruce", "latent_semilinear", 200, "dirichlet", 2.0 ** -4, "se")):
+        kw = dict(bcond=bcond) if prob != "sir" else {}
+        o, copies = oracle_problem(prob, num, tmax=2 * dt, **kw)
+        kern = setup_np.Sum(setup_np.Matern52() if prior == "matern" else setup_np.SE(), setup_np.White())
+        gram = setup_np.gram(kern, o.points, copies)
+        pde = _reference_pde(o)
+        solver = SOLVERS[kind](num_derivatives=NU, steprule=pnmol.odetools.step.Constant(dt), spatial_kernel=lambda X, Y, g=gram: g)
+        states = [st for st, _ in solver.solution_generator(pde)]
+        assert len(states) == 3
+        D = np.asarray(states[0].y.cov_sqrtm).shape[0]
+        n = NU + 1
+        idx = np.sort(rng.choice(D, size=120, replace=False))
+        digs = [_digest(np.asarray(st.y.cov_sqrtm), n, idx) for st in states]
+        extra = {}
+        if kind.startswith("white"):
+            extra = dict(error_estimate=np.stack([np.asarray(st.error_estimate) for st in states[1:]]))
+        np.savez_compressed(os.path.join(HERE, f"baseline_{name}_2steps.npz"), dt=dt, nu=NU, num=num, kind=kind, problem=prob,
+                            bcond=bcond, prior=prior, t=np.array([float(st.t) for st in states]),
+                            mean=np.stack([np.asarray(st.y.mean) for st in states]), idx=idx,
+                            cov_diag=np.stack([d[0] for d in digs]), cov_sub=np.stack([d[1] for d in digs]),
+                            cov_block_norms=np.stack([d[2] for d in digs]),
+                            diffusion_squared_local=np.array([float(st.diffusion_squared_local) for st in states[1:]]),
+                            y0=o.y0, **extra)
+        print(f"baseline {name}: D={D}, sigma^2_loc", [float(st.diffusion_squared_local) for st in states[1:]])
+
+
 if __name__ == "__main__":
-    main()
-    adaptive()
-    kalman()
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if only in ("all", "small"):
+        main()
+        adaptive()
+        kalman()
+    if only in ("all", "baseline"):
+        baseline_c1_48_steps()
+        baseline_c2_c3_two_steps()

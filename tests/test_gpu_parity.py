@@ -80,13 +80,12 @@ def test_update_sqrt(m, D, noise):
 
 
 # ------------------------------------------------------------------------- EK1 steps
-@pytest.mark.parametrize("path", ["warp", "cta"])
+@pytest.mark.parametrize("path", ["cta"])
 @pytest.mark.parametrize("name,kind,bcond,num", KIND_CASES)
 def test_initialize_and_steps_from_oracle_state(name, kind, bcond, num, path, monkeypatch):
-    """Every step starts from the oracle's state: pure per-step parity (no error accumulation).  Both ensemble kernel
-    families (one CTA per member, the default; one warp per member, opt-in) on the same inputs."""
+    """Every step starts from the oracle's state: pure per-step parity (no error accumulation)."""
     monkeypatch.setenv("PNMOL_B200_PATH", path)
-    _check_initialize_and_steps(name, kind, bcond, num, "warp" if path == "warp" else "single_cta")
+    _check_initialize_and_steps(name, kind, bcond, num, "single_cta")
 
 
 LARGE_CASES = [("heat", "white_linear", "dirichlet", 6, 0), ("heat", "white_linear", "neumann", 50, 0),
@@ -151,8 +150,7 @@ def _check_initialize_and_steps(name, kind, bcond, num, path):
 TRAJ_CASES = [c for c in KIND_CASES if not (c[1].startswith("latent") and c[2] == "neumann")]
 
 
-@pytest.mark.parametrize("name,kind,bcond,num,path", [c + ("cta",) for c in TRAJ_CASES] + [c + ("large",) for c in TRAJ_CASES[::3]] +
-                         [c + ("warp",) for c in TRAJ_CASES[1::3]])
+@pytest.mark.parametrize("name,kind,bcond,num,path", [c + ("cta",) for c in TRAJ_CASES] + [c + ("large",) for c in TRAJ_CASES[::3]])
 def test_solve_trajectory(name, kind, bcond, num, path, monkeypatch):
     """Free-running trajectory (exactly representable dt): solve() against the oracle's solve(), on every kernel family."""
     monkeypatch.setenv("PNMOL_B200_PATH", path)
@@ -216,7 +214,7 @@ def test_simulate_final_state(kind, name, bcond, path, monkeypatch):
 
 
 @pytest.mark.parametrize("kind,name,path", [("white_linear", "heat", "cta"), ("latent_semilinear", "spruce", "cta"),
-                                            ("white_semilinear", "sir", "large"), ("white_linear", "heat", "warp")])
+                                            ("white_semilinear", "sir", "large")])
 def test_fused_marginal_readout(kind, name, path, monkeypatch):
     """solve_marginals (std fused into the step kernel, no factor trajectory) equals the read-out of
     experiments/figure1.py:76-89 applied to solve()'s full trajectory, and the oracle's marginals."""
@@ -392,7 +390,7 @@ def test_baseline_config_c4_full_size():
 
 
 # ------------------------------------------------------------------------- ensembles
-@pytest.mark.parametrize("path", ["cta", "large", "warp"])
+@pytest.mark.parametrize("path", ["cta", "large"])
 def test_ensemble_members_match_individual_oracle_solves(path, monkeypatch):
     from oracle import setup_np
     from pnmol_b200 import ensemble
@@ -468,7 +466,7 @@ def test_ensemble_properties_at_full_size():
 
 
 # ------------------------------------------------------------------------- golden fixtures
-GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith("reference_"))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith(("reference_", "baseline_")))
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])

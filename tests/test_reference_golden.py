@@ -45,6 +45,12 @@ def _info(g):
     return {str(k): int(v) for k, v in zip(g["info_keys"], g["info_vals"])}
 
 
+def _product_case(g):
+    prob, num, bcond = str(g["problem"]), int(g["num"]), str(g["bcond"])
+    kw = dict(bcond=bcond) if prob in ("heat", "spruce") else {}
+    return cases.make_case(prob, num=num, tmax=float(g["tmax"]), nu=int(g["nu"]), **kw)
+
+
 @pytest.mark.parametrize("path", FILES, ids=IDS)
 def test_oracle_equals_reference_source(path):
     g = np.load(path, allow_pickle=False)
@@ -129,10 +135,38 @@ def test_cuda_smoother_step_reproduces_reference_source():
 
 
 
-def _product_case(g):
-    prob, num, bcond = str(g["problem"]), int(g["num"]), str(g["bcond"])
-    kw = dict(bcond=bcond) if prob in ("heat", "spruce") else {}
-    return cases.make_case(prob, num=num, tmax=float(g["tmax"]), nu=int(g["nu"]), **kw)
+def _q1_spread(g, case, seeds=6):
+    """Reproducibility of the quirk-Q1 quantities BY THE REFERENCE ITSELF: the reference's algorithm (oracle, pinned to
+    the golden to rounding above) re-run with eps-level normwise perturbations of every QR input -- the backward error
+    of LAPACK's own Householder QR.  Returns the largest relative deviation from the golden over `seeds` perturbations of
+    (per-step local diffusion, calibrated diffusion).  x = R1^-1 z (white.py:125, latent.py:204) depends on the row
+    signs of R1, so these spreads are 1e-4 .. 0.7 where means and covariances are reproducible to 1e-12."""
+    kind, nu, dt = str(g["kind"]), int(g["nu"]), float(g["dt"])
+    loc = np.zeros(len(g["diffusion_squared_local"]))
+    cal = 0.0
+    for seed in range(seeds):
+        with cases.perturbed_oracle(seed):
+            states = list(ek1_np.generate(kind, case["opde"], dt, nu, case["gram_sqrtm"]))[1:]
+        d = np.array([float(s.diffusion_squared_local) for s in states])
+        loc = np.maximum(loc, np.abs(d - g["diffusion_squared_local"]) / np.abs(g["diffusion_squared_local"]))
+        cal = max(cal, abs(d.mean() - float(g["diffusion_squared_calibrated"])) / abs(float(g["diffusion_squared_calibrated"])))
+    return loc, cal
+
+
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_quirk_q1_reproducibility_of_the_reference(path):
+    """Demonstration (CPU): the calibrated diffusion the reference returns is reproducible only to ~1e-4 .. 1 relative
+    under eps-level perturbations of its own QR inputs, although the same runs reproduce the means to 1e-9.  This is why
+    the CUDA tests bound the diffusion by a multiple of this spread instead of a fixed 1e-9."""
+    g = np.load(path, allow_pickle=False)
+    case = _product_case(g)
+    loc, cal = _q1_spread(g, case, seeds=3)
+    n = int(g["nu"]) + 1
+    with cases.perturbed_oracle(0):
+        eps = ek1_np.solve(str(g["kind"]), case["opde"], float(g["dt"]), int(g["nu"]), case["gram_sqrtm"])
+    mean_dev = max(cases.block_rel(eps.mean[k], g["mean"][k], n) for k in range(1, len(g["t"])))
+    assert cal > 1e-7 and loc.max() > 1e-7            # far above the 1e-9 of the means ...
+    assert mean_dev < 1e-5 and mean_dev < 1e-2 * max(cal, loc.max())  # ... which the very same runs reproduce
 
 
 @pytest.mark.gpu
@@ -156,6 +190,25 @@ def test_cuda_path_reproduces_reference_source(path, family, monkeypatch):
     for k in range(len(g["t"])):
         assert cases.mean_excess(mean[k], g["mean"][k], spread=eps.mean[k]) < 1, k
         assert cases.cov_excess(chol[k], g["cov_sqrtm"][k], n) < 1, k
+    # quirk Q1 (white.py:125-128, pdefilter.py:82-95,113-116): local / calibrated diffusion and the rescaled covariance
+    # simulate_final_state returns, against the golden; tolerance = 20 x the reference's own reproducibility
+    loc_spread, cal_spread = _q1_spread(g, case)
+    states = [s for s, _ in cases.make_solver(kind, case).solution_generator(case["pde"])][1:]
+    loc = np.array([float(s.diffusion_squared_local) for s in states])
+    loc_err = np.abs(loc - g["diffusion_squared_local"]) / np.abs(g["diffusion_squared_local"])
+    assert np.all(loc_err <= 20 * loc_spread + 1e-9), (loc_err, loc_spread)
+    cal_ref = float(g["diffusion_squared_calibrated"])
+    cal_err = abs(float(sol.diffusion_squared_calibrated) - cal_ref) / abs(cal_ref)
+    assert cal_err <= 20 * cal_spread + 1e-9, (cal_err, cal_spread)
+    final, _ = cases.make_solver(kind, case).simulate_final_state(case["pde"])
+    Lf = final.y.cov_sqrtm.cpu().numpy()
+    # P_final = sigma^2 P_unscaled: the covariance error is the diffusion error plus the unscaled covariance's
+    fin_err = cases.block_rel(cases.cov(Lf), cases.cov(g["final_cov_sqrtm"]), n)
+    unscaled_err = cases.block_rel(cases.cov(chol[-1]), cases.cov(g["cov_sqrtm"][-1]), n)
+    assert fin_err <= 20 * cal_spread + 2 * unscaled_err + 1e-8, (fin_err, cal_spread, unscaled_err)
+    got = cases.cov(Lf)
+    want = cases.cov(chol[-1]) * float(sol.diffusion_squared_calibrated)
+    assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))  # rescaling itself: exact to rounding
 
 
 @pytest.mark.gpu
@@ -173,3 +226,111 @@ def test_cuda_adaptive_reproduces_reference_source():
     state, info = solver.simulate_final_state(case["pde"])
     assert info == _info(g) and state.t == float(g["t"])
     assert cases.mean_excess(state.y.mean.cpu().numpy(), g["mean"]) < 1
+
+
+# ----------------------------------------------------------------------------------------------- BASELINE-sized goldens
+# Produced by the reference's own source as well (make_reference_golden.py baseline): config 1 / the C5 member over the
+# full 48 steps, configs 2 and 3 at full size (two steps; factors as digests).
+C1_48 = os.path.join(HERE, "golden", "baseline_c1_heat_N50_48steps.npz")
+C23 = {"c2": os.path.join(HERE, "golden", "baseline_c2_sir_N100_2steps.npz"),
+       "c3": os.path.join(HERE, "golden", "baseline_c3_spruce_N200_latent_2steps.npz")}
+
+
+def _c23_case(g):
+    prob = str(g["problem"])
+    kw = dict(bcond=str(g["bcond"])) if prob != "sir" else {}
+    dt = float(g["dt"])
+    return cases.make_case(prob, num=int(g["num"]), dt=dt, prior=str(g["prior"]), tmax=2 * dt, **kw)
+
+
+def _digest_excess(L, g, k, n, rtol=cases.COV_RTOL):
+    """cov_excess (tests/cases.py) evaluated on the stored digest of step k: the diagonal and a principal sub-matrix."""
+    P = cases.cov(L)
+    D = P.shape[0]
+    idx = g["idx"]
+    sig = np.sqrt(np.abs(g["cov_diag"][k]))
+    eps = np.finfo(np.float64).eps
+    blockmax = np.array([[np.max(np.abs(P[i::n, j::n])) for j in range(n)] for i in range(n)])
+    tol_d = rtol * blockmax[np.arange(D) % n, np.arange(D) % n] + 10.0 * D * eps * sig.max() * 2 * sig
+    worst = np.max(np.abs(np.diag(P) - g["cov_diag"][k]) / np.maximum(tol_d, 1e-300))
+    tol_s = rtol * blockmax[np.ix_(idx % n, idx % n)] + 10.0 * D * eps * sig.max() * (sig[idx][:, None] + sig[idx][None, :])
+    worst = max(worst, np.max(np.abs(P[np.ix_(idx, idx)] - g["cov_sub"][k]) / np.maximum(tol_s, 1e-300)))
+    norms = np.array([[np.linalg.norm(P[i::n, j::n]) for j in range(n)] for i in range(n)])
+    worst = max(worst, np.max(np.abs(norms - g["cov_block_norms"][k]) / (rtol * np.sqrt(D) * np.maximum(g["cov_block_norms"][k], 1e-300)
+                                                                   + 10.0 * D * D * eps * sig.max() ** 2)))
+    return float(worst)
+
+
+def test_oracle_equals_reference_source_c1_48_steps():
+    g = np.load(C1_48, allow_pickle=False)
+    case = cases.make_case("heat", num=50, tmax=3.0)
+    assert np.allclose(case["gram_sqrtm"], np.linalg.cholesky(g["gram"]), rtol=1e-13, atol=0)
+    sol = ek1_np.solve("white_linear", case["opde"], float(g["dt"]), 2, case["gram_sqrtm"])
+    assert np.array_equal(sol.t, g["t"]) and len(sol.t) == 49
+    for k in range(49):
+        assert cases.block_rel(sol.mean[k], g["mean"][k], 3) <= 1e-11, k
+    for q, k in enumerate(g["keep"]):
+        assert cases.block_rel(cases.cov(sol.cov_sqrtm[k]), cases.cov(g["cov_sqrtm_keep"][q]), 3) <= 1e-10, k
+    assert float(sol.diffusion_squared_calibrated) == pytest.approx(float(g["diffusion_squared_calibrated"]), rel=1e-9)
+
+
+@pytest.mark.parametrize("cfg", sorted(C23))
+def test_oracle_equals_reference_source_c2_c3_full_size(cfg):
+    g = np.load(C23[cfg], allow_pickle=False)
+    case = _c23_case(g)
+    kind = str(g["kind"])
+    n = int(g["nu"]) + 1
+    states = list(ek1_np.generate(kind, case["opde"], float(g["dt"]), int(g["nu"]), case["gram_sqrtm"]))
+    assert len(states) == 3
+    for k, st in enumerate(states):
+        assert cases.block_rel(st.mean, g["mean"][k], n) <= 1e-10, k
+        assert _digest_excess(st.cov_sqrtm, g, k, n, rtol=1e-10) < 1, k
+    assert np.allclose([float(st.diffusion_squared_local) for st in states[1:]], g["diffusion_squared_local"], rtol=1e-8)
+
+
+@pytest.mark.gpu
+def test_cuda_path_reproduces_reference_source_c1_48_steps():
+    """BASELINE config 1 / the benchmark's ensemble member: 48 free-running steps at D = 150 against the reference's
+    own trajectory (every mean, the factors at steps 0, 1, 12, 24, 36, 48)."""
+    import __graft_entry__
+
+    __graft_entry__.ensure_built()
+    g = np.load(C1_48, allow_pickle=False)
+    case = cases.make_case("heat", num=50, tmax=3.0)
+    sol = cases.make_solver("white_linear", case).solve(case["pde"])
+    assert np.array_equal(np.asarray(sol.t), g["t"]) and sol.info == _info(g)
+    with cases.perturbed_oracle():
+        eps = ek1_np.solve("white_linear", case["opde"], float(g["dt"]), 2, case["gram_sqrtm"])
+    mean, chol = sol.mean.cpu().numpy(), sol.cov_sqrtm.cpu().numpy()
+    for k in range(49):
+        assert cases.mean_excess(mean[k], g["mean"][k], spread=eps.mean[k]) < 1, k
+    for q, k in enumerate(g["keep"]):
+        assert cases.cov_excess(chol[k], g["cov_sqrtm_keep"][q], 3) < 1, k
+    # the ensemble route (what bench.py times) returns the same final state
+    from pnmol_b200 import ensemble
+
+    res = ensemble.EnsembleSolver(cases.make_solver("white_linear", case), case["pde"], y0=np.tile(case["pde"].y0, (3, 1))
+                                  ).simulate_final_state(rescale=False)
+    assert cases.mean_excess(res.mean[1].cpu().numpy(), g["mean"][48], spread=eps.mean[48]) < 1
+    assert cases.cov_excess(res.cov_sqrtm[2].cpu().numpy(), g["cov_sqrtm_keep"][-1], 3) < 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", sorted(C23))
+def test_cuda_path_reproduces_reference_source_c2_c3_full_size(cfg):
+    """BASELINE configs 2 and 3 at full size, initialise + two FREE-RUNNING steps, against the reference's own run."""
+    import __graft_entry__
+
+    __graft_entry__.ensure_built()
+    g = np.load(C23[cfg], allow_pickle=False)
+    case = _c23_case(g)
+    kind = str(g["kind"])
+    n = int(g["nu"]) + 1
+    sol = cases.make_solver(kind, case).solve(case["pde"])
+    assert np.allclose(np.asarray(sol.t), g["t"], rtol=0, atol=0)
+    with cases.perturbed_oracle():
+        eps = ek1_np.solve(kind, case["opde"], float(g["dt"]), int(g["nu"]), case["gram_sqrtm"])
+    mean, chol = sol.mean.cpu().numpy(), sol.cov_sqrtm.cpu().numpy()
+    for k in range(3):
+        assert cases.mean_excess(mean[k], g["mean"][k], spread=eps.mean[k]) < 1, k
+        assert _digest_excess(chol[k], g, k, n) < 1, k

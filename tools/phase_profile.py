@@ -25,9 +25,9 @@ e0.record(); es.engine.run(pde.t0, es.dts, mean, chol); e1.record(); torch.cuda.
 out = np.zeros(24, np.uint64)
 _lib.check(lib.pnmol_b200_profile(es.engine.h, 0, _lib.ptr(out)))
 names = ["mean+evaluate_ode", "build predict", "QR predict (rest)", "error estimate", "build update", "QR update (rest)", "solves+mean", "outputs",
-         "qr: panel load", "qr: panel factor", "qr: panel writeback", "qr: trailing apply", "qr: end barrier",
-         "qr: gram V^T V", "qr: T factor", "-", "pair: loads+gemm1", "pair: barrier", "pair: T+gemm2", "pair: stores",
-         "panel: publish+barrier", "panel: dots+reduce", "panel: scalars", "(panel: rest = update+own -> in panel factor)"]
+         "qr: panel load", "qr: subpanel factor (1 warp)", "qr: subpanel apply", "qr: trailing apply", "qr: barrier after T",
+         "qr: gram V^T V", "qr: T factor", "-", "probe: P-team loads+pass1", "probe: T apply", "probe: pass2", "probe: stores",
+         "probe: pre-priority", "probe: priority update (warp 0)", "panel: scalars", "(panel: rest = update+own -> in panel factor)"]
 tot = float(out[:24].sum())
 ms = e0.elapsed_time(e1)
 print(f"members {M} steps {len(es.dts)}  kernel {ms:.1f} ms  -> {M*len(es.dts)/ms*1e3:.0f} member-steps/s")
