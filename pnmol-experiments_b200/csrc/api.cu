@@ -3,6 +3,7 @@
 #include "../../include/pnmol_b200.h"
 #include "ek1_kernels.cuh"
 #include "ek1_large.cuh"
+#include "ek1_small.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -97,6 +98,8 @@ struct pnmol_b200_handle {
     size_t smem_bytes, smem_optin;
     bool have_op = false, have_prior = false;
     double* steparr = nullptr;  // device: dts | tnew | pv | pinv
+    double* step_host = nullptr;  // pinned staging of the same
+    cudaEvent_t step_ev = nullptr;
     int steparr_cap = 0;
     // host-path state (pnmol_b200_simulate_final_state_host)
     double *hs_y0 = nullptr, *hs_mean_a = nullptr, *hs_mean_b = nullptr, *hs_chol_a = nullptr, *hs_chol_b = nullptr,
@@ -109,6 +112,10 @@ struct pnmol_b200_handle {
     LargeQR q{};
     size_t smem_large = 0;
     int cluster = 1;  // thread-block cluster size of the multi-CTA kernels (panel factorisation on cluster 0)
+    // small-state path (ek1_small.cuh): one warp per member, workspace in the warp's shared-memory slice
+    bool small = false;
+    SmallGeom sgeo{};
+    size_t smem_small = 0;
 };
 
 namespace {
@@ -151,23 +158,30 @@ int upload_steps(pnmol_b200_handle* h, int nsteps, double t0, const double* dts,
                  cudaStream_t st, RunArgs* a) {
     const int n = h->P.n;
     const size_t per = (size_t)nsteps * (2 + 2 * n);
+    // Device array + a pinned staging buffer owned by the handle; the copy is asynchronous, and an event recorded after it
+    // tells the next call when the staging buffer may be overwritten (no synchronisation of the caller's stream).
     if (h->steparr_cap < (int)per) {
+        if (h->step_ev) CU(cudaEventSynchronize(h->step_ev));
         CU(cudaStreamSynchronize(st));
         if (h->steparr) CU(cudaFree(h->steparr));
+        if (h->step_host) CU(cudaFreeHost(h->step_host));
         CU(cudaMalloc((void**)&h->steparr, per * sizeof(double)));
+        CU(cudaMallocHost((void**)&h->step_host, per * sizeof(double)));
         h->steparr_cap = (int)per;
     }
-    std::vector<double> buf(per);
+    if (!h->step_ev) CU(cudaEventCreateWithFlags(&h->step_ev, cudaEventDisableTiming));
+    else CU(cudaEventSynchronize(h->step_ev));  // the previous upload has left the staging buffer
+    double* buf = h->step_host;
     double t = t0;
     for (int s = 0; s < nsteps; ++s) {
         buf[s] = dts[s];
         t = t + dts[s];  // same floating-point accumulation as pdefilter.py:140 / white.py:139
         buf[nsteps + s] = t;
     }
-    std::memcpy(buf.data() + 2 * (size_t)nsteps, pv, sizeof(double) * nsteps * n);
-    std::memcpy(buf.data() + 2 * (size_t)nsteps + (size_t)nsteps * n, pinv, sizeof(double) * nsteps * n);
-    CU(cudaMemcpyAsync(h->steparr, buf.data(), per * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));  // buf is a stack-owned staging vector
+    std::memcpy(buf + 2 * (size_t)nsteps, pv, sizeof(double) * nsteps * n);
+    std::memcpy(buf + 2 * (size_t)nsteps + (size_t)nsteps * n, pinv, sizeof(double) * nsteps * n);
+    CU(cudaMemcpyAsync(h->steparr, buf, per * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(h->step_ev, st));
     a->dts = h->steparr;
     a->tnew = h->steparr + nsteps;
     a->pv = h->steparr + 2 * (size_t)nsteps;
@@ -195,7 +209,9 @@ int launch_large(pnmol_b200_handle* h, Kernel kernel, Args& a, cudaStream_t st) 
 }
 
 int launch_run(pnmol_b200_handle* h, RunArgs& a, cudaStream_t st) {
-    if (h->large) {
+    if (h->small) {
+        k_run_small<<<h->grid, 32 * h->sgeo.nwarps, h->smem_small, st>>>(h->P, a, h->sgeo);
+    } else if (h->large) {
         int rc = launch_large(h, k_run_large, a, st);
         if (rc) return rc;
     } else {
@@ -271,7 +287,9 @@ int pnmol_b200_destroy(pnmol_b200_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->step_ev) { cudaEventSynchronize(h->step_ev); cudaEventDestroy(h->step_ev); }
     if (h->steparr) cudaFree(h->steparr);
+    if (h->step_host) cudaFreeHost(h->step_host);
     for (void* p : {(void*)h->hs_y0, (void*)h->hs_mean_a, (void*)h->hs_mean_b, (void*)h->hs_chol_a, (void*)h->hs_chol_b,
                     (void*)h->hs_diffsum, (void*)h->hs_diffcal, (void*)h->hs_status, (void*)h->hs_err, (void*)h->hs_ref})
         if (p) cudaFree(p);
@@ -341,6 +359,36 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
         const std::string want_path = pathenv ? pathenv : "";
         if (want_path == "large") h->large = true;
         if (want_path == "cta" && h->smem_bytes <= h->smem_optin) h->large = false;
+        // Small state dimension: one warp per member with the whole workspace in shared memory (ek1_small.cuh).
+        // Auto-selected when at least 4 members fit an SM's shared memory side by side (D <~ 48).
+        if (want_path == "small" || (want_path.empty() && !force)) {
+            const int ld_small = (2 * P.D) | 1;  // odd leading dimension: conflict-free lane-per-column accesses
+            const int ldm_small = P.m | 1;
+            size_t per_warp = small_smem_doubles(P.D, P.m, P.dd, ld_small, ldm_small, P.wh);
+            per_warp += per_warp & 1;
+            const int fit = (int)(h->smem_optin / sizeof(double) / per_warp);
+            if (P.m <= 96 && (fit >= 4 || (want_path == "small" && fit >= 1))) {
+                h->small = true;
+                h->large = false;
+                P.ld = ld_small;
+                P.ldm = ldm_small;
+                SmallGeom& geo = h->sgeo;
+                geo.per_warp = (int)per_warp;
+                geo.nwarps = std::min(PNMOL_SMALL_THREADS / 32, fit);
+                if (const char* e = std::getenv("PNMOL_B200_WARPS")) geo.nwarps = std::max(1, std::min(geo.nwarps, std::atoi(e)));  // tuning
+                h->smem_small = (size_t)geo.per_warp * geo.nwarps * sizeof(double);
+                CU(cudaFuncSetAttribute(k_run_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_small));
+                CU(cudaFuncSetAttribute(k_init_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_small));
+                int occ = 0;
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_small, 32 * geo.nwarps, h->smem_small));
+                occ = std::max(1, occ);
+                h->grid = std::min((P.batch + geo.nwarps - 1) / geo.nwarps, occ * h->num_sms);
+                if (const char* e = std::getenv("PNMOL_B200_GRID")) h->grid = std::max(1, std::min(h->grid, std::atoi(e)));
+                h->have_op = true;
+                return 0;
+            }
+            if (want_path == "small") return fail(-1, "PNMOL_B200_PATH=small: the member's workspace does not fit in shared memory");
+        }
         if (h->large) {
             // one member at a time on the whole grid: one workspace, vectors in global scratch
             LargeQR& q = h->q;
@@ -481,7 +529,9 @@ int pnmol_b200_initialize(pnmol_b200_handle* h, const double* y0, double t0, dou
     a.y0 = y0; a.t0 = t0; a.prior_scale0 = diffuse_prior_scale;
     a.nugget = h->P.latent ? 1e-6 : 1e-10;  // latent.py:71,98 / white.py:33,51
     a.mean_out = mean_out; a.chol_out = chol_out; a.status = status;
-    if (h->large) {
+    if (h->small) {
+        k_init_small<<<h->grid, 32 * h->sgeo.nwarps, h->smem_small, (cudaStream_t)stream>>>(h->P, a, h->sgeo);
+    } else if (h->large) {
         int rc2 = launch_large(h, k_init_large, a, (cudaStream_t)stream);
         if (rc2) return rc2;
     } else {
@@ -577,9 +627,14 @@ int pnmol_b200_run_adaptive(pnmol_b200_handle* h, double t0, double tmax, const 
     a.dt0 = dt0; a.mean_a = mean; a.chol_a = chol; a.mean_b = mean_tmp; a.chol_b = chol_tmp;
     a.err = h->hs_err; a.ref = h->hs_ref; a.t_out = t_out; a.dt_out = dt_out; a.diff_sum = diff_sum; a.diff_last = diff_last;
     a.nsteps = num_steps; a.nattempts = num_attempts; a.status = status; a.max_attempts = max_attempts; a.flags = flags;
-    CU(cudaFuncSetAttribute(k_run_adaptive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    CU(cudaMemsetAsync(h->P.smslot, 0, sizeof(int) * h->num_sms, (cudaStream_t)stream));
-    k_run_adaptive<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
+    if (h->small) {
+        CU(cudaFuncSetAttribute(k_run_adaptive_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_small));
+        k_run_adaptive_small<<<h->grid, 32 * h->sgeo.nwarps, h->smem_small, (cudaStream_t)stream>>>(h->P, a, h->sgeo);
+    } else {
+        CU(cudaFuncSetAttribute(k_run_adaptive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        CU(cudaMemsetAsync(h->P.smslot, 0, sizeof(int) * h->num_sms, (cudaStream_t)stream));
+        k_run_adaptive<<<h->grid, kThreads, h->smem_bytes, (cudaStream_t)stream>>>(h->P, a);
+    }
     ++g_launches;
     CU(cudaGetLastError());
     return 0;
@@ -615,7 +670,7 @@ int pnmol_b200_profile(pnmol_b200_handle* h, int enable, uint64_t* cycles_out) {
 int pnmol_b200_path(pnmol_b200_handle* h) {
     if (!h) return fail(-1, "null handle");
     if (!h->have_op) return fail(-1, "pnmol_b200_set_operator has not been called");
-    return h->large ? 1 : 0;
+    return h->small ? 2 : (h->large ? 1 : 0);
 }
 
 int pnmol_b200_rescale(pnmol_b200_handle* h, double* chol, const double* diff_sum, int nsteps, double* diff_cal_out,
@@ -624,7 +679,7 @@ int pnmol_b200_rescale(pnmol_b200_handle* h, double* chol, const double* diff_su
     if (rc) return rc;
     if (!chol || !diff_sum || nsteps <= 0) return fail(-1, "invalid argument");
     const Problem& P = h->P;
-    dim3 g(std::max(1, std::min(64, (int)((size_t)P.D * P.D / 1024))), P.batch);
+    dim3 g(std::max(1, std::min(64, (int)((size_t)P.D * P.D / 1024))), std::min(P.batch, 32768));
     k_rescale<<<g, 256, 0, (cudaStream_t)stream>>>(chol, diff_sum, diff_cal_out, nsteps, (size_t)P.D * P.D, P.batch);
     ++g_launches;
     CU(cudaGetLastError());
@@ -667,19 +722,19 @@ int pnmol_b200_simulate_final_state_host(pnmol_b200_handle* h, const double* y0_
 
 // ------------------------------------------------------------------ dense sqrt functions
 namespace {
-struct Scratch { double* p = nullptr; size_t cap = 0; int device = -1; };
-Scratch g_scratch;
-int get_scratch(int device, size_t count, double** out) {
-    if (g_scratch.device != device || g_scratch.cap < count) {
-        CU(cudaDeviceSynchronize());
-        if (g_scratch.p) { cudaSetDevice(g_scratch.device); cudaFree(g_scratch.p); cudaSetDevice(device); }
-        CU(cudaMalloc((void**)&g_scratch.p, count * sizeof(double)));
-        g_scratch.cap = count;
-        g_scratch.device = device;
+// Workspace of the handle-less dense entry points: allocated and freed in stream order on the CALLER's stream
+// (cudaMallocAsync / cudaFreeAsync), so concurrent calls on different streams or from different threads never share it.
+struct StreamScratch {
+    double* p = nullptr;
+    cudaStream_t st = nullptr;
+    int acquire(size_t count, cudaStream_t stream) {
+        st = stream;
+        cudaError_t e = cudaMallocAsync((void**)&p, std::max<size_t>(count, 1) * sizeof(double), st);
+        if (e != cudaSuccess) return fail(-2, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+        return 0;
     }
-    *out = g_scratch.p;
-    return 0;
-}
+    ~StreamScratch() { if (p) cudaFreeAsync(p, st); }
+};
 }  // namespace
 
 int pnmol_b200_sqrt_propagate(const double* S1, const double* S2, double* out, int r, int c1, int c2, int batch, int device,
@@ -691,9 +746,10 @@ int pnmol_b200_sqrt_propagate(const double* S1, const double* S2, double* out, i
     CU(cudaSetDevice(device));
     const int rows = c1 + c2;
     const int grid = std::min(batch, 296);
-    double* W;
-    int rc = get_scratch(device, (size_t)grid * rows * r, &W);
+    StreamScratch ws;
+    int rc = ws.acquire((size_t)grid * rows * r, (cudaStream_t)stream);
     if (rc) return rc;
+    double* W = ws.p;
     const size_t smem = sizeof(double) * (rows + 4 + 2 * kWarps);
     CU(cudaFuncSetAttribute(k_sqrt_propagate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     k_sqrt_propagate<<<grid, kThreads, smem, (cudaStream_t)stream>>>(S1, S2, out, r, c1, c2, batch, W);
@@ -711,9 +767,10 @@ int pnmol_b200_sqrt_update(const double* H, const double* C, const double* measc
     if (device < 0 || device >= ndev) return fail(-3, "no such CUDA device (libpnmol_b200 has no CPU fallback)");
     CU(cudaSetDevice(device));
     const int grid = std::min(batch, 296);
-    double* W;
-    int rc = get_scratch(device, (size_t)grid * (D + m) * (m + D), &W);
+    StreamScratch ws;
+    int rc = ws.acquire((size_t)grid * (D + m) * (m + D), (cudaStream_t)stream);
     if (rc) return rc;
+    double* W = ws.p;
     const size_t smem = sizeof(double) * (D + m + 4 + 2 * kWarps);
     CU(cudaFuncSetAttribute(k_sqrt_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     k_sqrt_update<<<grid, kThreads, smem, (cudaStream_t)stream>>>(H, C, meascov, C_out, K_out, S_out, m, D, batch, W);
@@ -732,9 +789,10 @@ int pnmol_b200_smoother_step(const double* m, const double* sc, const double* m_
     if (device < 0 || device >= ndev) return fail(-3, "no such CUDA device (libpnmol_b200 has no CPU fallback)");
     CU(cudaSetDevice(device));
     const int grid = std::min(batch, 296);
-    double* W;
-    int rc = get_scratch(device, (size_t)grid * 3 * d * 2 * d, &W);
+    StreamScratch ws;
+    int rc = ws.acquire((size_t)grid * 3 * d * 2 * d, (cudaStream_t)stream);
     if (rc) return rc;
+    double* W = ws.p;
     const size_t smem = sizeof(double) * (3 * d + 4 + 2 * kWarps);
     CU(cudaFuncSetAttribute(k_smoother_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     k_smoother_step<<<grid, kThreads, smem, (cudaStream_t)stream>>>(m, sc, m_fut, sc_fut, sgain, sq, mp, x, mean_out, chol_out, d,

@@ -297,18 +297,22 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_init(const Problem
         update_stage(P, b, sm, P.m, P.latent ? E_NUGGET_ONLY : E_STEP_PLUS_NUGGET, a.nugget, chol, nullptr, nullptr, Hcol,
                      Hval, W, o2, &nonfinite, pc);
         if (tid == 0 && a.status) a.status[b] = nonfinite;
+        if (nonfinite) {  // as in k_run: do not leave NaNs in the padding rows of the workspace for the next member
+            for (size_t k = tid; k < (size_t)P.ld * (P.m + P.D); k += kThreads) W[k] = 0.0;
+        }
         __syncthreads();
     }
 }
 
 // cov_sqrtm *= sqrt(mean local diffusion)   pdefilter.py:113-116
 __global__ void k_rescale(double* chol, const double* diff_sum, double* diff_cal, int nsteps, size_t csz, int batch) {
-    const int b = blockIdx.y;
-    const double cal = diff_sum[b] / nsteps;
-    const double s = sqrt(cal);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && diff_cal) diff_cal[b] = cal;
-    double* c = chol + (size_t)b * csz;
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < csz; k += (size_t)gridDim.x * blockDim.x) c[k] *= s;
+    for (int b = blockIdx.y; b < batch; b += gridDim.y) {  // (gridDim.y is capped below the 65535 limit)
+        const double cal = diff_sum[b] / nsteps;
+        const double s = sqrt(cal);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && diff_cal) diff_cal[b] = cal;
+        double* c = chol + (size_t)b * csz;
+        for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < csz; k += (size_t)gridDim.x * blockDim.x) c[k] *= s;
+    }
 }
 
 // Stand-alone marginal read-out of `count` factors (D x D each): out[count][dd].

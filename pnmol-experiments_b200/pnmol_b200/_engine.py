@@ -55,7 +55,9 @@ class Engine:
         if not torch.cuda.is_available():
             raise _lib.PnmolB200Error("pnmol_b200 needs a CUDA device: the EK1 path has no CPU fallback")
         self.lib = _lib.load()
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        dev = torch.device("cuda") if device is None else torch.device(device)
+        # normalise once: torch.device("cuda") has index None and means the CURRENT device, not device 0
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         semil = bool(getattr(pde, "is_semilinear", False)) and pde.reaction is not None
         if getattr(pde, "is_semilinear", False) and pde.reaction is None:
             raise NotImplementedError("semi-linear problems need a device Reaction tag (pde.reaction); arbitrary "
@@ -78,7 +80,7 @@ class Engine:
         reaction_id = pde.reaction.id if semil else 0
         h = ctypes.c_void_p()
         _lib.check(self.lib.pnmol_b200_create(ctypes.byref(h), self.kind, self.d, self.nu, self.nb, self.ncomp, batch,
-                                              reaction_id, self.device.index or 0))
+                                              reaction_id, self.device.index))
         self.h = h
         lcol, lval = to_ell(L)
         bcol, bval = to_ell(B)
@@ -114,11 +116,12 @@ class Engine:
 
     @property
     def path(self):
-        """"single_cta" (one CTA per member) or "multi_cta" (whole grid per member)."""
+        """"small" (one warp per member, workspace in shared memory), "single_cta" (one CTA per member) or "multi_cta"
+        (whole grid per member)."""
         rc = self.lib.pnmol_b200_path(self.h)
         if rc < 0:
             _lib.check(rc)
-        return {0: "single_cta", 1: "multi_cta"}[rc]
+        return {0: "single_cta", 1: "multi_cta", 2: "small"}[rc]
 
     # ------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=torch.float64):
@@ -257,7 +260,8 @@ def marginal_std(chol, num_derivatives):
     count = int(np.prod(lead)) if len(lead) else 1
     out = torch.empty((count, D // n), dtype=torch.float64, device=chol.device)
     _lib.check(_lib.load().pnmol_b200_marginal_std(_lib.ptr(chol), _lib.ptr(out), D, int(num_derivatives), count,
-                                                   chol.device.index or 0, _lib.current_stream(chol.device)))
+                                                   chol.device.index if chol.device.index is not None else torch.cuda.current_device(),
+                                                   _lib.current_stream(chol.device)))
     return out.reshape(*lead, D // n)
 
 

@@ -103,7 +103,7 @@ class PDEFilter(ABC):
                 and os.environ.get("PNMOL_B200_HOST_ADAPTIVE") != "1"):
             state0 = self.initialize(pde)
             eng = self._engine
-            if eng.path == "single_cta":  # accept/reject and the step-size proposal run inside one kernel launch
+            if eng.path in ("single_cta", "small"):  # accept/reject and the step-size proposal run inside one kernel launch
                 mean = state0.y.mean[None].contiguous()
                 chol = state0.y.cov_sqrtm[None].contiguous()
                 out = eng.run_adaptive(pde.t0, pde.tmax, self.steprule.first_dt(pde), self.steprule, mean, chol)

@@ -80,12 +80,26 @@ def test_update_sqrt(m, D, noise):
 
 
 # ------------------------------------------------------------------------- EK1 steps
-@pytest.mark.parametrize("path", ["cta"])
-@pytest.mark.parametrize("name,kind,bcond,num", KIND_CASES)
+SMALL_CASES = [c for c in KIND_CASES if c[3] <= 6]  # D <= 45: the member's workspace fits a warp's shared-memory slice
+
+
+@pytest.mark.parametrize("name,kind,bcond,num,path", [c + ("cta",) for c in KIND_CASES] + [c + ("small",) for c in SMALL_CASES])
 def test_initialize_and_steps_from_oracle_state(name, kind, bcond, num, path, monkeypatch):
-    """Every step starts from the oracle's state: pure per-step parity (no error accumulation)."""
+    """Every step starts from the oracle's state: pure per-step parity (no error accumulation).  Both ensemble kernel
+    families (one CTA per member; one warp per member with the workspace in shared memory for small state dimension)
+    on the same inputs."""
     monkeypatch.setenv("PNMOL_B200_PATH", path)
-    _check_initialize_and_steps(name, kind, bcond, num, "single_cta")
+    _check_initialize_and_steps(name, kind, bcond, num, "small" if path == "small" else "single_cta")
+
+
+def test_small_state_path_is_selected_automatically(monkeypatch):
+    """D = 18 (the reference's own test mesh, dx = 0.2): the warp-per-member kernels; D = 150: one CTA per member."""
+    monkeypatch.delenv("PNMOL_B200_PATH", raising=False)
+    for num, want in ((6, "small"), (50, "single_cta")):
+        case = cases.make_case("heat", num=num)
+        solver = cases.make_solver("white_linear", case)
+        solver.initialize(case["pde"])
+        assert solver._engine.path == want
 
 
 LARGE_CASES = [("heat", "white_linear", "dirichlet", 6, 0), ("heat", "white_linear", "neumann", 50, 0),
@@ -150,7 +164,8 @@ def _check_initialize_and_steps(name, kind, bcond, num, path):
 TRAJ_CASES = [c for c in KIND_CASES if not (c[1].startswith("latent") and c[2] == "neumann")]
 
 
-@pytest.mark.parametrize("name,kind,bcond,num,path", [c + ("cta",) for c in TRAJ_CASES] + [c + ("large",) for c in TRAJ_CASES[::3]])
+@pytest.mark.parametrize("name,kind,bcond,num,path", [c + ("cta",) for c in TRAJ_CASES] + [c + ("large",) for c in TRAJ_CASES[::3]] +
+                         [c + ("small",) for c in TRAJ_CASES if c[3] <= 6])
 def test_solve_trajectory(name, kind, bcond, num, path, monkeypatch):
     """Free-running trajectory (exactly representable dt): solve() against the oracle's solve(), on every kernel family."""
     monkeypatch.setenv("PNMOL_B200_PATH", path)
@@ -214,7 +229,7 @@ def test_simulate_final_state(kind, name, bcond, path, monkeypatch):
 
 
 @pytest.mark.parametrize("kind,name,path", [("white_linear", "heat", "cta"), ("latent_semilinear", "spruce", "cta"),
-                                            ("white_semilinear", "sir", "large")])
+                                            ("white_semilinear", "sir", "large"), ("white_linear", "heat", "small")])
 def test_fused_marginal_readout(kind, name, path, monkeypatch):
     """solve_marginals (std fused into the step kernel, no factor trajectory) equals the read-out of
     experiments/figure1.py:76-89 applied to solve()'s full trajectory, and the oracle's marginals."""
@@ -390,7 +405,7 @@ def test_baseline_config_c4_full_size():
 
 
 # ------------------------------------------------------------------------- ensembles
-@pytest.mark.parametrize("path", ["cta", "large"])
+@pytest.mark.parametrize("path", ["cta", "large", "small"])
 def test_ensemble_members_match_individual_oracle_solves(path, monkeypatch):
     from oracle import setup_np
     from pnmol_b200 import ensemble

@@ -170,7 +170,7 @@ def test_quirk_q1_reproducibility_of_the_reference(path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("family", ["cta", "large"])
+@pytest.mark.parametrize("family", ["cta", "large", "small"])
 @pytest.mark.parametrize("path", FILES, ids=IDS)
 def test_cuda_path_reproduces_reference_source(path, family, monkeypatch):
     import __graft_entry__
@@ -178,6 +178,8 @@ def test_cuda_path_reproduces_reference_source(path, family, monkeypatch):
     __graft_entry__.ensure_built()
     monkeypatch.setenv("PNMOL_B200_PATH", family)
     g = np.load(path, allow_pickle=False)
+    if family == "small" and g["L"].shape[0] > 15:
+        pytest.skip("the small-state kernels keep a member's workspace in one warp's shared memory (D <~ 48)")
     kind, nu, dt = str(g["kind"]), int(g["nu"]), float(g["dt"])
     n = nu + 1
     case = _product_case(g)
