@@ -51,10 +51,14 @@ def member_parameters(num_members, x, seed):
     return y0, diff, prior
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of pnmol::k_run per member-step, from the committed `ncu --set full`
-# capture profiles/r01_ncu_k_run_full_summary_v8.csv (296 members x 8 steps per launch: 727 MB read + 2777 MB written).
-# Four times the algorithmic 363 KB: the L2-resident per-CTA workspaces are written back to HBM as dirty lines.
-NCU_DRAM_BYTES_PER_MEMBER_STEP = (726.918400e6 + 2776.589e6) / (296 * 8)
+def ncu_traffic_record():
+    """dram__bytes_read.sum + dram__bytes_write.sum of pnmol::k_run per member-step, from the committed `ncu --set full`
+    capture record profiles/r02_ncu_k_run_c5.json (written by tools/ncu_summary.py: carries the git head of the captured
+    build, the capture command and the member-steps per launch).  None when the record is missing."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_k_run_c5.json")))
+    except Exception:
+        return None
 
 
 def work_model(D, m, d):
@@ -267,6 +271,45 @@ def run_b200_arm(args):
     member_steps = world * M * T * args.steps
     value = member_steps / (elapsed_ms * 1e-3)
 
+    # Strong scaling (BASELINE config 5: ONE ensemble of 4096 members sharded over the GPUs): the same time loop on this
+    # rank's slice of args.members members, timed the same way (device events, max over ranks), incl. the final gather.
+    strong = None
+    if world > 1:
+        from pnmol_b200.ensemble import member_slice
+
+        sl = member_slice(M, world, rank)
+        y0s, diffs, priors = member_parameters(M, pde.mesh_spatial.points[:, 0], SEED)
+        es_s = ensemble.EnsembleSolver(solver, pde, y0=y0s[sl], diff_scale=diffs[sl], prior_scale=priors[sl], device=dev)
+        m0s, c0s, _ = es_s.initialize()
+        ms_, cs_ = torch.empty_like(m0s), torch.empty_like(c0s)
+        Ms = sl.stop - sl.start
+        gath_s = torch.empty((world * ((M + world - 1) // world), D), dtype=torch.float64, device=dev)
+        pad = torch.zeros(((M + world - 1) // world, D), dtype=torch.float64, device=dev)
+
+        def strong_step():
+            ms_.copy_(m0s); cs_.copy_(c0s)
+            o = es_s.engine.run(pde.t0, es_s.dts, ms_, cs_)
+            pad[:Ms] = ms_.reshape(Ms, D)
+            dist.all_gather_into_tensor(gath_s, pad)
+            return o
+
+        for _ in range(3):
+            strong_step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            strong_step()
+        s1.record()
+        barrier()
+        tt = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "members_total": M, "members_per_gpu": Ms, "value": M * T * args.steps / (float(tt[0]) * 1e-3),
+                  "unit": "member-steps/s", "ms_per_step": float(tt[0]) / args.steps,
+                  "note": "one 4096-member ensemble sharded over the GPUs; members are indivisible units of 48 sequential "
+                          "steps, so 4096 / N members per GPU on 296 resident CTAs run in ceil(4096 / N / 296) waves"}
+        del es_s, m0s, c0s, ms_, cs_
+
     # FP64 peak: cuBLAS DGEMM through torch (same method as MEASURED_PEAKS.json uses for bf16)
     n_gemm = 4096
     a = torch.randn(n_gemm, n_gemm, dtype=torch.float64, device=dev)
@@ -289,10 +332,12 @@ def run_b200_arm(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     ach_tf = f_alg * M * T / (kernel_ms * 1e-3) * 1e-12
     ach_gbs = b_alg * M * T / (kernel_ms * 1e-3) * 1e-9
+    rec = ncu_traffic_record()
     roofline = {"bound": "tensor", "pipe": "fp64 (mma.sync DMMA + DFMA; tcgen05 has no FP64 MMA)", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
-                "traffic": NCU_DRAM_BYTES_PER_MEMBER_STEP * M * T,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per member-step "
-                                  "(profiles/r01_ncu_k_run_full_summary_v8.csv) x member-steps per launch",
+                "traffic": rec["dram_bytes_per_member_step"] * M * T if rec else None,
+                "traffic_source": (f"ncu dram__bytes_read.sum + dram__bytes_write.sum per member-step x member-steps per launch; "
+                                   f"capture of build {rec['git_head']} ({rec['command']}, profiles/r02_ncu_k_run_c5_summary.csv)"
+                                   if rec else "no capture record (profiles/r02_ncu_k_run_c5.json missing)"),
                 "kernel": "pnmol::k_run", "kernel_ms_per_launch": kernel_ms,
                 "algorithmic_flops_per_member_step": f_alg, "algorithmic_bytes_per_member_step": b_alg,
                 "peak_source": "measured in this run: cuBLAS DGEMM 4096^3 via torch.matmul(float64), best of 5 "
@@ -325,6 +370,9 @@ def run_b200_arm(args):
     other = None
     if rank == 0 and world == 1 and not args.no_other_configs:
         other = other_configs_timing(dev, fp64_peak)
+        # the other BASELINE configs' roofline fractions next to the headline's (same denominators)
+        roofline["other_configs"] = {k: {kk: v[kk] for kk in ("fp64_frac", "hbm_frac", "ms_per_step", "member_steps_per_sec", "path")
+                                         if kk in v} for k, v in other.items() if "error" not in v}
 
     if rank == 0:
         line = {
@@ -332,7 +380,7 @@ def run_b200_arm(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, T), "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "other_configs": other,
+            "gpu_launches": int(launches), "clocks": clocks, "strong_scaling": strong, "other_configs": other,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -384,9 +432,9 @@ def other_configs_timing(dev, fp64_peak):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    for name in ("c5_sir_N17_ensemble_4096", "c5_heat_N6_probe_ensemble_4096"):
+    for name in ("c5_sir_N17_ensemble_4096", "c5_heat_N6_probe_ensemble_65536", "c5_heat_N12_ensemble_16384", "c5_heat_N24_ensemble_4096"):
         try:
-            M = 4096
+            M = int(name.rsplit("_", 1)[1])
             rng = np.random.default_rng(SEED)
             if "sir" in name:
                 pde = examples.sir_1d_discretized(num=17, tmax=TMAX, diffusion_rate_S=0.035, diffusion_rate_I=0.035,
@@ -396,7 +444,7 @@ def other_configs_timing(dev, fp64_peak):
                 es = ensemble.EnsembleSolver(solver, pde, y0=np.tile(pde.y0, (M, 1)) * rng.uniform(0.9, 1.1, (M, 1)),
                                              diff_scale=np.exp(rng.uniform(np.log(0.3), np.log(3.0), (M, 3))), device=dev)
             else:
-                pde = examples.heat_1d_discretized(num=6, tmax=TMAX, diffusion_rate=0.035)
+                pde = examples.heat_1d_discretized(num=int(name.split("_N")[1].split("_")[0]), tmax=TMAX, diffusion_rate=0.035)
                 solver = white.LinearWhiteNoiseEK1(num_derivatives=NU, steprule=step.Constant(DT),
                                                    spatial_kernel=kernels.SquareExponential() + kernels.WhiteNoise())
                 y0, diff, prior = member_parameters(M, pde.mesh_spatial.points[:, 0], SEED)

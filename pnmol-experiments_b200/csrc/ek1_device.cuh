@@ -143,7 +143,10 @@ __host__ __device__ __forceinline__ size_t fastqr_doubles(int LP) {
 // vld = rows of a panel buffer (LP of the blocked QR: 64, 128 or 256)
 // wh: ELL width of the sparse rows of H (> 0: they live in shared memory; 0: in the global scratch Problem::Hcol/Hval)
 __host__ __device__ __forceinline__ size_t smem_doubles(int D, int m, int dd, int vld, int ldm, int wh) {
-    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 80 + 1 + fastqr_doubles(vld) + (size_t)m * ldm + 8 +
+    // (the m x ldm scratch of the error estimate and of the triangular solves aliases the panel buffers of the QR, which are
+    // idle then; it only takes extra room beyond their 2 x 16 x vld doubles)
+    const size_t msq = (size_t)m * ldm, bufs = 2 * (size_t)16 * vld;
+    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 80 + 1 + fastqr_doubles(vld) + (msq > bufs ? msq - bufs : 0) + 8 +
            (3 * (size_t)D + 2 * ((size_t)m + D) + 2) / 2 + 2 * (size_t)m * wh;
 }
 
@@ -174,8 +177,11 @@ __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vl
     s.fq.tau = (unsigned)(base - base0);    base += 2 * 16;
     s.fq.t4 = (unsigned)(base - base0);     base += 64;
     s.fqend = base;
-    s.msq = ldm > 0 ? base : nullptr;
-    base += (size_t)m * ldm + 8;
+    s.msq = ldm > 0 ? s.fqbase : nullptr;   // aliases the panel buffers (never live at the same time)
+    {
+        const size_t msq = (size_t)m * ldm, bufs = 2 * (size_t)16 * vld;
+        base += (msq > bufs ? msq - bufs : 0) + 8;
+    }
     int32_t* ib = reinterpret_cast<int32_t*>(base);
     s.te_p = ib;  ib += D;
     s.be_p = ib;  ib += D;
