@@ -217,7 +217,7 @@ __device__ __forceinline__ void load_envelopes(const Problem& P, const Smem& sm)
 // Unblocked, structure-aware, on the global (L2-resident) workspace.  After return the
 // upper triangle holds R and every entry below the diagonal inside the support envelope
 // is exactly zero.
-__device__ void householder_columns(double* __restrict__ W, int ld, const Shape& s, int jbeg, int jend, double* vbuf,
+static __device__ void householder_columns(double* __restrict__ W, int ld, const Shape& s, int jbeg, int jend, double* vbuf,
                                     double* red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nrows = s.nt + s.nbot;
@@ -288,7 +288,7 @@ __device__ void householder_columns(double* __restrict__ W, int ld, const Shape&
     }
 }
 
-__device__ void householder_qr(double* __restrict__ W, int ld, const Shape s, double* vbuf, double* red) {
+static __device__ void householder_qr(double* __restrict__ W, int ld, const Shape s, double* vbuf, double* red) {
     const int nrows = s.nt + s.nbot;
     householder_columns(W, ld, s, 0, nrows < s.ncols ? nrows : s.ncols, vbuf, red);
 }
@@ -747,7 +747,7 @@ struct UpdateOut {
 };
 
 // ---- part 1a: right block (rows 0..k hold R, copied from Rsrc if given; the rest of the envelope is zero)
-__device__ void update_build_right(const Problem& P, int mcur, int nrows, const double* __restrict__ Rsrc,
+static __device__ void update_build_right(const Problem& P, int mcur, int nrows, const double* __restrict__ Rsrc,
                                    const int32_t* te, const int32_t* be, double* Wr, int w0, int nw) {
     const int lane = threadIdx.x & 31;
     const int D = P.D, ld = P.ld;
@@ -766,7 +766,7 @@ __device__ void update_build_right(const Problem& P, int mcur, int nrows, const 
 }
 
 // ---- part 1b: left block: top = R H^T (column r = sum over the sparse row r of H), bottom = E^T
-__device__ void update_build_left(const Problem& P, int b, int mcur, int nrows, EMode emode, double nugget,
+static __device__ void update_build_left(const Problem& P, int b, int mcur, int nrows, EMode emode, double nugget,
                                   const int32_t* te, const int32_t* be, const int32_t* Hcol, const double* Hval,
                                   double* Wl, const double* Wr, int w0, int nw) {
     const int lane = threadIdx.x & 31;
@@ -921,7 +921,7 @@ __device__ int update_output_mean(const Problem& P, const Smem& sm, const Update
 
 // ---- part 3b: factor = P R3^T (white.py:132): row r of the factor = column m + r of R, rows m..
 // (R3[c][r] = W[(m + r) ld + m + c]).  Returns 1 on a non-finite value.
-__device__ int update_output_factor(const Problem& P, const Smem& sm, const UpdateOut& out, int mcur, int nrows,
+static __device__ int update_output_factor(const Problem& P, const Smem& sm, const UpdateOut& out, int mcur, int nrows,
                                     const double* Wr, int w0, int nw) {
     const int lane = threadIdx.x & 31;
     const int n = P.n, D = P.D, ld = P.ld;
@@ -950,7 +950,7 @@ __device__ int update_output_factor(const Problem& P, const Smem& sm, const Upda
     return bad;
 }
 
-__device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, EMode emode, double nugget,
+static __device__ void update_stage(const Problem& P, int b, const Smem& sm, int mcur, EMode emode, double nugget,
                              const double* __restrict__ Rsrc, const int32_t* te, const int32_t* be,
                              const int32_t* Hcol, const double* Hval, double* W, const UpdateOut out,
                              int* nonfinite, PhaseClock& pc) {

@@ -38,7 +38,7 @@ struct InitArgs {
 };
 
 // One EK1 step for member b: state (mean_in, chol_in) -> (mean_out, chol_out).
-__device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, double dt, double tnew,
+static __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, double dt, double tnew,
                          const double* mean_in, const double* chol_in, double* mean_out, double* chol_out,
                          double* err_out, double* ref_out, double* diff_out, int flags, int* nonfinite) {
     const int tid = threadIdx.x;
@@ -77,6 +77,7 @@ __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, doub
                  nonfinite, pc);
 }
 
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_RUN)
 __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem P, const RunArgs a) {
     extern __shared__ __align__(16) double smem_raw[];
     Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm, P.whs);
@@ -142,6 +143,9 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem 
         __syncthreads();
     }
 }
+#else
+__global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem P, const RunArgs a);
+#endif
 
 // Adaptive time loop on the device (src/pnmol/pdefilter.py:118-227 with src/pnmol/odetools/step.py:58-119): every
 // member advances with its own step size, accept/reject and step-size proposal happen in the kernel.  White-noise
@@ -156,6 +160,7 @@ struct AdaptiveArgs {
     int max_attempts, flags;
 };
 
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_ADAPTIVE)
 __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run_adaptive(const Problem P, const AdaptiveArgs a) {
     extern __shared__ __align__(16) double smem_raw[];
     Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm, P.whs);
@@ -239,8 +244,12 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run_adaptive(const
         __syncthreads();
     }
 }
+#else
+__global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run_adaptive(const Problem P, const AdaptiveArgs a);
+#endif
 
 // initialize(): two square-root updates on a Kronecker-structured prior factor.
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_INIT)
 __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_init(const Problem P, const InitArgs a) {
     extern __shared__ __align__(16) double smem_raw[];
     Smem sm = carve(smem_raw, P.D, P.m, P.dd, P.vld, P.ldm, P.whs);
@@ -303,8 +312,12 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_init(const Problem
         __syncthreads();
     }
 }
+#else
+__global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_init(const Problem P, const InitArgs a);
+#endif
 
 // cov_sqrtm *= sqrt(mean local diffusion)   pdefilter.py:113-116
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_MISC)
 __global__ void k_rescale(double* chol, const double* diff_sum, double* diff_cal, int nsteps, size_t csz, int batch) {
     for (int b = blockIdx.y; b < batch; b += gridDim.y) {  // (gridDim.y is capped below the 65535 limit)
         const double cal = diff_sum[b] / nsteps;
@@ -314,14 +327,22 @@ __global__ void k_rescale(double* chol, const double* diff_sum, double* diff_cal
         for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < csz; k += (size_t)gridDim.x * blockDim.x) c[k] *= s;
     }
 }
+#else
+__global__ void k_rescale(double* chol, const double* diff_sum, double* diff_cal, int nsteps, size_t csz, int batch);
+#endif
 
 // Stand-alone marginal read-out of `count` factors (D x D each): out[count][dd].
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_MISC)
 __global__ void k_marginal_std(const double* chol, double* out, int D, int n, int dd, int count) {
     for (int b = blockIdx.x; b < count; b += gridDim.x)
         marginal_std_rows(chol + (size_t)b * D * D, D, n, dd, out + (size_t)b * dd, threadIdx.x >> 5, blockDim.x >> 5);
 }
+#else
+__global__ void k_marginal_std(const double* chol, double* out, int D, int n, int dd, int count);
+#endif
 
 // K = Lk Lk^T (spatial Gram matrix), once per set_prior.
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_MISC)
 __global__ void k_gram(const double* Lk, double* Kg, int d) {
     const int r = blockIdx.x;
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -331,9 +352,13 @@ __global__ void k_gram(const double* Lk, double* Kg, int d) {
         Kg[(size_t)r * d + c] = acc;
     }
 }
+#else
+__global__ void k_gram(const double* Lk, double* Kg, int d);
+#endif
 
 // ---------------------------------------------------------------- dense sqrt entry points
 // propagate_cholesky_factor for dense S1 (r x c1), S2 (r x c2): QR of the (c1+c2) x r stack.
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_MISC)
 __global__ void __launch_bounds__(kThreads) k_sqrt_propagate(const double* S1, const double* S2, double* out, int r,
                                                             int c1, int c2, int batch, double* Wall) {
     extern __shared__ __align__(16) double smem_raw[];
@@ -358,7 +383,12 @@ __global__ void __launch_bounds__(kThreads) k_sqrt_propagate(const double* S1, c
         __syncthreads();
     }
 }
+#else
+__global__ void __launch_bounds__(kThreads) k_sqrt_propagate(const double* S1, const double* S2, double* out, int r,
+                                                            int c1, int c2, int batch, double* Wall);
+#endif
 
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_MISC)
 __global__ void __launch_bounds__(kThreads) k_sqrt_update(const double* H, const double* C, const double* E, double* C_out,
                                                          double* K_out, double* S_out, int m, int D, int batch,
                                                          double* Wall) {
@@ -418,11 +448,17 @@ __global__ void __launch_bounds__(kThreads) k_sqrt_update(const double* H, const
         __syncthreads();
     }
 }
+#else
+__global__ void __launch_bounds__(kThreads) k_sqrt_update(const double* H, const double* C, const double* E, double* C_out,
+                                                         double* K_out, double* S_out, int m, int D, int batch,
+                                                         double* Wall);
+#endif
 
 // Square-root RTS smoother step (src/pnmol/base/kalman.py:49-66): new_mean = m - G (mp - m_fut); the new factor is the
 // transpose of R[d:2d, d:] of the QR of the 3d x 2d matrix [[x^T, sc^T], [sq^T, 0], [0, sc_fut^T G^T]].
 // All inputs row-major [batch, ...]; one CTA per member, unblocked Householder QR on an L2-resident workspace.
 // (sc_fut may be any square root of the future covariance, not necessarily triangular.)
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_MISC)
 __global__ void __launch_bounds__(kThreads) k_smoother_step(const double* m, const double* sc, const double* m_fut,
                                                            const double* sc_fut, const double* sgain, const double* sq,
                                                            const double* mp, const double* x, double* mean_out,
@@ -469,5 +505,11 @@ __global__ void __launch_bounds__(kThreads) k_smoother_step(const double* m, con
         __syncthreads();
     }
 }
+#else
+__global__ void __launch_bounds__(kThreads) k_smoother_step(const double* m, const double* sc, const double* m_fut,
+                                                           const double* sc_fut, const double* sgain, const double* sq,
+                                                           const double* mp, const double* x, double* mean_out,
+                                                           double* chol_out, int d, int batch, double* Wall);
+#endif
 
 }  // namespace pnmol

@@ -27,7 +27,7 @@ __device__ __forceinline__ Smem large_vectors(const Problem& P, const LargeQR& q
 // Error estimate (white.py:153-162) with the m x d / m x m assemblies spread over the grid and a right-looking
 // Cholesky whose trailing update is spread over the grid (the diagonal of L is kept apart in q.Ld so that no CTA
 // reads an entry another one overwrites in the same phase).  sigma and the read-out stay on CTA 0.
-__device__ void error_estimate_large(cg::grid_group& grid, const Problem& P, int b, const Smem& sm, const LargeQR& q,
+static __device__ void error_estimate_large(cg::grid_group& grid, const Problem& P, int b, const Smem& sm, const LargeQR& q,
                                      const LargeSmem& ls, double p1s, double dt, EMode emode, const int32_t* Hcol, const double* Hval,
                                      double* F, double* S, double* err_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -156,7 +156,7 @@ __device__ void error_estimate_large(cg::grid_group& grid, const Problem& P, int
 }
 
 // update_stage (ek1_device.cuh) on the grid.  Ends with a grid barrier.
-__device__ void update_stage_large(cg::grid_group& grid, const Problem& P, int b, const Smem& sm, const LargeQR& q,
+static __device__ void update_stage_large(cg::grid_group& grid, const Problem& P, int b, const Smem& sm, const LargeQR& q,
                                    const LargeSmem& ls, int mcur, EMode emode, double nugget, const double* Rsrc,
                                    const int32_t* te, const int32_t* be, const int32_t* Hcol, const double* Hval, double* W,
                                    const UpdateOut out, double* diff_cta0, PhaseClock& pc) {
@@ -191,6 +191,7 @@ __device__ void update_stage_large(cg::grid_group& grid, const Problem& P, int b
     pc.mark(7);
 }
 
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_LARGE_RUN)
 __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const Problem P, const RunArgs a, const LargeQR q) {
     extern __shared__ __align__(16) double smem_raw[];
     cg::grid_group grid = cg::this_grid();
@@ -278,8 +279,12 @@ __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const 
         grid.sync();
     }
 }
+#else
+__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const Problem P, const RunArgs a, const LargeQR q);
+#endif
 
 // initialize() (white.py:12-80, latent.py:20-134) on the grid.
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_LARGE_INIT)
 __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_init_large(const Problem P, const InitArgs a, const LargeQR q) {
     extern __shared__ __align__(16) double smem_raw[];
     cg::grid_group grid = cg::this_grid();
@@ -337,5 +342,8 @@ __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_init_large(const
         grid.sync();
     }
 }
+#else
+__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_init_large(const Problem P, const InitArgs a, const LargeQR q);
+#endif
 
 }  // namespace pnmol

@@ -51,7 +51,7 @@ __device__ __forceinline__ Smem carve_small(double* base, const Problem& P, doub
 // Unblocked Householder QR of the column-major matrix W (per-warp shared memory, odd leading dimension: the lanes'
 // columns fall into different banks) by one warp.  Envelopes as in householder_columns; on return the upper triangle
 // holds R (the reflectors stay below the diagonal and are never read again).
-__device__ __noinline__ void qr_small(double* __restrict__ W, int ld, const Shape s) {
+static __device__ __noinline__ void qr_small(double* __restrict__ W, int ld, const Shape s) {
     const int lane = threadIdx.x & 31;
     const int nrows = s.nt + s.nbot;
     const int nref = nrows < s.ncols ? nrows : s.ncols;
@@ -118,7 +118,7 @@ __device__ __noinline__ void qr_small(double* __restrict__ W, int ld, const Shap
 }
 
 // update_stage (ek1_device.cuh) for one warp on its shared-memory workspace.  Returns the local diffusion.
-__device__ __noinline__ double update_stage_small(const Problem& P, int b, const Smem& sm, int mcur, EMode emode, double nugget,
+static __device__ __noinline__ double update_stage_small(const Problem& P, int b, const Smem& sm, int mcur, EMode emode, double nugget,
                                                   const double* __restrict__ Rsrc, const int32_t* te, const int32_t* be,
                                                   double* W, const UpdateOut out, int* bad, PhaseClock& pc) {
     const int D = P.D, ld = P.ld;
@@ -178,6 +178,7 @@ __device__ __forceinline__ double ek1_step_small(const Problem& P, int b, const 
 #define PNMOL_SMALL_THREADS 512
 #endif
 
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_SMALL)
 __global__ void __launch_bounds__(PNMOL_SMALL_THREADS, 1) k_run_small(const Problem P, const RunArgs a, const SmallGeom geo) {
     extern __shared__ __align__(16) double smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -240,8 +241,12 @@ __global__ void __launch_bounds__(PNMOL_SMALL_THREADS, 1) k_run_small(const Prob
         __syncwarp();
     }
 }
+#else
+__global__ void __launch_bounds__(PNMOL_SMALL_THREADS, 1) k_run_small(const Problem P, const RunArgs a, const SmallGeom geo);
+#endif
 
 // initialize(): two square-root updates on a Kronecker-structured prior factor (white.py:12-80, latent.py:20-134).
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_SMALL)
 __global__ void __launch_bounds__(PNMOL_SMALL_THREADS, 1) k_init_small(const Problem P, const InitArgs a, const SmallGeom geo) {
     extern __shared__ __align__(16) double smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -298,9 +303,13 @@ __global__ void __launch_bounds__(PNMOL_SMALL_THREADS, 1) k_init_small(const Pro
         __syncwarp();
     }
 }
+#else
+__global__ void __launch_bounds__(PNMOL_SMALL_THREADS, 1) k_init_small(const Problem P, const InitArgs a, const SmallGeom geo);
+#endif
 
 // Adaptive time loop on the device, one warp per member (k_run_adaptive of ek1_kernels.cuh; src/pnmol/pdefilter.py:118-227
 // with src/pnmol/odetools/step.py:58-119): accept/reject and the step-size proposal per member inside the kernel.
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_SMALL)
 __global__ void __launch_bounds__(PNMOL_SMALL_THREADS, 1) k_run_adaptive_small(const Problem P, const AdaptiveArgs a, const SmallGeom geo) {
     extern __shared__ __align__(16) double smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -379,5 +388,8 @@ __global__ void __launch_bounds__(PNMOL_SMALL_THREADS, 1) k_run_adaptive_small(c
         __syncwarp();
     }
 }
+#else
+__global__ void __launch_bounds__(PNMOL_SMALL_THREADS, 1) k_run_adaptive_small(const Problem P, const AdaptiveArgs a, const SmallGeom geo);
+#endif
 
 }  // namespace pnmol

@@ -499,7 +499,7 @@ __device__ __noinline__ void trailing_dmma(double* __restrict__ W, int ld, int n
 // both warps apply T redundantly and update their own rows in place.  Every warp runs the same number of rounds.
 constexpr int kHalf = 16;  // tiles per warp (row lists up to 256)
 
-__device__ __noinline__ void trailing_dmma_pair(double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
+static __device__ __noinline__ void trailing_dmma_pair(double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
                                                 const double* __restrict__ Vs, int ldt, const double* __restrict__ Vr,
                                                 const double* __restrict__ Ts, double* __restrict__ xch, PhaseClock& pc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -836,7 +836,7 @@ __device__ __noinline__ void qr_panel_step(double* __restrict__ W, int ld, const
 
 // Blocked QR driver.  Panels whose row list exceeds 512 rows (or the smem V buffer) fall
 // back to the unblocked column-by-column routine.
-__device__ void householder_qr_blocked(double* __restrict__ W, int ld, const Shape s, double* Vs, int vld, double* xraw,
+static __device__ void householder_qr_blocked(double* __restrict__ W, int ld, const Shape s, double* Vs, int vld, double* xraw,
                                        double* sc, double* Vr, double* Ts, double* Gs, double* scratch, double* vbuf,
                                        double* red, PhaseClock& pc) {
     const int nrows = s.nt + s.nbot;

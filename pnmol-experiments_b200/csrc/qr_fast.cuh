@@ -236,7 +236,7 @@ __device__ __forceinline__ int swz_odd(int x, int sw) { return (x ^ (sw & 7)) - 
 //   T[4s:4s+4, 4s:4s+4] = T4_s (from the factor warp),   T[0:4s, 4s:4s+4] = -T[0:4s, 0:4s] (V_<s^T V_s) T4_s.
 // Three helper warps (h = 0, 1, 2; named barrier 4) share the Gram block V_<s^T V_s on the tensor pipe -- every warp a
 // third of the 8-row tiles, partial blocks summed in a fixed order -- and helper 0 does the two small products.
-__device__ __noinline__ void t_extend(unsigned buf_off, int LP, int ntile, int sidx, unsigned ts_off, unsigned t4_off,
+static __device__ __noinline__ void t_extend(unsigned buf_off, int LP, int ntile, int sidx, unsigned ts_off, unsigned t4_off,
                                       unsigned scratch_off, int h) {
     extern __shared__ __align__(16) double smem_raw[];
     const double* buf = smem_raw + buf_off;
@@ -671,7 +671,7 @@ __device__ __forceinline__ void panel_factor_dispatch(double* __restrict__ W, in
 // k+1, one column group each, and release the panel team through a named barrier; the panel team then loads and
 // factors panel k+1 into the other buffer (T factor included) while the update team applies panel k to the columns
 // beyond.  One block barrier per panel joins the teams.
-__device__ __noinline__ void householder_qr_fast(double* __restrict__ W, int ld, const Shape s, const FastQR fq, PhaseClock& pc) {
+static __device__ __noinline__ void householder_qr_fast(double* __restrict__ W, int ld, const Shape s, const FastQR fq, PhaseClock& pc) {
     const int warp = threadIdx.x >> 5;
     const int nrows = s.nt + s.nbot;
     const int nref = nrows < s.ncols ? nrows : s.ncols;

@@ -57,7 +57,7 @@ __device__ __forceinline__ int row_cidx(const RowMap& rm, int row) { return row 
 
 // Gram matrix of the panel's reflectors on the tensor pipe (upper triangle, Gs[k * 17 + i], k <= i), V(refl, c) =
 // V[refl * ldv + c] zero padded to a multiple of 8 rows; per-warp partial blocks are summed in a fixed order.
-__device__ void large_gram(const double* __restrict__ V, int ldv, int len, double* __restrict__ Gs, double* __restrict__ scratch) {
+static __device__ void large_gram(const double* __restrict__ V, int ldv, int len, double* __restrict__ Gs, double* __restrict__ scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int ntile = (len + 7) >> 3;
@@ -98,7 +98,7 @@ __device__ void large_gram(const double* __restrict__ V, int ldv, int len, doubl
 // Two block barriers per column: the warp that updates the next column also reduces that column's norm and diagonal
 // entry (published in shared memory), so every thread derives the next reflector's scalars without another
 // reduction round; each warp updates two panel columns at once (one pass over the reflector).
-__device__ void large_panel_factor(double* __restrict__ W, int ld, const Shape& s, int j0, int nbk, const RowMap rm,
+static __device__ void large_panel_factor(double* __restrict__ W, int ld, const Shape& s, int j0, int nbk, const RowMap rm,
                                    const LargeQR& q, const LargeSmem& ls, PhaseClock& pc) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = rm.len, lp = (L + 7) & ~7, nt = s.nt;
@@ -289,7 +289,7 @@ __device__ void large_panel_factor(double* __restrict__ W, int ld, const Shape& 
 // Requires Lc >= kNB (the diagonal block lives in CTA 0) -- the caller falls back to large_panel_factor otherwise.
 constexpr int kGath = 2 * kNB;  // doubles per CTA and column round: kNB partial dots + kNB row-i entries
 
-__device__ void large_panel_factor_cluster(cg::cluster_group& cluster, double* __restrict__ W, int ld, const Shape& s, int j0,
+static __device__ void large_panel_factor_cluster(cg::cluster_group& cluster, double* __restrict__ W, int ld, const Shape& s, int j0,
                                            int nbk, const RowMap rm, const LargeQR& q, const LargeSmem& ls, int Lc) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int CS = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
@@ -451,7 +451,7 @@ __device__ void large_panel_factor_cluster(cg::cluster_group& cluster, double* _
 }
 
 // S2: partial Y^T = C^T V per (row chunk, column group) item.
-__device__ void large_trailing_y(const double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
+static __device__ void large_trailing_y(const double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
                                  const LargeQR& q, int RC, double* __restrict__ Vr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -509,7 +509,7 @@ __device__ void large_trailing_y(const double* __restrict__ W, int ld, int ncols
 }
 
 // S3: C^T -= (Y^T T) V^T on the rows of each item's chunk.
-__device__ void large_trailing_u(double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
+static __device__ void large_trailing_u(double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
                                  const LargeQR& q, int RC, double* __restrict__ Vs, double* __restrict__ Ts) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -602,7 +602,7 @@ __device__ __forceinline__ int large_chunk_rows(int L, int ntrail, int cap) {
 }
 
 // Grid-wide blocked QR.  On return (after a grid barrier) the upper triangle holds R.
-__device__ void householder_qr_large(cg::grid_group& grid, double* __restrict__ W, int ld, const Shape s, const LargeQR& q,
+static __device__ void householder_qr_large(cg::grid_group& grid, double* __restrict__ W, int ld, const Shape s, const LargeQR& q,
                                      const LargeSmem& ls, PhaseClock& pc) {
     const int nrows = s.nt + s.nbot;
     const int nref = nrows < s.ncols ? nrows : s.ncols;

@@ -379,7 +379,6 @@ def test_baseline_configs_c2_c3_full_size(name, kind, bcond, num, dt):
     print(f"[{name} N={num} D={st.cov_sqrtm.shape[0]}] initialize {t_init:.3f} s, step {t_step:.3f} s (multi-CTA path)")
 
 
-@pytest.mark.skipif(not os.environ.get("PNMOL_B200_SLOW"), reason="the NumPy oracle needs ~1 min of host time at D=3072; set PNMOL_B200_SLOW=1")
 def test_baseline_config_c4_full_size():
     """BASELINE.json config 4 (heat N=1024: D=3072, m=1026): one step from the oracle's state (multi-CTA path)."""
     import time
