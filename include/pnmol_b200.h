@@ -219,6 +219,27 @@ int pnmol_b200_smoother_step(const double* m, const double* sc, const double* m_
                              const double* sq, const double* mp, const double* x, double* mean_out, double* chol_out, int d,
                              int batch, int device, void* stream);
 
+/* Batched probabilistic finite-difference stencils (src/pnmol/discretize.py:177-201
+ * fd_coefficients, vmapped over the mesh points as in fd_probabilistic :61-77 and, here, over `nbatch` kernel
+ * hyper-parameter sets).  kernel_kind: 0 SquareExponential, 1 Matern52, 2 Polynomial (src/pnmol/kernels.py:107-144);
+ * kernel_params dev [nbatch, 4] = (input_scale, output_scale, order, const); x dev [npoints] evaluation points,
+ * neighbors dev [npoints, stencil] stencil points (1-D meshes; stencil <= 8); diffop: 0 gradient, 1 laplace.
+ * Outputs: weights dev [nbatch, npoints, stencil] (rows of L), uncertainties dev [nbatch, npoints] (diagonal of
+ * E_sqrtm).  Asynchronous on `stream`. */
+int pnmol_b200_fd_coefficients(int kernel_kind, const double* kernel_params, int nbatch, const double* x,
+                               const double* neighbors, int npoints, int stencil, int diffop, double nugget_gram_matrix,
+                               double* weights, double* uncertainties, int device, void* stream);
+
+/* Batched spatial Gram matrix and its Cholesky factor, chol(k(X, X) + diagonal_add I) (src/pnmol/white.py:82-94
+ * initialize_iwp; diagonal_add = WhiteNoise output_scale^2 + nugget), and optionally the Gaussian log-likelihood of
+ * `data` under each Gram matrix (src/pnmol/kernels.py:186-211 mle_input_scale / log_likelihood).  points dev [d]
+ * (1-D mesh), data dev [d] or NULL, chol_out dev [nbatch, d, d] (lower, zeros above the diagonal), loglik_out dev
+ * [nbatch] or NULL (needs d (d + 2) doubles of shared memory: d <= 168), status_out dev int32 [nbatch] or NULL (1 = not
+ * positive definite).  Asynchronous on `stream`. */
+int pnmol_b200_gram_cholesky(int kernel_kind, const double* kernel_params, int nbatch, const double* points, int d,
+                             double diagonal_add, const double* data, double* chol_out, double* loglik_out,
+                             int32_t* status_out, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@
 #include "ek1_kernels.cuh"
 #include "ek1_large.cuh"
 #include "ek1_small.cuh"
+#include "discretize.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -797,6 +798,50 @@ int pnmol_b200_smoother_step(const double* m, const double* sc, const double* m_
     CU(cudaFuncSetAttribute(k_smoother_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     k_smoother_step<<<grid, kThreads, smem, (cudaStream_t)stream>>>(m, sc, m_fut, sc_fut, sgain, sq, mp, x, mean_out, chol_out, d,
                                                                     batch, W);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pnmol_b200_fd_coefficients(int kernel_kind, const double* kernel_params, int nbatch, const double* x, const double* neighbors,
+                               int npoints, int stencil, int diffop, double nugget_gram_matrix, double* weights,
+                               double* uncertainties, int device, void* stream) {
+    if (!kernel_params || !x || !neighbors || !weights || !uncertainties || nbatch <= 0 || npoints <= 0)
+        return fail(-1, "invalid argument");
+    if (kernel_kind < 0 || kernel_kind > 2) return fail(-1, "kernel_kind: 0 SquareExponential, 1 Matern52, 2 Polynomial");
+    if (diffop < 0 || diffop > 1) return fail(-1, "diffop: 0 gradient, 1 laplace");
+    if (stencil < 1 || stencil > kMaxStencil) return fail(-1, "stencil size must be 1..8");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(-3, "no such CUDA device (libpnmol_b200 has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const size_t total = (size_t)nbatch * npoints;
+    const unsigned grid = (unsigned)((total + 127) / 128);
+    k_fd_coefficients<<<grid, 128, 0, (cudaStream_t)stream>>>(kernel_kind, kernel_params, nbatch, x, neighbors, npoints, stencil,
+                                                              diffop, nugget_gram_matrix, weights, uncertainties);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pnmol_b200_gram_cholesky(int kernel_kind, const double* kernel_params, int nbatch, const double* points, int d,
+                             double diagonal_add, const double* data, double* chol_out, double* loglik_out, int32_t* status_out,
+                             int device, void* stream) {
+    if (!kernel_params || !points || !chol_out || nbatch <= 0 || d <= 0) return fail(-1, "invalid argument");
+    if (kernel_kind < 0 || kernel_kind > 2) return fail(-1, "kernel_kind: 0 SquareExponential, 1 Matern52, 2 Polynomial");
+    if (loglik_out && !data) return fail(-1, "the log-likelihood needs data");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(-3, "no such CUDA device (libpnmol_b200 has no CPU fallback)");
+    CU(cudaSetDevice(device));
+    const size_t smem = sizeof(double) * ((size_t)d * (d + 1) + d);
+    int optin = 0;
+    CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    const bool in_smem = smem + 256 <= (size_t)optin;
+    if (loglik_out && !in_smem) return fail(-4, "log-likelihood: d too large for the shared-memory factorisation");
+    if (in_smem) CU(cudaFuncSetAttribute(k_gram_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gram_cholesky<<<std::min(nbatch, 8 * 148), 256, in_smem ? smem : 0, (cudaStream_t)stream>>>(
+        kernel_kind, kernel_params, nbatch, points, d, diagonal_add, data, chol_out, loglik_out, status_out, in_smem ? 1 : 0);
     ++g_launches;
     CU(cudaGetLastError());
     return 0;

@@ -4,3 +4,4 @@
 #include "ek1_kernels.cuh"
 #include "ek1_large.cuh"
 #include "ek1_small.cuh"
+#include "discretize.cuh"

@@ -38,6 +38,10 @@ SIGNATURES = {
     "pnmol_b200_sqrt_propagate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pnmol_b200_smoother_step": (c_int, [c_void_p] * 10 + [c_int, c_int, c_int, c_void_p]),
     "pnmol_b200_sqrt_update": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_int, c_void_p]),
+    "pnmol_b200_fd_coefficients": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p,
+                                           c_void_p, c_int, c_void_p]),
+    "pnmol_b200_gram_cholesky": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_int, c_void_p]),
 }
 
 _lib = None

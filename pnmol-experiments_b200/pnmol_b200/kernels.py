@@ -157,3 +157,69 @@ class _StackedKernel(Kernel):
 def duplicate(kernel, num):
     """kernels.py:178-183."""
     return _StackedKernel(kernel_list=[kernel] * num)
+
+
+# ------------------------------------------------------------------------- batched, on the device (SURVEY section 8f, rank 3)
+def _device_kernel_table(kernel_list):
+    """(kind, params [B, 4], white-noise variance) of a list of kernels of ONE type (optionally `+ WhiteNoise`)."""
+    kinds, rows, white = set(), [], set()
+    for k in kernel_list:
+        w = 0.0
+        if isinstance(k, _Sum):
+            base, wn = (k.a, k.b) if isinstance(k.b, WhiteNoise) else (k.b, k.a)
+            if not isinstance(wn, WhiteNoise):
+                raise NotImplementedError("device kernels: only `kernel + WhiteNoise` sums")
+            k, w = base, wn.output_scale ** 2
+        if isinstance(k, SquareExponential):
+            kinds.add(0); rows.append((k.input_scale, k.output_scale, 0.0, 0.0))
+        elif isinstance(k, Matern52):
+            kinds.add(1); rows.append((k.input_scale, k.output_scale, 0.0, 0.0))
+        elif isinstance(k, Polynomial):
+            kinds.add(2); rows.append((1.0, 1.0, float(k.order), float(k.const)))
+        else:
+            raise NotImplementedError(f"device kernels: {type(k).__name__} has no closed-form device implementation")
+        white.add(w)
+    if len(kinds) != 1 or len(white) != 1:
+        raise ValueError("a batch must hold kernels of one type with one white-noise scale")
+    return kinds.pop(), np.asarray(rows, dtype=np.float64), white.pop()
+
+
+def gram_cholesky_batched(kernel_list, mesh_points, *, data=None, nugget=0.0, device=None):
+    """``cholesky(k(X, X.T))`` for every kernel of the list in one launch (white.py:82-94 initialize_iwp, batched over
+    kernel hyper-parameters), and -- with ``data`` -- the log-likelihood of kernels.py:203-211 under each Gram matrix.
+
+    Returns torch CUDA tensors ``chol [B, d, d]`` (lower), ``status [B]`` (1 = not positive definite) and
+    ``loglik [B]`` or None."""
+    import torch
+
+    from . import _lib
+
+    kind, params, white = _device_kernel_table(kernel_list)
+    X = np.asarray(mesh_points, dtype=np.float64)
+    if X.ndim == 2:
+        if X.shape[1] != 1:
+            raise NotImplementedError("device kernels are 1-D")
+        X = X[:, 0]
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    dev = torch.device("cuda", idx if idx is not None else torch.cuda.current_device())
+    lib = _lib.load()
+    B, d = len(params), len(X)
+    par = torch.as_tensor(params, device=dev)
+    pts = torch.as_tensor(X, device=dev)
+    y = None if data is None else torch.as_tensor(np.asarray(data, dtype=np.float64).reshape(-1), device=dev)
+    chol = torch.empty((B, d, d), dtype=torch.float64, device=dev)
+    status = torch.zeros(B, dtype=torch.int32, device=dev)
+    ll = None if data is None else torch.empty(B, dtype=torch.float64, device=dev)
+    _lib.check(lib.pnmol_b200_gram_cholesky(kind, _lib.ptr(par), B, _lib.ptr(pts), d, float(white + nugget), _lib.ptr(y),
+                                            _lib.ptr(chol), _lib.ptr(ll), _lib.ptr(status), dev.index,
+                                            _lib.current_stream(dev)))
+    return chol, status, ll
+
+
+def mle_input_scale(*, mesh_points, data, kernel_type, input_scale_trials, nugget=0.0):
+    """kernels.py:186-200: the trial input scale with the largest Gaussian log-likelihood of ``data``; all trials are
+    factored in one launch (Cholesky instead of the reference's LU-based solve/det: same value for a positive
+    definite Gram matrix)."""
+    trials = np.asarray(input_scale_trials, dtype=np.float64)
+    _, _, ll = gram_cholesky_batched([kernel_type(input_scale=float(s)) for s in trials], mesh_points, data=data, nugget=nugget)
+    return trials[int(np.argmax(np.nan_to_num(ll.cpu().numpy(), nan=-np.inf)))]
