@@ -140,6 +140,31 @@ int dev_upload(pnmol_b200_handle* h, const T** out, const T* host, size_t count)
     return 0;
 }
 
+// 2-D tensor map of the reflector buffer of the multi-CTA QR (qr_large.cuh): dim0 = compact row index (contiguous, `lv`
+// doubles per reflector), dim1 = reflector; one box = `box_rows` rows x kNB reflectors.  The driver entry point is
+// resolved at run time (no link-time dependency on libcuda).
+int make_reflector_tensor_map(CUtensorMap* out, double* base, int lv, int box_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(-2, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)lv, (cuuint64_t)kNB};
+    const cuuint64_t strides[1] = {(cuuint64_t)lv * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)kNB};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-2, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return 0;
+}
+
 int prop_smem_per_sm(int device) {
     int v = 0;
     cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
@@ -410,9 +435,10 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
                 return fail(-1, "state dimension too large: one panel column does not fit in shared memory");
             q.cap = cap;
             q.cb = cb_for(cap);
-            q.lv = lp + 8;
+            q.lv = std::max(lp + 8, 256);
             q.ycols = P.m + P.D;
-            h->smem_large = (size_t)(kLargeFixed + cap) * sizeof(double);
+            // (the two TMA stages of the trailing phases live in the panel buffer: 2 x 16 x 242 doubles, 128-byte aligned)
+            h->smem_large = (size_t)(kLargeFixed + std::max(cap, 2 * kTmaStage + 16)) * sizeof(double);
             P.ldm = 0;
             CU(cudaFuncSetAttribute(k_run_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_large));
             CU(cudaFuncSetAttribute(k_init_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_large));
@@ -452,6 +478,8 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
             if ((rc = dev_alloc(h, &P.S, (size_t)P.m * P.m))) return rc;
             if ((rc = dev_alloc(h, &q.Vg, (size_t)kNB * q.lv))) return rc;
             if ((rc = dev_alloc(h, &q.Tg, (size_t)kNB * kLdr))) return rc;
+            for (int i = 0; i < kTmaBoxes; ++i)
+                if ((rc = make_reflector_tensor_map(&q.tmapV[i], q.Vg, q.lv, large_box_pitch(i)))) return rc;
             if ((rc = dev_alloc(h, &q.Yp, (size_t)(maxlen / 64 + 2) * q.ycols * kNB))) return rc;
             if ((rc = dev_alloc(h, &q.vec, (size_t)P.D + 3 * (size_t)P.m + P.dd + 8))) return rc;
             if ((rc = dev_alloc(h, &q.Ld, (size_t)P.m))) return rc;

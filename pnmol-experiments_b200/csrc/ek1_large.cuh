@@ -192,10 +192,13 @@ static __device__ void update_stage_large(cg::grid_group& grid, const Problem& P
 }
 
 #if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_LARGE_RUN)
-__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const Problem P, const RunArgs a, const LargeQR q) {
+__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const Problem P, const RunArgs a, const __grid_constant__ LargeQR q) {
     extern __shared__ __align__(16) double smem_raw[];
     cg::grid_group grid = cg::this_grid();
-    const LargeSmem ls = carve_large(smem_raw);
+    LargeSmem ls = carve_large(smem_raw);
+    __shared__ __align__(8) unsigned long long tma_bars[2];
+    __shared__ unsigned tma_nload;
+    large_init_barriers(ls, tma_bars, &tma_nload);
     const Smem sm = large_vectors(P, q, ls);
     __shared__ double diff_s;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -280,15 +283,18 @@ __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const 
     }
 }
 #else
-__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const Problem P, const RunArgs a, const LargeQR q);
+__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const Problem P, const RunArgs a, const __grid_constant__ LargeQR q);
 #endif
 
 // initialize() (white.py:12-80, latent.py:20-134) on the grid.
 #if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_LARGE_INIT)
-__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_init_large(const Problem P, const InitArgs a, const LargeQR q) {
+__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_init_large(const Problem P, const InitArgs a, const __grid_constant__ LargeQR q) {
     extern __shared__ __align__(16) double smem_raw[];
     cg::grid_group grid = cg::this_grid();
-    const LargeSmem ls = carve_large(smem_raw);
+    LargeSmem ls = carve_large(smem_raw);
+    __shared__ __align__(8) unsigned long long tma_bars[2];
+    __shared__ unsigned tma_nload;
+    large_init_barriers(ls, tma_bars, &tma_nload);
     const Smem sm = large_vectors(P, q, ls);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gw = blockIdx.x * kWarps + warp, gnw = gridDim.x * kWarps;
@@ -343,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_init_large(const
     }
 }
 #else
-__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_init_large(const Problem P, const InitArgs a, const LargeQR q);
+__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_init_large(const Problem P, const InitArgs a, const __grid_constant__ LargeQR q);
 #endif
 
 }  // namespace pnmol

@@ -19,12 +19,18 @@
 //     --  grid barrier
 #pragma once
 #include <cooperative_groups.h>
+#include <cuda.h>
 
 namespace pnmol {
 
 namespace cg = cooperative_groups;
 
-struct LargeQR {   // global scratch of the multi-CTA path (one set per handle)
+constexpr int kTmaBoxes = 3;                         // tensor maps of the reflector buffer: boxes of 82 / 130 / 242 rows x kNB
+__host__ __device__ constexpr int large_box_pitch(int i) { return i == 0 ? 82 : i == 1 ? 130 : 242; }   // = 2 (mod 16)
+constexpr int kTmaStage = kNB * 242;                 // doubles per TMA stage (30976 bytes)
+
+struct LargeQR {   // global scratch of the multi-CTA path (one set per handle); passed as a __grid_constant__ parameter
+    alignas(64) CUtensorMap tmapV[kTmaBoxes];  // 2-D tensor maps of Vg: dim0 = compact row (lv), dim1 = reflector
     double* Vg;    // [kNB][lv]  reflectors of the current panel
     double* Tg;    // [kNB][kLdr] T factor of the current panel
     double* Yp;    // [row chunk][ycols][kNB] partial Y^T
@@ -37,7 +43,47 @@ struct LargeQR {   // global scratch of the multi-CTA path (one set per handle)
 
 struct LargeSmem {
     double *red, *pv, *pinv, *sc, *Ts, *Gs, *scratch, *PB;
+    unsigned long long* bars;   // two mbarriers of the TMA stages (initialised once per kernel)
+    unsigned* nload;            // TMA loads issued so far by this CTA (stage and phase parity of the next one)
 };
+
+// ---------------------------------------------------------------- TMA / mbarrier helpers
+__device__ __forceinline__ unsigned large_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void large_tma_load(double* dst, const CUtensorMap* tmap, int x, int y, unsigned long long* bar, unsigned bytes) {
+    const unsigned b = large_smem_u32(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                 ::"r"(large_smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(b) : "memory");
+}
+__device__ __forceinline__ void large_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned b = large_smem_u32(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(b), "r"(parity) : "memory");
+}
+// Once per kernel: the two mbarriers and the load counter.
+__device__ __forceinline__ void large_init_barriers(LargeSmem& ls, unsigned long long* bars, unsigned* nload) {
+    ls.bars = bars;
+    ls.nload = nload;
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < 2; ++j)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(large_smem_u32(&bars[j])) : "memory");
+        *nload = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+}
+// Which tensor map serves chunks of RC rows (RC <= 240), and the two stage buffers (128-byte aligned) in the panel buffer.
+__device__ __forceinline__ int large_box_index(int RC) { return RC + 2 <= 82 ? 0 : RC + 2 <= 130 ? 1 : 2; }
+__device__ __forceinline__ double* large_stage(const LargeSmem& ls, int i) {
+    return reinterpret_cast<double*>((reinterpret_cast<size_t>(ls.PB) + 127) & ~(size_t)127) + (size_t)i * kTmaStage;
+}
 constexpr int kLargeFixed = 16 + 2 * kMaxN + 80 + 288 + 272 + kWarps * 192;
 
 __device__ __forceinline__ LargeSmem carve_large(double* base) {
@@ -450,73 +496,97 @@ static __device__ void large_panel_factor_cluster(cg::cluster_group& cluster, do
     }
 }
 
-// S2: partial Y^T = C^T V per (row chunk, column group) item.
+// S2: partial Y^T = C^T V per (row chunk, column group) item.  The item's chunk of the reflectors (RC rows x kNB) is
+// staged in shared memory by TMA (cp.async.bulk.tensor.2d, reflector-major, pitch = 2 mod 16) into one of two stages:
+// the load of the CTA's next item is in flight while the tensor cores work on the current one.
 static __device__ void large_trailing_y(const double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
-                                 const LargeQR& q, int RC, double* __restrict__ Vr) {
+                                 const LargeQR& q, int RC, const LargeSmem& ls) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int first = j0 + nbk, ntrail = ncols - first, L = rm.len;
     const int ncg = (ntrail + 63) >> 6, nrc = (L + RC - 1) / RC;
-    for (int it = blockIdx.x; it < nrc * ncg; it += gridDim.x) {
+    const int nitems = nrc * ncg;
+    const int bi = large_box_index(RC), pitch = large_box_pitch(bi);
+    const unsigned bytes = (unsigned)(kNB * pitch * sizeof(double));
+    const CUtensorMap* tmap = &q.tmapV[bi];
+    unsigned n = *ls.nload;
+    __syncthreads();
+    if (tid == 0 && (int)blockIdx.x < nitems) {
+        asm volatile("fence.proxy.async;\n" ::: "memory");  // the panel team wrote the reflectors through the generic proxy
+        large_tma_load(large_stage(ls, n & 1), tmap, ((int)blockIdx.x / ncg) * RC, 0, &ls.bars[n & 1], bytes);
+    }
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
         const int rcx = it / ncg, cgx = it - rcx * ncg;
         const int c0 = rcx * RC;
         const int rows = L - c0 < RC ? L - c0 : RC;
         const int nt8 = (rows + 7) >> 3;
-        __syncthreads();
-        for (int idx = tid; idx < kNB * 8 * nt8; idx += kThreads) {
-            const int refl = idx / (8 * nt8), cl = idx - refl * (8 * nt8);
-            Vr[cl * kLdr + refl] = cl < rows ? q.Vg[(size_t)refl * q.lv + c0 + cl] : 0.0;
-        }
-        __syncthreads();
+        const int nxt = it + (int)gridDim.x;
+        if (tid == 0 && nxt < nitems)
+            large_tma_load(large_stage(ls, (n + 1) & 1), tmap, (nxt / ncg) * RC, 0, &ls.bars[(n + 1) & 1], bytes);
+        const double* Vt = large_stage(ls, n & 1);
+        large_mbar_wait(&ls.bars[n & 1], (n >> 1) & 1);
         const int cbase = (cgx * 8 + warp) * 8;
-        if (cbase >= ntrail) continue;
-        const int cidx = cbase + g;
-        const bool have = cidx < ntrail;
-        const double* cp = W + (size_t)(first + (have ? cidx : cbase)) * ld;
-        double y[2][2][2];
+        if (cbase < ntrail) {
+            const int cidx = cbase + g;
+            const bool have = cidx < ntrail;
+            const double* cp = W + (size_t)(first + (have ? cidx : cbase)) * ld;
+            double y[2][2][2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
+            for (int e = 0; e < 2; ++e)
 #pragma unroll
-            for (int n = 0; n < 2; ++n) { y[e][n][0] = 0.0; y[e][n][1] = 0.0; }
-        for (int i0 = 0; i0 < nt8; i0 += kCh) {
-            double xa[kCh][2];
+                for (int nn = 0; nn < 2; ++nn) { y[e][nn][0] = 0.0; y[e][nn][1] = 0.0; }
+            const double* v1 = Vt + (size_t)g * pitch + 2 * t;
+            for (int i0 = 0; i0 < nt8; i0 += kCh) {
+                double xa[kCh][2];
 #pragma unroll
-            for (int a = 0; a < kCh; ++a) {
-                const int cl = 8 * (i0 + a) + 2 * t;
-                xa[a][0] = (have && cl < rows) ? cp[rm.row(c0 + cl)] : 0.0;
-                xa[a][1] = (have && cl + 1 < rows) ? cp[rm.row(c0 + cl + 1)] : 0.0;
+                for (int a = 0; a < kCh; ++a) {
+                    const int cl = 8 * (i0 + a) + 2 * t;
+                    xa[a][0] = (have && cl < rows) ? cp[rm.row(c0 + cl)] : 0.0;
+                    xa[a][1] = (have && cl + 1 < rows) ? cp[rm.row(c0 + cl + 1)] : 0.0;
+                }
+#pragma unroll
+                for (int a = 0; a < kCh; ++a) {
+                    if (i0 + a < nt8) {
+                        const double2 lo = *reinterpret_cast<const double2*>(v1 + 8 * (i0 + a));
+                        const double2 hi = *reinterpret_cast<const double2*>(v1 + 8 * (i0 + a) + (size_t)8 * pitch);
+                        dmma884(y[0][0][0], y[0][0][1], xa[a][0], lo.x);
+                        dmma884(y[0][1][0], y[0][1][1], xa[a][0], hi.x);
+                        dmma884(y[1][0][0], y[1][0][1], xa[a][1], lo.y);
+                        dmma884(y[1][1][0], y[1][1][1], xa[a][1], hi.y);
+                    }
+                }
             }
+            if (have) {
+                double* yp = q.Yp + ((size_t)rcx * q.ycols + cidx) * kNB;
 #pragma unroll
-            for (int a = 0; a < kCh; ++a) {
-                if (i0 + a < nt8) {
-                    const double* v0 = Vr + (8 * (i0 + a) + 2 * t) * kLdr + g;
-                    dmma884(y[0][0][0], y[0][0][1], xa[a][0], v0[0]);
-                    dmma884(y[0][1][0], y[0][1][1], xa[a][0], v0[8]);
-                    dmma884(y[1][0][0], y[1][0][1], xa[a][1], v0[kLdr]);
-                    dmma884(y[1][1][0], y[1][1][1], xa[a][1], v0[kLdr + 8]);
+                for (int nn = 0; nn < 2; ++nn) {
+                    yp[8 * nn + 2 * t] = y[0][nn][0] + y[1][nn][0];
+                    yp[8 * nn + 2 * t + 1] = y[0][nn][1] + y[1][nn][1];
                 }
             }
         }
-        if (have) {
-            double* yp = q.Yp + ((size_t)rcx * q.ycols + cidx) * kNB;
-#pragma unroll
-            for (int n = 0; n < 2; ++n) {
-                yp[8 * n + 2 * t] = y[0][n][0] + y[1][n][0];
-                yp[8 * n + 2 * t + 1] = y[0][n][1] + y[1][n][1];
-            }
-        }
+        __syncthreads();  // the stage is free for the load after next
+        ++n;
     }
+    __syncthreads();
+    if (tid == 0) *ls.nload = n;
 }
 
-// S3: C^T -= (Y^T T) V^T on the rows of each item's chunk.
+// S3: C^T -= (Y^T T) V^T on the rows of each item's chunk; the reflector chunk is TMA-staged as in S2.
 static __device__ void large_trailing_u(double* __restrict__ W, int ld, int ncols, int j0, int nbk, const RowMap rm,
-                                 const LargeQR& q, int RC, double* __restrict__ Vs, double* __restrict__ Ts) {
+                                 const LargeQR& q, int RC, const LargeSmem& ls, double* __restrict__ Ts) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int first = j0 + nbk, ntrail = ncols - first, L = rm.len;
     const int ncg = (ntrail + 63) >> 6, nrc = (L + RC - 1) / RC;
-    const int ldt = RC + 2;
+    const int nitems = nrc * ncg;
+    const int bi = large_box_index(RC), pitch = large_box_pitch(bi);
+    const unsigned bytes = (unsigned)(kNB * pitch * sizeof(double));
+    const CUtensorMap* tmap = &q.tmapV[bi];
+    unsigned n = *ls.nload;
     __syncthreads();
+    if (tid == 0 && (int)blockIdx.x < nitems)
+        large_tma_load(large_stage(ls, n & 1), tmap, ((int)blockIdx.x / ncg) * RC, 0, &ls.bars[n & 1], bytes);
     for (int idx = tid; idx < kNB * kLdr; idx += kThreads) Ts[idx] = q.Tg[idx];
     __syncthreads();
     double tf[2][2][2];
@@ -525,69 +595,76 @@ static __device__ void large_trailing_u(double* __restrict__ W, int ld, int ncol
 #pragma unroll
         for (int sx = 0; sx < 2; ++sx)
 #pragma unroll
-            for (int n = 0; n < 2; ++n) tf[h][sx][n] = Ts[(8 * h + 2 * t + sx) * kLdr + g + 8 * n];
-    for (int it = blockIdx.x; it < nrc * ncg; it += gridDim.x) {
+            for (int nn = 0; nn < 2; ++nn) tf[h][sx][nn] = Ts[(8 * h + 2 * t + sx) * kLdr + g + 8 * nn];
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
         const int rcx = it / ncg, cgx = it - rcx * ncg;
         const int c0 = rcx * RC;
         const int rows = L - c0 < RC ? L - c0 : RC;
         const int nt8 = (rows + 7) >> 3;
-        __syncthreads();
-        for (int idx = tid; idx < kNB * 8 * nt8; idx += kThreads) {
-            const int refl = idx / (8 * nt8), cl = idx - refl * (8 * nt8);
-            Vs[refl * ldt + cl] = cl < rows ? q.Vg[(size_t)refl * q.lv + c0 + cl] : 0.0;
-        }
-        __syncthreads();
+        const int nxt = it + (int)gridDim.x;
+        if (tid == 0 && nxt < nitems)
+            large_tma_load(large_stage(ls, (n + 1) & 1), tmap, (nxt / ncg) * RC, 0, &ls.bars[(n + 1) & 1], bytes);
+        const double* Vs = large_stage(ls, n & 1);
         const int cbase = (cgx * 8 + warp) * 8;
-        if (cbase >= ntrail) continue;
+        const bool active = cbase < ntrail;
         const int cidx = cbase + g;
-        const bool have = cidx < ntrail;
-        double* cp = W + (size_t)(first + (have ? cidx : cbase)) * ld;
-        double yt[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // Y^T[col g][reflectors 8n + 2t, 8n + 2t + 1]
-        if (have) {
-            for (int r = 0; r < nrc; ++r) {
-                const double* yp = q.Yp + ((size_t)r * q.ycols + cidx) * kNB;
-#pragma unroll
-                for (int n = 0; n < 2; ++n) { yt[n][0] += yp[8 * n + 2 * t]; yt[n][1] += yp[8 * n + 2 * t + 1]; }
-            }
-        }
+        const bool have = active && cidx < ntrail;
+        double* cp = W + (size_t)(first + (have ? cidx : (active ? cbase : 0))) * ld;
         double z[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        if (active) {  // (sums of the partial products while the reflector chunk is in flight)
+            double yt[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // Y^T[col g][reflectors 8n + 2t, 8n + 2t + 1]
+            if (have) {
+                for (int r = 0; r < nrc; ++r) {
+                    const double* yp = q.Yp + ((size_t)r * q.ycols + cidx) * kNB;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int sx = 0; sx < 2; ++sx)
-#pragma unroll
-                for (int n = 0; n < 2; ++n) dmma884(z[n][0], z[n][1], yt[h][sx], tf[h][sx][n]);
-#pragma unroll
-        for (int n = 0; n < 2; ++n) { z[n][0] = -z[n][0]; z[n][1] = -z[n][1]; }
-        for (int i0 = 0; i0 < nt8; i0 += kCh) {
-            double xa[kCh][2];
-#pragma unroll
-            for (int a = 0; a < kCh; ++a) {
-                const int cl = 8 * (i0 + a) + 2 * t;
-                xa[a][0] = (have && cl < rows) ? cp[rm.row(c0 + cl)] : 0.0;
-                xa[a][1] = (have && cl + 1 < rows) ? cp[rm.row(c0 + cl + 1)] : 0.0;
-            }
-#pragma unroll
-            for (int a = 0; a < kCh; ++a) {
-                if (i0 + a < nt8) {
-                    const double* vb = Vs + 8 * (i0 + a) + g;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int sx = 0; sx < 2; ++sx) dmma884(xa[a][0], xa[a][1], z[h][sx], vb[(8 * h + 2 * t + sx) * ldt]);
+                    for (int nn = 0; nn < 2; ++nn) { yt[nn][0] += yp[8 * nn + 2 * t]; yt[nn][1] += yp[8 * nn + 2 * t + 1]; }
                 }
             }
 #pragma unroll
-            for (int a = 0; a < kCh; ++a) {
-                const int cl = 8 * (i0 + a) + 2 * t;
-                if (have && cl < rows) cp[rm.row(c0 + cl)] = xa[a][0];
-                if (have && cl + 1 < rows) cp[rm.row(c0 + cl + 1)] = xa[a][1];
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int sx = 0; sx < 2; ++sx)
+#pragma unroll
+                    for (int nn = 0; nn < 2; ++nn) dmma884(z[nn][0], z[nn][1], yt[h][sx], tf[h][sx][nn]);
+#pragma unroll
+            for (int nn = 0; nn < 2; ++nn) { z[nn][0] = -z[nn][0]; z[nn][1] = -z[nn][1]; }
+        }
+        large_mbar_wait(&ls.bars[n & 1], (n >> 1) & 1);
+        if (active) {
+            for (int i0 = 0; i0 < nt8; i0 += kCh) {
+                double xa[kCh][2];
+#pragma unroll
+                for (int a = 0; a < kCh; ++a) {
+                    const int cl = 8 * (i0 + a) + 2 * t;
+                    xa[a][0] = (have && cl < rows) ? cp[rm.row(c0 + cl)] : 0.0;
+                    xa[a][1] = (have && cl + 1 < rows) ? cp[rm.row(c0 + cl + 1)] : 0.0;
+                }
+#pragma unroll
+                for (int a = 0; a < kCh; ++a) {
+                    if (i0 + a < nt8) {
+                        const double* vb = Vs + 8 * (i0 + a) + g;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int sx = 0; sx < 2; ++sx) dmma884(xa[a][0], xa[a][1], z[h][sx], vb[(size_t)(8 * h + 2 * t + sx) * pitch]);
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < kCh; ++a) {
+                    const int cl = 8 * (i0 + a) + 2 * t;
+                    if (have && cl < rows) cp[rm.row(c0 + cl)] = xa[a][0];
+                    if (have && cl + 1 < rows) cp[rm.row(c0 + cl + 1)] = xa[a][1];
+                }
             }
         }
+        __syncthreads();  // the stage is free for the load after next
+        ++n;
     }
+    __syncthreads();
+    if (tid == 0) *ls.nload = n;
 }
 
-// Rows per chunk of the trailing phases: about two items per CTA, chunks of 64 .. 1024 rows (multiple of 8).
+// Rows per chunk of the trailing phases: about two items per CTA, chunks of 64 .. 240 rows (multiple of 8; one TMA box).
 __device__ __forceinline__ int large_chunk_rows(int L, int ntrail, int cap) {
     const int ncg = (ntrail + 63) >> 6;
     int want = (2 * (int)gridDim.x + ncg - 1) / ncg;
@@ -595,9 +672,8 @@ __device__ __forceinline__ int large_chunk_rows(int L, int ntrail, int cap) {
     int RC = (L + want - 1) / want;
     RC = (RC + 7) & ~7;
     if (RC < 64) RC = 64;
-    int rcmax = 1024;
-    while (rcmax > 64 && (size_t)rcmax * kLdr > (size_t)cap) rcmax >>= 1;
-    if (RC > rcmax) RC = rcmax;
+    (void)cap;
+    if (RC > 240) RC = 240;
     return RC;
 }
 
@@ -625,11 +701,11 @@ static __device__ void householder_qr_large(cg::grid_group& grid, double* __rest
         const int ntrail = s.ncols - (j0 + nbk);
         if (ntrail > 0) {
             const int RC = large_chunk_rows(rm.len, ntrail, q.cap);
-            large_trailing_y(W, ld, s.ncols, j0, nbk, rm, q, RC, ls.PB);
+            large_trailing_y(W, ld, s.ncols, j0, nbk, rm, q, RC, ls);
             pc.mark(10);
             grid.sync();
             pc.mark(11);
-            large_trailing_u(W, ld, s.ncols, j0, nbk, rm, q, RC, ls.PB, ls.Ts);
+            large_trailing_u(W, ld, s.ncols, j0, nbk, rm, q, RC, ls, ls.Ts);
             pc.mark(12);
             grid.sync();
             pc.mark(13);
