@@ -100,6 +100,8 @@ struct Smem {
     int32_t *te_p, *be_p, *te_pd, *te_u, *be_u;  // shared-memory copies of the QR envelopes (Problem::te_p ...)
     double* Hval; int32_t *Hcol, *Hpt;           // sparse rows of H (m x wh; Hpt = mesh point of an entry) when they fit in
                                                  // shared memory, else nullptr
+    double* tri = nullptr;                       // multi-CTA path: shared-memory scratch of the blocked triangular solves
+                                                 // (2 m + kTriScratch doubles), else nullptr
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -802,6 +804,98 @@ static __device__ void update_build_left(const Problem& P, int b, int mcur, int 
     }
 }
 
+// ---- blocked triangular solves on one CTA (large m: the multi-CTA path), vector in shared memory.
+// Blocks of kTriB unknowns: the off-diagonal part is a matrix-vector product spread over all warps (independent,
+// coalesced loads), the kTriB x kTriB diagonal block is staged in shared memory (leading dimension kTriB + 1) and solved
+// by one warp with register-resident right-hand sides -- instead of one block barrier and one L2 round trip per unknown.
+constexpr int kTriB = 64;
+constexpr int kTriScratch = kTriB * (kTriB + 1) + kTriB;
+
+// Lower-triangular system  L u = v  where row k of L is T + k rs (entries 0..k contiguous; diag != nullptr overrides
+// the diagonal).  v: right-hand side on entry, solution on exit.
+static __device__ void tri_solve_lower_rows(const double* __restrict__ T, size_t rs, const double* __restrict__ diag, int m,
+                                            double* __restrict__ v, double* __restrict__ scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* Bs = scratch;
+    double* part = scratch + kTriB * (kTriB + 1);
+    for (int jb = 0; jb < m; jb += kTriB) {
+        const int nb = m - jb < kTriB ? m - jb : kTriB;
+        for (int r = warp; r < nb; r += kWarps) {  // part[r] = sum_{c < jb} L[jb + r][c] u[c]
+            const double* row = T + (size_t)(jb + r) * rs;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int c = lane;
+            for (; c + 96 < jb; c += 128) {
+                a0 = fma(row[c], v[c], a0); a1 = fma(row[c + 32], v[c + 32], a1);
+                a2 = fma(row[c + 64], v[c + 64], a2); a3 = fma(row[c + 96], v[c + 96], a3);
+            }
+            for (; c < jb; c += 32) a0 = fma(row[c], v[c], a0);
+            const double sum = warp_sum((a0 + a1) + (a2 + a3));
+            if (lane == 0) part[r] = sum;
+        }
+        for (int idx = tid; idx < nb * nb; idx += kThreads) {
+            const int r = idx / nb, c = idx - r * nb;
+            if (c <= r) Bs[r * (kTriB + 1) + c] = (c == r && diag) ? diag[jb + r] : T[(size_t)(jb + r) * rs + jb + c];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int r0 = lane, r1 = lane + 32;
+            double rhs0 = r0 < nb ? v[jb + r0] - part[r0] : 0.0, rhs1 = r1 < nb ? v[jb + r1] - part[r1] : 0.0;
+            for (int k = 0; k < nb; ++k) {
+                const double cand = (k < 32 ? rhs0 : rhs1) / Bs[k * (kTriB + 1) + k];
+                const double uk = __shfl_sync(0xffffffffu, cand, k & 31);
+                if (r0 > k && r0 < nb) rhs0 = fma(-Bs[r0 * (kTriB + 1) + k], uk, rhs0);
+                if (r1 > k && r1 < nb) rhs1 = fma(-Bs[r1 * (kTriB + 1) + k], uk, rhs1);
+                if (lane == (k & 31)) { if (k < 32) rhs0 = uk; else rhs1 = uk; }
+            }
+            if (r0 < nb) v[jb + r0] = rhs0;
+            if (r1 < nb) v[jb + r1] = rhs1;
+        }
+        __syncthreads();
+    }
+}
+
+// Upper-triangular system  R x = v  where column k of R is T + k cs (entries 0..k contiguous).
+static __device__ void tri_solve_upper_cols(const double* __restrict__ T, size_t cs, int m, double* __restrict__ v,
+                                            double* __restrict__ scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* Bs = scratch;
+    for (int jb = ((m - 1) / kTriB) * kTriB; jb >= 0; jb -= kTriB) {
+        const int nb = m - jb < kTriB ? m - jb : kTriB;
+        for (int idx = tid; idx < nb * nb; idx += kThreads) {
+            const int c = idx / nb, r = idx - c * nb;
+            if (r <= c) Bs[r * (kTriB + 1) + c] = T[(size_t)(jb + c) * cs + jb + r];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int r0 = lane, r1 = lane + 32;
+            double rhs0 = r0 < nb ? v[jb + r0] : 0.0, rhs1 = r1 < nb ? v[jb + r1] : 0.0;
+            for (int k = nb - 1; k >= 0; --k) {
+                const double cand = (k < 32 ? rhs0 : rhs1) / Bs[k * (kTriB + 1) + k];
+                const double xk = __shfl_sync(0xffffffffu, cand, k & 31);
+                if (r0 < k) rhs0 = fma(-Bs[r0 * (kTriB + 1) + k], xk, rhs0);
+                if (r1 < k) rhs1 = fma(-Bs[r1 * (kTriB + 1) + k], xk, rhs1);
+                if (lane == (k & 31)) { if (k < 32) rhs0 = xk; else rhs1 = xk; }
+            }
+            if (r0 < nb) v[jb + r0] = rhs0;
+            if (r1 < nb) v[jb + r1] = rhs1;
+        }
+        __syncthreads();
+        for (int c = tid; c < jb; c += kThreads) {  // v[c] -= sum_k R[c][jb + k] x[jb + k]
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int k = 0;
+            for (; k + 3 < nb; k += 4) {
+                a0 = fma(T[(size_t)(jb + k) * cs + c], v[jb + k], a0);
+                a1 = fma(T[(size_t)(jb + k + 1) * cs + c], v[jb + k + 1], a1);
+                a2 = fma(T[(size_t)(jb + k + 2) * cs + c], v[jb + k + 2], a2);
+                a3 = fma(T[(size_t)(jb + k + 3) * cs + c], v[jb + k + 3], a3);
+            }
+            for (; k < nb; ++k) a0 = fma(T[(size_t)(jb + k) * cs + c], v[jb + k], a0);
+            v[c] -= (a0 + a1) + (a2 + a3);
+        }
+        __syncthreads();
+    }
+}
+
 // ---- part 2 (one CTA): R1 = Wl[0:m, 0:m] (upper, column-major).  y = R1^-T z (for the mean),  x = R1^-1 z (quirk Q1,
 // white.py:125 / latent.py:204);  m_new = mp - R2^T y (white.py:123, sqrt.py:72) is left in sm.mp.  Returns the
 // local diffusion x.x / m.
@@ -858,6 +952,18 @@ __device__ double update_solve(const Problem& P, const Smem& sm, int mcur, const
         }
         T::sync();
         diff = sm.red[14];
+    } else if (sm.tri && T::size == kThreads) {
+        // multi-CTA path (large m): blocked solves with the vectors in shared memory
+        double* vy = sm.tri;
+        double* vx = sm.tri + mcur;
+        double* scratch = sm.tri + 2 * mcur;
+        for (int r = tid; r < mcur; r += kThreads) { const double zr = sm.z[r]; vy[r] = zr; vx[r] = zr; }
+        __syncthreads();
+        tri_solve_lower_rows(Wl, (size_t)ld, nullptr, mcur, vy, scratch);   // R1^T y = z: row k of R1^T is column k of R1
+        tri_solve_upper_cols(Wl, (size_t)ld, mcur, vx, scratch);            // R1 x = z
+        double part = 0.0;
+        for (int r = tid; r < mcur; r += kThreads) { sm.y[r] = vy[r]; part = fma(vx[r], vx[r], part); }
+        diff = T::sum(part, sm.red) / mcur;
     } else {
         for (int r = tid; r < mcur; r += T::size) { sm.y[r] = sm.z[r]; sm.xw[r] = sm.z[r]; }
         T::sync();

@@ -21,6 +21,7 @@ __device__ __forceinline__ Smem large_vectors(const Problem& P, const LargeQR& q
     sm.xat = base;
     sm.vbuf = nullptr; sm.Vs = nullptr; sm.xraw = nullptr; sm.Vr = nullptr; sm.msq = nullptr;
     sm.red = ls.red; sm.pv = ls.pv; sm.pinv = ls.pinv; sm.sc = ls.sc; sm.Ts = ls.Ts; sm.Gs = ls.Gs;
+    sm.tri = (size_t)2 * P.m + kTriScratch <= (size_t)q.cap ? ls.PB : nullptr;  // (the panel buffer is idle during the solves)
     return sm;
 }
 
@@ -134,7 +135,15 @@ static __device__ void error_estimate_large(cg::grid_group& grid, const Problem&
         grid.sync();
     }
     if (blockIdx.x == 0) {
-        // forward solve L u = z  (xw <- u), row-oriented dot form
+        // forward solve L u = z  (xw <- u): blocked, vector in shared memory (the panel buffer is free again)
+        if (sm.tri) {
+            double* vu = sm.tri;
+            for (int r = tid; r < m; r += kThreads) vu[r] = sm.z[r];
+            __syncthreads();
+            tri_solve_lower_rows(S, (size_t)m, q.Ld, m, vu, sm.tri + 2 * m);
+            for (int r = tid; r < m; r += kThreads) sm.xw[r] = vu[r];
+            __syncthreads();
+        } else {
         for (int r = tid; r < m; r += kThreads) sm.xw[r] = sm.z[r];
         __syncthreads();
         for (int k = 0; k < m; ++k) {
@@ -145,6 +154,7 @@ static __device__ void error_estimate_large(cg::grid_group& grid, const Problem&
                 if (lane == 0) sm.xw[k] = (sm.xw[k] - acc) / q.Ld[k];
             }
             __syncthreads();
+        }
         }
         double part = 0.0;
         for (int r = tid; r < m; r += kThreads) part = fma(sm.xw[r], sm.xw[r], part);
