@@ -72,63 +72,108 @@ static __device__ void error_estimate_large(cg::grid_group& grid, const Problem&
     grid.sync();
     if (blockIdx.x == 0)
         for (int r = tid; r < m; r += kThreads) sm.y[r] = S[(size_t)r * m + r];  // diag(S) before factorisation
-    // Right-looking blocked Cholesky of the lower triangle (row-major), panels of kCB columns staged in shared memory
-    // (leading dimension kCB + 1): CTA 0 factors the (m - k0) x kCB panel there and writes L back (its diagonal also to
-    // q.Ld), then every CTA stages the panel and applies the rank-kCB update to its share of the rows below.
-    constexpr int kCB = 16;         // widest panel; q.cb (16, 8 or 4) is what fits the panel buffer
-    const int cbw = q.cb, kCL = q.cb + 1;
-    double* Lp = ls.PB;
-    for (int k0 = 0; k0 < m; k0 += cbw) {
-        const int kb = m - k0 < cbw ? m - k0 : cbw;
-        const int pr = m - k0;  // panel rows
-        if (blockIdx.x == 0) {
-            for (int idx = tid; idx < pr * cbw; idx += kThreads) {
-                const int r = idx / cbw, kk = idx - r * cbw;
-                Lp[r * kCL + kk] = (kk < kb && kk <= r) ? S[(size_t)(k0 + r) * m + k0 + kk] : 0.0;
+    // Right-looking blocked Cholesky of the lower triangle (row-major), panels of kCB = 32 columns, no serial panel:
+    //   (1) every CTA factors the kb x kb diagonal block redundantly in its own shared memory (no communication),
+    //   (2) the rows below the block are independent triangular solves  L21[r] = A21[r] L11^-T: one thread per row,
+    //       rows dealt round-robin to the CTAs; CTA 0 writes L11 and the diagonal (q.Ld) back,
+    //   (3) after one grid barrier the trailing matrix is updated in 64 x 64 tiles, one per CTA and round: the tile's
+    //       two row blocks of L21 are staged in shared memory, each thread owns a 4 x 4 micro-tile.
+    constexpr int kCB = 32, kCP = kCB + 1, kTile = 64;
+    double* Bs = ls.PB;                      // [kCB][kCP] diagonal block
+    double* Li = Bs + kCB * kCP;             // [kTile][kCP]
+    double* Lj = Li + kTile * kCP;           // [kTile][kCP]
+    for (int k0 = 0; k0 < m; k0 += kCB) {
+        const int kb = m - k0 < kCB ? m - k0 : kCB;
+        for (int idx = tid; idx < kb * kb; idx += kThreads) {
+            const int r = idx / kb, c = idx - r * kb;
+            if (c <= r) Bs[r * kCP + c] = S[(size_t)(k0 + r) * m + k0 + c];
+        }
+        __syncthreads();
+        for (int kk = 0; kk < kb; ++kk) {
+            const double piv = sqrt(Bs[kk * kCP + kk]);
+            const double rinv = 1.0 / piv;
+            __syncthreads();
+            if (tid >= kk && tid < kb) Bs[tid * kCP + kk] = tid == kk ? piv : Bs[tid * kCP + kk] * rinv;
+            __syncthreads();
+            const int rem = kb - kk - 1;  // B[r][c] -= L[r][kk] L[c][kk],  kk < c <= r
+            for (int idx = tid; idx < rem * rem; idx += kThreads) {
+                const int r = kk + 1 + idx / rem, c = kk + 1 + idx % rem;
+                if (c <= r) Bs[r * kCP + c] = fma(-Bs[r * kCP + kk], Bs[c * kCP + kk], Bs[r * kCP + c]);
             }
             __syncthreads();
-            for (int kk = 0; kk < kb; ++kk) {
-                const double piv = sqrt(Lp[kk * kCL + kk]);
-                const double rinv = 1.0 / piv;
-                __syncthreads();
-                for (int r = kk + tid; r < pr; r += kThreads) Lp[r * kCL + kk] = r == kk ? piv : Lp[r * kCL + kk] * rinv;
-                __syncthreads();
-                const int rem = kb - kk - 1;  // S[r][c] -= L[r][kk] L[c][kk],  c in (kk, kb), r >= c
-                for (int idx = tid; idx < (pr - kk - 1) * rem; idx += kThreads) {
-                    const int r = kk + 1 + idx / rem, c = kk + 1 + idx % rem;
-                    if (c <= r) Lp[r * kCL + c] = fma(-Lp[r * kCL + kk], Lp[c * kCL + kk], Lp[r * kCL + c]);
+        }
+        if (blockIdx.x == 0) {
+            for (int idx = tid; idx < kb * kb; idx += kThreads) {
+                const int r = idx / kb, c = idx - r * kb;
+                if (c <= r) S[(size_t)(k0 + r) * m + k0 + c] = Bs[r * kCP + c];
+            }
+            if (tid < kb) q.Ld[k0 + tid] = Bs[tid * kCP + tid];
+        }
+        const int c0 = k0 + kb;
+        {   // (2) rows below: thread t of CTA b takes row c0 + b + t gridDim.x
+            const int r = c0 + (int)blockIdx.x + tid * (int)gridDim.x;
+            if (r < m) {
+                double* row = S + (size_t)r * m + k0;
+                double x[kCB];
+#pragma unroll
+                for (int j = 0; j < kCB; ++j) x[j] = j < kb ? row[j] : 0.0;
+#pragma unroll
+                for (int j = 0; j < kCB; ++j) {
+                    if (j < kb) {
+                        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                        for (int i = 0; i < j; i += 2) {
+                            a0 = fma(x[i], Bs[j * kCP + i], a0);
+                            if (i + 1 < j) a1 = fma(x[i + 1], Bs[j * kCP + i + 1], a1);
+                        }
+                        x[j] = (x[j] - (a0 + a1)) / Bs[j * kCP + j];
+                    }
                 }
-                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < kCB; ++j)
+                    if (j < kb) row[j] = x[j];
             }
-            for (int idx = tid; idx < pr * cbw; idx += kThreads) {
-                const int r = idx / cbw, kk = idx - r * cbw;
-                if (kk < kb && kk <= r) S[(size_t)(k0 + r) * m + k0 + kk] = Lp[r * kCL + kk];
-            }
-            if (tid < kb) q.Ld[k0 + tid] = Lp[tid * kCL + tid];
         }
         grid.sync();
-        const int c0 = k0 + kb;
-        if (c0 < m) {
-            const int tr = m - c0;  // rows below the panel
-            if (blockIdx.x != 0) {  // (CTA 0 still holds the panel: rows c0.. start at local row kb)
-                for (int idx = tid; idx < tr * cbw; idx += kThreads) {
-                    const int r = idx / cbw, kk = idx - r * cbw;
-                    Lp[(kb + r) * kCL + kk] = kk < kb ? S[(size_t)(c0 + r) * m + k0 + kk] : 0.0;
+        if (c0 < m) {  // (3) S[r][c] -= sum_k L[r][k] L[c][k] for c0 <= c <= r, in 64 x 64 tiles (I >= J)
+            const int nt = (m - c0 + kTile - 1) / kTile;
+            const int ntiles = nt * (nt + 1) / 2;
+            const int ty = tid >> 4, tx = tid & 15;
+            for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+                int I = 0;
+                while ((I + 1) * (I + 2) / 2 <= tl) ++I;
+                const int J = tl - I * (I + 1) / 2;
+                const int r0 = c0 + I * kTile, q0 = c0 + J * kTile;
+                __syncthreads();
+                for (int idx = tid; idx < kTile * kCB; idx += kThreads) {
+                    const int rr = idx / kCB, kk = idx - rr * kCB;
+                    Li[rr * kCP + kk] = (r0 + rr < m && kk < kb) ? S[(size_t)(r0 + rr) * m + k0 + kk] : 0.0;
+                    Lj[rr * kCP + kk] = (q0 + rr < m && kk < kb) ? S[(size_t)(q0 + rr) * m + k0 + kk] : 0.0;
                 }
-            }
-            __syncthreads();
-            for (int r = c0 + gw; r < m; r += gnw) {  // S[r][c] -= sum_k L[r][k] L[c][k],  c0 <= c <= r
-                double lr[kCB];
+                __syncthreads();
+                double acc[4][4];
 #pragma unroll
-                for (int kk = 0; kk < kCB; ++kk) lr[kk] = kk < kb ? Lp[(r - k0) * kCL + kk] : 0.0;  // (zero beyond the panel width)
-                for (int c = c0 + lane; c <= r; c += 32) {
-                    const double* lc = Lp + (c - k0) * kCL;
-                    double a0 = 0.0, a1 = 0.0;
+                for (int u = 0; u < 4; ++u)
 #pragma unroll
-                    for (int kk = 0; kk < kCB; kk += 2) {
-                        if (kk < cbw) { a0 = fma(lr[kk], lc[kk], a0); a1 = fma(lr[kk + 1], lc[kk + 1], a1); }
+                    for (int w = 0; w < 4; ++w) acc[u][w] = 0.0;
+#pragma unroll 4
+                for (int kk = 0; kk < kCB; ++kk) {
+                    double a[4], bb[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { a[u] = Li[(ty + 16 * u) * kCP + kk]; bb[u] = Lj[(tx + 16 * u) * kCP + kk]; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) acc[u][w] = fma(a[u], bb[w], acc[u][w]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + ty + 16 * u;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const int c = q0 + tx + 16 * w;
+                        if (r < m && c <= r) S[(size_t)r * m + c] -= acc[u][w];
                     }
-                    S[(size_t)r * m + c] -= a0 + a1;
                 }
             }
         }
