@@ -176,6 +176,20 @@ int pnmol_b200_run_adaptive(pnmol_b200_handle* h, double t0, double tmax, const 
                             double* diff_sum, double* diff_last, int32_t* num_steps, int32_t* num_attempts,
                             int32_t* status, int flags, void* stream);
 
+/* The same loop with the TRAJECTORY of the accepted states, i.e. solve() with step.Adaptive (src/pnmol/pdefilter.py:75-103,
+ * 192-227) in one launch: slot s of mean_traj dev [max_traj, batch, n, dd] / chol_traj dev [max_traj, batch, D, D] /
+ * t_traj dev [batch, max_traj] receives the state after accepted step s + 1 (unscaled factors).  A member that accepts
+ * more than max_traj steps keeps going and sets status bit 2 (value 4: trajectory truncated; num_steps tells the
+ * capacity a second call needs).  err_last / ref_last dev [batch, d] or NULL: error estimate and reference state of the
+ * last attempted step (the PDEFilterState fields of the final state).  All trajectory pointers NULL = pnmol_b200_run_adaptive. */
+int pnmol_b200_run_adaptive_trajectory(pnmol_b200_handle* h, double t0, double tmax, const double* dt0, double abstol,
+                                       double reltol, double change_min, double change_max, double safety_scale,
+                                       int max_attempts, double* mean, double* chol, double* mean_tmp, double* chol_tmp,
+                                       double* t_out, double* dt_out, double* diff_sum, double* diff_last,
+                                       int32_t* num_steps, int32_t* num_attempts, int32_t* status, double* err_last,
+                                       double* ref_last, double* t_traj, double* mean_traj, double* chol_traj, int max_traj,
+                                       int flags, void* stream);
+
 /* Marginal standard deviations of `count` factors: chol dev [count, D, D] -> std_out dev [count, D / (nu + 1)]
  * (same read-out as above for states that already exist, e.g. the initial state or PDESolution.cov_sqrtm). */
 int pnmol_b200_marginal_std(const double* chol, double* std_out, int D, int num_derivatives, int count, int device,

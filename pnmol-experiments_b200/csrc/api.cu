@@ -636,6 +636,19 @@ int pnmol_b200_run_adaptive(pnmol_b200_handle* h, double t0, double tmax, const 
                             double* chol, double* mean_tmp, double* chol_tmp, double* t_out, double* dt_out,
                             double* diff_sum, double* diff_last, int32_t* num_steps, int32_t* num_attempts,
                             int32_t* status, int flags, void* stream) {
+    return pnmol_b200_run_adaptive_trajectory(h, t0, tmax, dt0, abstol, reltol, change_min, change_max, safety_scale,
+                                              max_attempts, mean, chol, mean_tmp, chol_tmp, t_out, dt_out, diff_sum, diff_last,
+                                              num_steps, num_attempts, status, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                                              flags, stream);
+}
+
+int pnmol_b200_run_adaptive_trajectory(pnmol_b200_handle* h, double t0, double tmax, const double* dt0, double abstol,
+                                       double reltol, double change_min, double change_max, double safety_scale,
+                                       int max_attempts, double* mean, double* chol, double* mean_tmp, double* chol_tmp,
+                                       double* t_out, double* dt_out, double* diff_sum, double* diff_last, int32_t* num_steps,
+                                       int32_t* num_attempts, int32_t* status, double* err_last, double* ref_last,
+                                       double* t_traj, double* mean_traj, double* chol_traj, int max_traj, int flags,
+                                       void* stream) {
     int rc = ensure_ready(h);
     if (rc) return rc;
     if (h->P.latent) return fail(-1, "adaptive steps need an error estimate: white-noise solvers only (src/pnmol/latent.py:217-223)");
@@ -644,6 +657,9 @@ int pnmol_b200_run_adaptive(pnmol_b200_handle* h, double t0, double tmax, const 
         !num_attempts || !status)
         return fail(-1, "null argument");
     if (!(tmax > t0) || max_attempts <= 0) return fail(-1, "invalid time span or attempt limit");
+    if ((mean_traj || chol_traj || t_traj) && (!mean_traj || !chol_traj || !t_traj || max_traj <= 0))
+        return fail(-1, "the trajectory needs t_traj, mean_traj, chol_traj and max_traj > 0");
+    if ((err_last == nullptr) != (ref_last == nullptr)) return fail(-1, "err_last and ref_last go together");
     const Problem& P = h->P;
     if (!h->hs_err) {
         CU(cudaMalloc((void**)&h->hs_err, sizeof(double) * P.batch * P.d));
@@ -654,7 +670,9 @@ int pnmol_b200_run_adaptive(pnmol_b200_handle* h, double t0, double tmax, const 
     a.t0 = t0; a.tmax = tmax; a.abstol = abstol; a.reltol = reltol; a.change_min = change_min; a.change_max = change_max;
     a.safety = safety_scale; a.inv_rate = 1.0 / (double)P.n;  // local convergence rate = num_derivatives + 1 (pdefilter.py:215)
     a.dt0 = dt0; a.mean_a = mean; a.chol_a = chol; a.mean_b = mean_tmp; a.chol_b = chol_tmp;
-    a.err = h->hs_err; a.ref = h->hs_ref; a.t_out = t_out; a.dt_out = dt_out; a.diff_sum = diff_sum; a.diff_last = diff_last;
+    a.err = err_last ? err_last : h->hs_err; a.ref = ref_last ? ref_last : h->hs_ref;
+    a.t_traj = t_traj; a.mean_traj = mean_traj; a.chol_traj = chol_traj; a.max_traj = max_traj;
+    a.t_out = t_out; a.dt_out = dt_out; a.diff_sum = diff_sum; a.diff_last = diff_last;
     a.nsteps = num_steps; a.nattempts = num_attempts; a.status = status; a.max_attempts = max_attempts; a.flags = flags;
     if (h->small) {
         CU(cudaFuncSetAttribute(k_run_adaptive_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_small));

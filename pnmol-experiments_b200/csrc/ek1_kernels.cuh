@@ -156,8 +156,12 @@ struct AdaptiveArgs {
     double *mean_a, *chol_a, *mean_b, *chol_b;   // current state in a; b is the proposal buffer
     double *err, *ref;            // [batch][d] scratch: error estimate and reference state of the proposal
     double *t_out, *dt_out, *diff_sum, *diff_last;   // [batch]
-    int32_t *nsteps, *nattempts, *status;            // [batch]; status: 1 non-finite, 2 attempt limit reached
+    int32_t *nsteps, *nattempts, *status;            // [batch]; status: 1 non-finite, 2 attempt limit reached, 4 trajectory truncated
     int max_attempts, flags;
+    // optional trajectory of the accepted states (solve() with step.Adaptive): slot s = state after accepted step s + 1
+    double *t_traj;                // [batch][max_traj]
+    double *mean_traj, *chol_traj; // [max_traj][batch][D], [max_traj][batch][D * D]
+    int max_traj;
 };
 
 #if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_ADAPTIVE)
@@ -217,6 +221,17 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run_adaptive(const
                 ++nsteps;
                 difflast = diff_s;
                 diffsum += diff_s;
+                if (a.mean_traj) {  // the accepted state joins the trajectory
+                    if (nsteps <= a.max_traj) {
+                        double* mt = a.mean_traj + ((size_t)(nsteps - 1) * P.batch + b) * msz;
+                        double* ct = a.chol_traj + ((size_t)(nsteps - 1) * P.batch + b) * csz;
+                        for (size_t k = tid; k < msz; k += kThreads) mt[k] = mout[k];
+                        for (size_t k = tid; k < csz; k += kThreads) ct[k] = cout[k];
+                        if (tid == 0) a.t_traj[(size_t)b * a.max_traj + nsteps - 1] = t;
+                    } else {
+                        stat |= 4;
+                    }
+                }
                 dt = fmin(suggested, a.tmax - t);
                 if (!(suggested == suggested)) dt = suggested;
             } else {

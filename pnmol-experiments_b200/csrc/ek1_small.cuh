@@ -368,6 +368,17 @@ __global__ void __launch_bounds__(PNMOL_SMALL_THREADS, 1) k_run_adaptive_small(c
                 difflast = diff;
                 diffsum += diff;
                 bad |= badstep;
+                if (a.mean_traj) {  // the accepted state joins the trajectory
+                    if (nsteps <= a.max_traj) {
+                        double* mt = a.mean_traj + ((size_t)(nsteps - 1) * P.batch + b) * msz;
+                        double* ct = a.chol_traj + ((size_t)(nsteps - 1) * P.batch + b) * csz;
+                        for (size_t k = lane; k < msz; k += 32) mt[k] = mout[k];
+                        for (size_t k = lane; k < csz; k += 32) ct[k] = cout[k];
+                        if (lane == 0) a.t_traj[(size_t)b * a.max_traj + nsteps - 1] = t;
+                    } else {
+                        stat |= 4;
+                    }
+                }
             }
             dt = fmin(suggested, a.tmax - t);
             if (!(suggested == suggested)) dt = suggested;

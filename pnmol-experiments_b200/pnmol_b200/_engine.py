@@ -201,21 +201,30 @@ class Engine:
         out["_keepalive"] = (mean_tmp, chol_tmp)
         return out
 
-    def run_adaptive(self, t0, tmax, dt0, rule, mean, chol, *, max_attempts=100000, flags=0):
-        """Adaptive time loop on the device (white-noise solvers, CTA-per-member path): mean/chol are advanced in place
-        from t0 to tmax, every member with its own step sizes.  `rule` is a step.Adaptive; dt0 is [batch]."""
+    def run_adaptive(self, t0, tmax, dt0, rule, mean, chol, *, max_attempts=100000, flags=0, trajectory=0):
+        """Adaptive time loop on the device (white-noise solvers, CTA-per-member and small-state paths): mean/chol are
+        advanced in place from t0 to tmax, every member with its own step sizes.  `rule` is a step.Adaptive; dt0 is
+        [batch].  trajectory = capacity (accepted steps per member) of the optional trajectory output
+        (t_traj [batch, cap], mean_traj [cap, batch, n, dd], chol_traj [cap, batch, D, D]; status bit 4 = truncated)."""
         assert mean.is_contiguous() and chol.is_contiguous()
         dt0 = torch.as_tensor(np.broadcast_to(np.asarray(dt0, dtype=np.float64), (self.batch,)).copy(), device=self.device)
         mean_tmp, chol_tmp = torch.empty_like(mean), torch.empty_like(chol)
         out = dict(t=self._empty(self.batch), dt=self._empty(self.batch), diff_sum=self._empty(self.batch),
                    diff_last=self._empty(self.batch), num_steps=self._empty(self.batch, dtype=torch.int32),
-                   num_attempts=self._empty(self.batch, dtype=torch.int32), status=self._empty(self.batch, dtype=torch.int32))
+                   num_attempts=self._empty(self.batch, dtype=torch.int32), status=self._empty(self.batch, dtype=torch.int32),
+                   err=self._empty(self.batch, self.d), ref=self._empty(self.batch, self.d))
+        cap = int(trajectory)
+        if cap > 0:
+            out.update(t_traj=self._empty(self.batch, cap), mean_traj=self._empty(cap, self.batch, self.n, self.dd),
+                       chol_traj=self._empty(cap, self.batch, self.D, self.D))
         small, large = rule.max_changes
-        _lib.check(self.lib.pnmol_b200_run_adaptive(
+        _lib.check(self.lib.pnmol_b200_run_adaptive_trajectory(
             self.h, float(t0), float(tmax), _lib.ptr(dt0), float(rule.abstol), float(rule.reltol), float(small), float(large),
             float(rule.safety_scale), int(max_attempts), _lib.ptr(mean), _lib.ptr(chol), _lib.ptr(mean_tmp), _lib.ptr(chol_tmp),
             _lib.ptr(out["t"]), _lib.ptr(out["dt"]), _lib.ptr(out["diff_sum"]), _lib.ptr(out["diff_last"]),
-            _lib.ptr(out["num_steps"]), _lib.ptr(out["num_attempts"]), _lib.ptr(out["status"]), int(flags), self._stream()))
+            _lib.ptr(out["num_steps"]), _lib.ptr(out["num_attempts"]), _lib.ptr(out["status"]), _lib.ptr(out["err"]),
+            _lib.ptr(out["ref"]), _lib.ptr(out.get("t_traj")), _lib.ptr(out.get("mean_traj")), _lib.ptr(out.get("chol_traj")),
+            cap, int(flags), self._stream()))
         out["_keepalive"] = (mean_tmp, chol_tmp, dt0)
         return out
 

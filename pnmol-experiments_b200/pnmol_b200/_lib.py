@@ -31,6 +31,8 @@ SIGNATURES = {
     "pnmol_b200_run_marginals": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_int] + [c_void_p] * 9 + [c_int, c_void_p]),
     "pnmol_b200_run_adaptive": (c_int, [c_void_p, c_double, c_double, c_void_p, c_double, c_double, c_double, c_double, c_double,
                                         c_int] + [c_void_p] * 11 + [c_int, c_void_p]),
+    "pnmol_b200_run_adaptive_trajectory": (c_int, [c_void_p, c_double, c_double, c_void_p, c_double, c_double, c_double, c_double,
+                                                   c_double, c_int] + [c_void_p] * 16 + [c_int, c_int, c_void_p]),
     "pnmol_b200_marginal_std": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "pnmol_b200_rescale": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "pnmol_b200_simulate_final_state_host": (c_int, [c_void_p, c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p,

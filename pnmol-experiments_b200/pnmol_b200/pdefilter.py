@@ -65,6 +65,10 @@ class PDEFilter(ABC):
         """pdefilter.py:75-103."""
         if self._persistent_ok(stop_at, progressbar):
             return self._solve_persistent(pde)
+        if self._device_adaptive_ok(stop_at, progressbar):
+            state0 = self.initialize(pde)
+            if self._engine.path in ("single_cta", "small"):
+                return self._solve_adaptive_device(pde, state0)
         means, covs, times, diffs, info = [], [], [], [], dict()
         for state, info in self.solution_generator(pde, stop_at=stop_at, progressbar=progressbar):
             times.append(state.t)
@@ -99,8 +103,7 @@ class PDEFilter(ABC):
             return PDEFilterState(t=t, y=y, error_estimate=out["err"][0] if white else None,
                                   reference_state=out["ref"][0] if white else None,
                                   diffusion_squared_local=out["diff_last"][0]), info
-        if (isinstance(self.steprule, step.Adaptive) and self.family == "white" and stop_at is None and not progressbar
-                and os.environ.get("PNMOL_B200_HOST_ADAPTIVE") != "1"):
+        if self._device_adaptive_ok(stop_at, progressbar):
             state0 = self.initialize(pde)
             eng = self._engine
             if eng.path in ("single_cta", "small"):  # accept/reject and the step-size proposal run inside one kernel launch
@@ -115,7 +118,7 @@ class PDEFilter(ABC):
                 info = _new_info()
                 info.update(num_f_evaluations=natt, num_df_evaluations=natt, num_steps=nsteps, num_attempted_steps=natt)
                 y = rv.MultivariateNormal(mean[0], _mark_tril(chol[0]))
-                return PDEFilterState(t=float(out["t"][0]), y=y, error_estimate=None, reference_state=None,
+                return PDEFilterState(t=float(out["t"][0]), y=y, error_estimate=out["err"][0], reference_state=out["ref"][0],
                                       diffusion_squared_local=out["diff_last"][0]), info
         state, info, diffs = None, None, []
         for state, info in self.solution_generator(pde, stop_at=stop_at, progressbar=progressbar):
@@ -126,6 +129,35 @@ class PDEFilter(ABC):
         cal = torch.stack([torch.as_tensor(x) for x in diffs]).mean()
         cov_new = state.y.cov_sqrtm * torch.sqrt(cal)
         return state._replace(y=state.y._replace(cov_sqrtm=cov_new)), info
+
+    def _device_adaptive_ok(self, stop_at, progressbar):
+        """Accept/reject, step-size control and (for solve) the trajectory of accepted states run inside ONE kernel launch
+        for the white-noise solvers (the latent-force solvers have no error estimate, latent.py:217-223)."""
+        return (isinstance(self.steprule, step.Adaptive) and self.family == "white" and stop_at is None and not progressbar
+                and os.environ.get("PNMOL_B200_HOST_ADAPTIVE") != "1")
+
+    def _solve_adaptive_device(self, pde, state0, capacity=64):
+        """solve() with step.Adaptive (pdefilter.py:75-103, 192-227) in one launch: the kernel appends every accepted state
+        to a trajectory buffer; if a solve accepts more steps than the buffer holds, it is repeated once with the exact
+        capacity (the step count is known then)."""
+        eng = self._engine
+        while True:
+            mean = state0.y.mean[None].clone()
+            chol = state0.y.cov_sqrtm[None].clone()
+            out = eng.run_adaptive(pde.t0, pde.tmax, self.steprule.first_dt(pde), self.steprule, mean, chol, trajectory=capacity)
+            status = int(out["status"][0])
+            if status & 2:
+                raise RuntimeError("adaptive time loop: attempt limit reached before tmax")
+            nsteps, natt = int(out["num_steps"][0]), int(out["num_attempts"][0])
+            if not (status & 4):
+                break
+            capacity = nsteps
+        info = _new_info()
+        info.update(num_f_evaluations=natt, num_df_evaluations=natt, num_steps=nsteps, num_attempted_steps=natt)
+        ts = np.concatenate([[pde.t0], out["t_traj"][0, :nsteps].cpu().numpy()])
+        means = torch.cat([state0.y.mean[None], out["mean_traj"][:nsteps, 0]])
+        covs = torch.cat([state0.y.cov_sqrtm[None], out["chol_traj"][:nsteps, 0]])
+        return PDESolution(t=ts, mean=means, cov_sqrtm=covs, info=info, diffusion_squared_calibrated=out["diff_sum"][0] / nsteps)
 
     def _solve_persistent(self, pde):
         state0 = self.initialize(pde)

@@ -289,6 +289,49 @@ def test_adaptive_time_loop_on_device(monkeypatch):
     assert launches_device < launches_host and launches_device <= 4  # gram, init, adaptive loop, rescale
 
 
+@pytest.mark.parametrize("num,path", [(9, "cta"), (6, "small")])
+def test_adaptive_solve_trajectory_on_device(num, path, monkeypatch):
+    """solve() with step.Adaptive (src/pnmol/pdefilter.py:75-103, 192-227) in ONE launch: the kernel appends every accepted
+    state to a trajectory buffer (a too small buffer triggers one exact-size repetition).  Same accepted times, step
+    counts, states and calibrated diffusion as the host loop over attempt_step; the final state's error estimate and
+    reference state equal those of the host loop's last accepted step."""
+    from pnmol_b200 import _lib, white
+    from pnmol_b200.odetools import step
+
+    monkeypatch.setenv("PNMOL_B200_PATH", path)
+    case = cases.make_case("heat", num=num, bcond="neumann", tmax=0.5)
+    rule = dict(abstol=1e-3, reltol=1e-2)
+    mk = lambda: white.LinearWhiteNoiseEK1(num_derivatives=2, steprule=step.Adaptive(**rule), spatial_kernel=case["kernel"])
+    n0 = _lib.launch_count()
+    sol = mk().solve(case["pde"])
+    launches_device = _lib.launch_count() - n0
+    solver_small_buffer = mk()
+    state0 = solver_small_buffer.initialize(case["pde"])
+    sol_small = solver_small_buffer._solve_adaptive_device(case["pde"], state0, capacity=2)   # forces the exact-size repetition
+    final, _ = mk().simulate_final_state(case["pde"])
+    monkeypatch.setenv("PNMOL_B200_HOST_ADAPTIVE", "1")
+    n0 = _lib.launch_count()
+    host_solver = mk()
+    sol_h = host_solver.solve(case["pde"])
+    launches_host = _lib.launch_count() - n0
+    last = None
+    for last, _info in mk().solution_generator(case["pde"]):
+        pass
+    assert sol.info == sol_h.info and sol.info["num_steps"] >= 3 and len(sol.t) == sol.info["num_steps"] + 1
+    # (accepted times: the step-size proposal uses pow() -- CUDA's and the host's differ in the last place; the end is exact)
+    assert np.allclose(sol.t, sol_h.t, rtol=1e-12, atol=0.0) and sol.t[-1] == sol_h.t[-1] and np.array_equal(sol_small.t, sol.t)
+    assert sol.mean.shape == sol_h.mean.shape and sol.cov_sqrtm.shape == sol_h.cov_sqrtm.shape
+    for k in range(len(sol.t)):
+        assert torch.allclose(sol.mean[k], sol_h.mean[k], rtol=1e-9, atol=1e-14)
+        assert cases.cov_excess(_np(sol.cov_sqrtm[k]), _np(sol_h.cov_sqrtm[k]), 3) < 1
+    assert torch.equal(sol_small.mean, sol.mean) and torch.equal(sol_small.cov_sqrtm, sol.cov_sqrtm)
+    assert float(sol.diffusion_squared_calibrated) == pytest.approx(float(sol_h.diffusion_squared_calibrated), rel=1e-6)
+    assert launches_device < launches_host and launches_device <= 3   # gram, init, adaptive loop with trajectory
+    # PDEFilterState fields of the final state (ADVICE r1: they were None on the device route)
+    assert torch.allclose(final.error_estimate, last.error_estimate, rtol=1e-6, atol=1e-300)
+    assert torch.allclose(final.reference_state, last.reference_state, rtol=1e-9, atol=1e-15)
+
+
 def test_adaptive_ensemble_per_member_steps():
     """Members with different diffusivities take different numbers of steps inside the same launch and match their
     individual oracle solves."""
