@@ -165,7 +165,7 @@ int pnmol_b200_run_marginals(pnmol_b200_handle* h, double t0, const double* dts,
 /* Adaptive time loop on the device: solution_generator + perform_full_step with
  * step.Adaptive (src/pnmol/pdefilter.py:118-227, src/pnmol/odetools/step.py:58-119) for every member, each with its own
  * step size; accept/reject, the step-size proposal and the Nordsieck preconditioner are evaluated in the kernel.
- * White-noise solvers on the CTA-per-member path only (-4 otherwise: use pnmol_b200_step from a host loop).
+ * White-noise solvers (the latent-force solvers have no error estimate); all three kernel families.
  *   dt0 dev [batch] first step (Adaptive.first_dt), mean/chol dev: state at t0 in, state at tmax out (unscaled factor;
  *   pnmol_b200_rescale applies the calibration with nsteps = num_steps), *_tmp scratch of the same shapes,
  *   t_out/dt_out/diff_sum/diff_last dev [batch], num_steps/num_attempts/status dev int32 [batch]

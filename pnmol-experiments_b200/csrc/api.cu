@@ -483,7 +483,7 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
             if ((rc = dev_alloc(h, &q.Yp, (size_t)(maxlen / 64 + 2) * q.ycols * kNB))) return rc;
             if ((rc = dev_alloc(h, &q.vec, (size_t)P.D + 3 * (size_t)P.m + P.dd + 8))) return rc;
             if ((rc = dev_alloc(h, &q.Ld, (size_t)P.m))) return rc;
-            if ((rc = dev_alloc(h, &q.nf, 1))) return rc;
+            if ((rc = dev_alloc(h, &q.nf, 2))) return rc;   // (two words: the adaptive loop alternates by attempt parity)
             CU(cudaMemset(P.W, 0, wsz * sizeof(double)));
             CU(cudaMemset(q.Vg, 0, (size_t)kNB * q.lv * sizeof(double)));
             h->have_op = true;
@@ -652,7 +652,6 @@ int pnmol_b200_run_adaptive_trajectory(pnmol_b200_handle* h, double t0, double t
     int rc = ensure_ready(h);
     if (rc) return rc;
     if (h->P.latent) return fail(-1, "adaptive steps need an error estimate: white-noise solvers only (src/pnmol/latent.py:217-223)");
-    if (h->large) return fail(-4, "the on-device adaptive loop is served by the CTA-per-member kernels only");
     if (!dt0 || !mean || !chol || !mean_tmp || !chol_tmp || !t_out || !dt_out || !diff_sum || !diff_last || !num_steps ||
         !num_attempts || !status)
         return fail(-1, "null argument");
@@ -674,7 +673,12 @@ int pnmol_b200_run_adaptive_trajectory(pnmol_b200_handle* h, double t0, double t
     a.t_traj = t_traj; a.mean_traj = mean_traj; a.chol_traj = chol_traj; a.max_traj = max_traj;
     a.t_out = t_out; a.dt_out = dt_out; a.diff_sum = diff_sum; a.diff_last = diff_last;
     a.nsteps = num_steps; a.nattempts = num_attempts; a.status = status; a.max_attempts = max_attempts; a.flags = flags;
-    if (h->small) {
+    if (h->large) {
+        CU(cudaFuncSetAttribute(k_run_adaptive_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_large));
+        if (h->cluster > 1) CU(cudaFuncSetAttribute(k_run_adaptive_large, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        int rc2 = launch_large(h, k_run_adaptive_large, a, (cudaStream_t)stream);
+        if (rc2) return rc2;
+    } else if (h->small) {
         CU(cudaFuncSetAttribute(k_run_adaptive_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_small));
         k_run_adaptive_small<<<h->grid, 32 * h->sgeo.nwarps, h->smem_small, (cudaStream_t)stream>>>(h->P, a, h->sgeo);
     } else {

@@ -214,7 +214,8 @@ static __device__ void error_estimate_large(cg::grid_group& grid, const Problem&
 static __device__ void update_stage_large(cg::grid_group& grid, const Problem& P, int b, const Smem& sm, const LargeQR& q,
                                    const LargeSmem& ls, int mcur, EMode emode, double nugget, const double* Rsrc,
                                    const int32_t* te, const int32_t* be, const int32_t* Hcol, const double* Hval, double* W,
-                                   const UpdateOut out, double* diff_cta0, PhaseClock& pc) {
+                                   const UpdateOut out, double* diff_cta0, PhaseClock& pc, int32_t* nf = nullptr) {
+    if (!nf) nf = q.nf;
     const int warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * kWarps + warp, gnw = gridDim.x * kWarps;
     const int D = P.D, ld = P.ld;
@@ -241,9 +242,49 @@ static __device__ void update_stage_large(cg::grid_group& grid, const Problem& P
     }
     pc.mark(6);
     bad |= update_output_factor(P, sm, out, mcur, nrows, Wr, gw, gnw);
-    if (bad) atomicOr(q.nf, 1);
+    if (bad) atomicOr(nf, 1);
     grid.sync();
     pc.mark(7);
+}
+
+// One EK1 step of member b on the grid (white.py:96-146 / latent.py:167-223): predict mean + linearisation on CTA 0,
+// predict-stack build, QR, error estimate, update.  ls.pv / ls.pinv hold the Nordsieck preconditioner of dt.  Ends with a
+// grid barrier; *diff_cta0 (shared memory of CTA 0) receives the local diffusion.
+static __device__ void ek1_step_large(cg::grid_group& grid, const Problem& P, int b, const Smem& sm, const LargeQR& q,
+                                      const LargeSmem& ls, double dt, const double* min_, const double* cin_, double* mout,
+                                      double* cout, double* err_out, double* ref_out, int flags, double* diff_cta0,
+                                      PhaseClock& pc, int32_t* nf = nullptr) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int gw = blockIdx.x * kWarps + warp, gnw = gridDim.x * kWarps;
+    const int n = P.n, D = P.D;
+    double* W = P.W;
+    // [predict mean + linearisation] on CTA 0   white.py:104-113
+    if (blockIdx.x == 0) {
+        for (int k = tid; k < D; k += kThreads) {
+            const int j = k / n, i = k - j * n;
+            double acc = 0.0;
+            for (int r = 0; r < n; ++r) acc = fma(P.A1d[i * n + r], ls.pinv[r] * min_[(size_t)r * P.dd + j], acc);
+            sm.mp[k] = acc;
+        }
+        __syncthreads();
+        evaluate_ode(P, b, sm, ls.pv[0], ls.pv[1], P.Hcol, P.Hval);
+    }
+    const bool dense = flags & 1;
+    pc.mark(0);
+    build_predict(P, b, sm, cin_, dense ? P.te_pd : P.te_p, W + (size_t)P.m * P.ld, gw, gnw);
+    grid.sync();
+    pc.mark(1);
+    Shape sp;
+    sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p;
+    householder_qr_large(grid, W + (size_t)P.m * P.ld, P.ld, sp, q, ls, pc);
+    if (!P.latent && !(flags & 2))
+        error_estimate_large(grid, P, b, sm, q, ls, ls.pv[1], dt, E_STEP_WHITE, P.Hcol, P.Hval, P.F, P.S, err_out);
+    pc.mark(3);
+    UpdateOut out;
+    out.mean_out = mout; out.chol_out = cout; out.diff_out = nullptr;
+    out.ref_out = P.latent ? nullptr : ref_out; out.scale_by_p = true;
+    update_stage_large(grid, P, b, sm, q, ls, P.m, P.latent ? E_NONE : E_STEP_WHITE, 0.0, nullptr, P.te_u, P.be_u,
+                       P.Hcol, P.Hval, W, out, diff_cta0, pc, nf);
 }
 
 #if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_LARGE_RUN)
@@ -284,34 +325,8 @@ __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const 
             double* mout = (even ? a.mean_b : a.mean_a) + b * msz;
             double* cout = (even ? a.chol_b : a.chol_a) + b * csz;
             const int flags = s == 0 ? a.flags : (a.flags & ~1);
-            // [predict mean + linearisation] on CTA 0   white.py:104-113
-            if (blockIdx.x == 0) {
-                for (int k = tid; k < D; k += kThreads) {
-                    const int j = k / n, i = k - j * n;
-                    double acc = 0.0;
-                    for (int r = 0; r < n; ++r) acc = fma(P.A1d[i * n + r], ls.pinv[r] * min_[(size_t)r * P.dd + j], acc);
-                    sm.mp[k] = acc;
-                }
-                __syncthreads();
-                evaluate_ode(P, b, sm, ls.pv[0], ls.pv[1], P.Hcol, P.Hval);
-            }
-            const bool dense = flags & 1;
-            pc.mark(0);
-            build_predict(P, b, sm, cin_, dense ? P.te_pd : P.te_p, W + (size_t)P.m * P.ld, gw, gnw);
-            grid.sync();
-            pc.mark(1);
-            Shape sp;
-            sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p;
-            householder_qr_large(grid, W + (size_t)P.m * P.ld, P.ld, sp, q, ls, pc);
-            if (!P.latent && !(flags & 2))
-                error_estimate_large(grid, P, b, sm, q, ls, ls.pv[1], dt, E_STEP_WHITE, P.Hcol, P.Hval, P.F, P.S,
-                                     a.err_out ? a.err_out + (size_t)b * P.d : nullptr);
-            pc.mark(3);
-            UpdateOut out;
-            out.mean_out = mout; out.chol_out = cout; out.diff_out = nullptr;
-            out.ref_out = (P.latent || !a.ref_out) ? nullptr : a.ref_out + (size_t)b * P.d; out.scale_by_p = true;
-            update_stage_large(grid, P, b, sm, q, ls, P.m, P.latent ? E_NONE : E_STEP_WHITE, 0.0, nullptr, P.te_u, P.be_u,
-                               P.Hcol, P.Hval, W, out, &diff_s, pc);
+            ek1_step_large(grid, P, b, sm, q, ls, dt, min_, cin_, mout, cout, a.err_out ? a.err_out + (size_t)b * P.d : nullptr,
+                           a.ref_out ? a.ref_out + (size_t)b * P.d : nullptr, flags, &diff_s, pc);
             if (blockIdx.x == 0) { __syncthreads(); diffsum += diff_s; }
             if (a.mean_traj) {
                 double* mt = a.mean_traj + ((size_t)s * P.batch + b) * msz;
@@ -339,6 +354,110 @@ __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const 
 }
 #else
 __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const Problem P, const RunArgs a, const __grid_constant__ LargeQR q);
+#endif
+
+// Adaptive time loop on the grid (src/pnmol/pdefilter.py:192-227, src/pnmol/odetools/step.py:58-119) for the multi-CTA
+// path: one member at a time, every CTA evaluates the scaled error norm and the step-size proposal redundantly from
+// the error estimate / reference state that the step left in global memory (same summation order everywhere, so all
+// CTAs take the same branch -- no broadcast).  The non-finite flag alternates between two words by attempt parity, so
+// that a rejected non-finite proposal can be forgotten without another grid barrier.
+#if defined(PNMOL_TU_ALL) || defined(PNMOL_TU_LARGE_ADAPTIVE)
+__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_adaptive_large(const Problem P, const AdaptiveArgs a, const __grid_constant__ LargeQR q) {
+    extern __shared__ __align__(16) double smem_raw[];
+    cg::grid_group grid = cg::this_grid();
+    LargeSmem ls = carve_large(smem_raw);
+    __shared__ __align__(8) unsigned long long tma_bars[2];
+    __shared__ unsigned tma_nload;
+    large_init_barriers(ls, tma_bars, &tma_nload);
+    const Smem sm = large_vectors(P, q, ls);
+    __shared__ double diff_s;
+    const int tid = threadIdx.x;
+    const size_t gtid = (size_t)blockIdx.x * kThreads + tid, gnt = (size_t)gridDim.x * kThreads;
+    const int nu = P.n - 1;
+    const size_t msz = (size_t)P.D, csz = (size_t)P.D * P.D;
+    PhaseClock pc;
+    pc.start(nullptr);
+    for (int b = 0; b < P.batch; ++b) {
+        if (blockIdx.x == 0 && tid == 0) { q.nf[0] = 0; q.nf[1] = 0; }
+        grid.sync();
+        double t = a.t0, dt = a.dt0[b], diffsum = 0.0, difflast = 0.0;
+        int nsteps = 0, natt = 0, cur = 0, stat = 0, bad = 0;
+        double* err = a.err + (size_t)b * P.d;
+        double* ref = a.ref + (size_t)b * P.d;
+        while (t < a.tmax) {
+            if (natt >= a.max_attempts) { stat |= 2; break; }
+            if (!(dt >= 0.0)) { stat |= 1; break; }  // pdefilter.py:225 asserts dt >= 0 (a NaN proposal ends here too)
+            __syncthreads();
+            if (tid < P.n) {  // Nordsieck preconditioner p_i = |dt|^(nu - i + 1/2) / (nu - i)!   (iwp.py:55-62)
+                const int k = nu - tid;
+                double fact = 1.0;
+                for (int qq = 2; qq <= k; ++qq) fact *= qq;
+                const double pw = pow(fabs(dt), k + 0.5);
+                ls.pv[tid] = pw / fact;
+                ls.pinv[tid] = fact / pw;
+            }
+            __syncthreads();
+            const double* min_ = (cur ? a.mean_b : a.mean_a) + b * msz;
+            const double* cin_ = (cur ? a.chol_b : a.chol_a) + b * csz;
+            double* mout = (cur ? a.mean_a : a.mean_b) + b * msz;
+            double* cout = (cur ? a.chol_a : a.chol_b) + b * csz;
+            const int flags = (natt == 0 || nsteps == 0) ? a.flags : (a.flags & ~1);
+            int32_t* nf = q.nf + (natt & 1);
+            ek1_step_large(grid, P, b, sm, q, ls, dt, min_, cin_, mout, cout, err, ref, flags, &diff_s, pc, nf);   // ends with a grid barrier
+            const int badstep = __ldcg(nf);
+            if (blockIdx.x == 0 && tid == 0) q.nf[(natt + 1) & 1] = 0;   // the other word serves the next attempt
+            // scaled error norm (step.py:97-108 on dt * error_estimate, pdefilter.py:208-213)
+            double part = 0.0;
+            for (int i = tid; i < P.d; i += kThreads) {
+                const double r = dt * __ldcg(err + i) / (a.abstol + a.reltol * __ldcg(ref + i));
+                part = fma(r, r, part);
+            }
+            const double norm = sqrt(block_sum(part, ls.red)) / sqrt((double)P.d);
+            double change = a.safety * pow(1.0 / norm, a.inv_rate);
+            change = fmax(a.change_min, fmin(change, a.change_max));
+            if (!(norm == norm)) change = norm;  // NaN propagates like jnp.minimum / jnp.maximum
+            const double suggested = change * dt;
+            ++natt;
+            if (norm < 1.0) {  // accepted: the proposal becomes the state
+                t = t + dt;
+                cur ^= 1;
+                ++nsteps;
+                bad |= badstep;
+                if (blockIdx.x == 0) { difflast = diff_s; diffsum += diff_s; }
+                if (a.mean_traj) {
+                    if (nsteps <= a.max_traj) {
+                        double* mt = a.mean_traj + ((size_t)(nsteps - 1) * P.batch + b) * msz;
+                        double* ct = a.chol_traj + ((size_t)(nsteps - 1) * P.batch + b) * csz;
+                        for (size_t k = gtid; k < msz; k += gnt) mt[k] = mout[k];
+                        for (size_t k = gtid; k < csz; k += gnt) ct[k] = cout[k];
+                        if (gtid == 0) a.t_traj[(size_t)b * a.max_traj + nsteps - 1] = t;
+                    } else {
+                        stat |= 4;
+                    }
+                }
+            }
+            dt = fmin(suggested, a.tmax - t);
+            if (!(suggested == suggested)) dt = suggested;
+        }
+        grid.sync();
+        if (cur) {  // bring the final state home
+            const double* ms = a.mean_b + b * msz; const double* cs = a.chol_b + b * csz;
+            double* md = a.mean_a + b * msz; double* cd = a.chol_a + b * csz;
+            for (size_t k = gtid; k < msz; k += gnt) md[k] = ms[k];
+            for (size_t k = gtid; k < csz; k += gnt) cd[k] = cs[k];
+        }
+        if (blockIdx.x == 0 && tid == 0) {
+            a.t_out[b] = t; a.dt_out[b] = dt; a.diff_sum[b] = diffsum; a.diff_last[b] = difflast;
+            a.nsteps[b] = nsteps; a.nattempts[b] = natt; a.status[b] = stat | (bad ? 1 : 0);
+        }
+        if (bad || stat || __ldcg(q.nf) || __ldcg(q.nf + 1)) {  // no NaNs in the workspace for the next member
+            for (size_t k = gtid; k < (size_t)P.ld * (P.m + P.D); k += gnt) P.W[k] = 0.0;
+        }
+        grid.sync();
+    }
+}
+#else
+__global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_adaptive_large(const Problem P, const AdaptiveArgs a, const __grid_constant__ LargeQR q);
 #endif
 
 // initialize() (white.py:12-80, latent.py:20-134) on the grid.

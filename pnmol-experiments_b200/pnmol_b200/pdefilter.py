@@ -67,8 +67,7 @@ class PDEFilter(ABC):
             return self._solve_persistent(pde)
         if self._device_adaptive_ok(stop_at, progressbar):
             state0 = self.initialize(pde)
-            if self._engine.path in ("single_cta", "small"):
-                return self._solve_adaptive_device(pde, state0)
+            return self._solve_adaptive_device(pde, state0)   # (all three kernel families serve the adaptive loop)
         means, covs, times, diffs, info = [], [], [], [], dict()
         for state, info in self.solution_generator(pde, stop_at=stop_at, progressbar=progressbar):
             times.append(state.t)
@@ -106,7 +105,7 @@ class PDEFilter(ABC):
         if self._device_adaptive_ok(stop_at, progressbar):
             state0 = self.initialize(pde)
             eng = self._engine
-            if eng.path in ("single_cta", "small"):  # accept/reject and the step-size proposal run inside one kernel launch
+            if True:  # accept/reject and the step-size proposal run inside one kernel launch (all kernel families)
                 mean = state0.y.mean[None].contiguous()
                 chol = state0.y.cov_sqrtm[None].contiguous()
                 out = eng.run_adaptive(pde.t0, pde.tmax, self.steprule.first_dt(pde), self.steprule, mean, chol)

@@ -289,7 +289,7 @@ def test_adaptive_time_loop_on_device(monkeypatch):
     assert launches_device < launches_host and launches_device <= 4  # gram, init, adaptive loop, rescale
 
 
-@pytest.mark.parametrize("num,path", [(9, "cta"), (6, "small")])
+@pytest.mark.parametrize("num,path", [(9, "cta"), (6, "small"), (9, "large")])
 def test_adaptive_solve_trajectory_on_device(num, path, monkeypatch):
     """solve() with step.Adaptive (src/pnmol/pdefilter.py:75-103, 192-227) in ONE launch: the kernel appends every accepted
     state to a trajectory buffer (a too small buffer triggers one exact-size repetition).  Same accepted times, step
