@@ -169,17 +169,29 @@ def test_quirk_q1_reproducibility_of_the_reference(path):
     assert mean_dev < 1e-5 and mean_dev < 1e-2 * max(cal, loc.max())  # ... which the very same runs reproduce
 
 
+def _family_cases():
+    """(golden file, kernel family): every file on the CTA-per-member and multi-CTA kernels; the small-state kernels keep
+    a member's workspace in one warp's shared memory (D <~ 48), so they get the files with at most 15 mesh points."""
+    out, ids = [], []
+    for path, name in zip(FILES, IDS):
+        small_ok = np.load(path, allow_pickle=False)["L"].shape[0] <= 15
+        for family in ("cta", "large") + (("small",) if small_ok else ()):
+            out.append((path, family))
+            ids.append(f"{name}-{family}")
+    return out, ids
+
+
+_FAMILY_CASES, _FAMILY_IDS = _family_cases()
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("family", ["cta", "large", "small"])
-@pytest.mark.parametrize("path", FILES, ids=IDS)
+@pytest.mark.parametrize("path,family", _FAMILY_CASES, ids=_FAMILY_IDS)
 def test_cuda_path_reproduces_reference_source(path, family, monkeypatch):
     import __graft_entry__
 
     __graft_entry__.ensure_built()
     monkeypatch.setenv("PNMOL_B200_PATH", family)
     g = np.load(path, allow_pickle=False)
-    if family == "small" and g["L"].shape[0] > 15:
-        pytest.skip("the small-state kernels keep a member's workspace in one warp's shared memory (D <~ 48)")
     kind, nu, dt = str(g["kind"]), int(g["nu"]), float(g["dt"])
     n = nu + 1
     case = _product_case(g)
