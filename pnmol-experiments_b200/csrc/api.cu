@@ -106,6 +106,8 @@ struct pnmol_b200_handle {
     double *hs_y0 = nullptr, *hs_mean_a = nullptr, *hs_mean_b = nullptr, *hs_chol_a = nullptr, *hs_chol_b = nullptr,
            *hs_diffsum = nullptr, *hs_diffcal = nullptr;
     int32_t* hs_status = nullptr;
+    cudaStream_t copy_stream = nullptr;               // device-to-host copies of finished chunks (host path)
+    cudaEvent_t chunk_ev = nullptr, copy_ev = nullptr;
     double *hs_err = nullptr, *hs_ref = nullptr;  // scratch of pnmol_b200_run_adaptive
     // multi-CTA path for large state dimension (ek1_large.cuh): chosen when the single-CTA kernels' shared memory
     // does not fit (or PNMOL_B200_FORCE_LARGE=1, used by the parity tests to run both paths on the same inputs)
@@ -319,6 +321,9 @@ int pnmol_b200_destroy(pnmol_b200_handle* h) {
     for (void* p : {(void*)h->hs_y0, (void*)h->hs_mean_a, (void*)h->hs_mean_b, (void*)h->hs_chol_a, (void*)h->hs_chol_b,
                     (void*)h->hs_diffsum, (void*)h->hs_diffcal, (void*)h->hs_status, (void*)h->hs_err, (void*)h->hs_ref})
         if (p) cudaFree(p);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->chunk_ev) cudaEventDestroy(h->chunk_ev);
+    if (h->copy_ev) cudaEventDestroy(h->copy_ev);
     delete h;
     return 0;
 }
@@ -757,16 +762,46 @@ int pnmol_b200_simulate_final_state_host(pnmol_b200_handle* h, const double* y0_
         CU(cudaMalloc((void**)&h->hs_diffcal, sizeof(double) * P.batch));
         CU(cudaMalloc((void**)&h->hs_status, sizeof(int32_t) * P.batch));
     }
-    CU(cudaMemcpyAsync(h->hs_y0, y0_host, sizeof(double) * P.batch * P.d, cudaMemcpyHostToDevice, st));
-    if ((rc = pnmol_b200_initialize(h, h->hs_y0, t0, diffuse_prior_scale, h->hs_mean_a, h->hs_chol_a, h->hs_status, stream))) return rc;
-    if ((rc = pnmol_b200_run(h, t0, dts, precond, precond_inv, nsteps, h->hs_mean_a, h->hs_chol_a, h->hs_mean_b, h->hs_chol_b,
-                             nullptr, nullptr, nullptr, h->hs_diffsum, nullptr, nullptr, h->hs_status, flags, stream)))
-        return rc;
-    if ((rc = pnmol_b200_rescale(h, h->hs_chol_a, h->hs_diffsum, nsteps, h->hs_diffcal, stream))) return rc;
-    CU(cudaMemcpyAsync(mean_host, h->hs_mean_a, sizeof(double) * msz, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(chol_host, h->hs_chol_a, sizeof(double) * csz, cudaMemcpyDeviceToHost, st));
+    // Members are independent: the ensemble runs in chunks of whole waves of CTAs, and the device-to-host copy of a
+    // finished chunk (the D x D factors dominate: 180 KB per member at D = 150) overlaps the next chunk's kernels on a
+    // second stream.  One chunk = the whole ensemble when it is small or runs on the multi-CTA path.
+    if (!h->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->chunk_ev, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming));
+    }
+    int chunk = P.batch;
+    if (!h->large && h->grid > 0 && P.batch >= 8 * h->grid) chunk = 4 * h->grid;
+    if (const char* e = std::getenv("PNMOL_B200_HOST_CHUNK")) chunk = std::max(1, std::atoi(e));
+    const Problem saved = h->P;
+    const size_t D = P.D, DD = (size_t)P.D * P.D;
+    for (int off = 0; off < saved.batch; off += chunk) {
+        const int nb = std::min(chunk, saved.batch - off);
+        h->P.batch = nb;
+        if (saved.diffscale) h->P.diffscale = saved.diffscale + (size_t)off * saved.ncomp;
+        if (saved.priorscale) h->P.priorscale = saved.priorscale + off;
+        if (saved.rparams) h->P.rparams = saved.rparams + (size_t)off * saved.nparams;
+        double* y0d = h->hs_y0 + (size_t)off * saved.d;
+        double *ma = h->hs_mean_a + off * D, *mb = h->hs_mean_b + off * D, *ca = h->hs_chol_a + off * DD, *cb = h->hs_chol_b + off * DD;
+        rc = 0;
+        cudaError_t ce = cudaMemcpyAsync(y0d, y0_host + (size_t)off * saved.d, sizeof(double) * nb * saved.d, cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) rc = pnmol_b200_initialize(h, y0d, t0, diffuse_prior_scale, ma, ca, h->hs_status + off, stream);
+        if (ce == cudaSuccess && !rc)
+            rc = pnmol_b200_run(h, t0, dts, precond, precond_inv, nsteps, ma, ca, mb, cb, nullptr, nullptr, nullptr,
+                                h->hs_diffsum + off, nullptr, nullptr, h->hs_status + off, flags, stream);
+        if (ce == cudaSuccess && !rc) rc = pnmol_b200_rescale(h, ca, h->hs_diffsum + off, nsteps, h->hs_diffcal + off, stream);
+        h->P = saved;
+        if (ce != cudaSuccess) return fail(-2, std::string("cudaMemcpyAsync (y0): ") + cudaGetErrorString(ce));
+        if (rc) return rc;
+        CU(cudaEventRecord(h->chunk_ev, st));
+        CU(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev, 0));
+        CU(cudaMemcpyAsync(mean_host + off * D, ma, sizeof(double) * nb * D, cudaMemcpyDeviceToHost, h->copy_stream));
+        CU(cudaMemcpyAsync(chol_host + off * DD, ca, sizeof(double) * nb * DD, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
     if (diff_cal_host) CU(cudaMemcpyAsync(diff_cal_host, h->hs_diffcal, sizeof(double) * P.batch, cudaMemcpyDeviceToHost, st));
     if (status_host) CU(cudaMemcpyAsync(status_host, h->hs_status, sizeof(int32_t) * P.batch, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(h->copy_ev, h->copy_stream));
+    CU(cudaStreamWaitEvent(st, h->copy_ev, 0));
     CU(cudaStreamSynchronize(st));
     return 0;
 }

@@ -477,6 +477,13 @@ def test_ensemble_members_match_individual_oracle_solves(path, monkeypatch):
     scale = torch.sqrt(host.diffusion_squared_calibrated)[:, None, None]
     assert torch.allclose(host.cov_sqrtm, res.cov_sqrtm.cpu() * scale, rtol=1e-13, atol=0)
     assert torch.allclose(host.diffusion_squared_calibrated, res.diffusion_squared_calibrated.cpu(), rtol=1e-13)
+    # the host route runs large ensembles in chunks of members (device-to-host copies overlap the next chunk's kernels):
+    # members are independent, so chunks of two give bitwise the same result
+    monkeypatch.setenv("PNMOL_B200_HOST_CHUNK", "2")
+    host2 = es.simulate_final_state_host()
+    assert torch.equal(host2.mean, host.mean) and torch.equal(host2.cov_sqrtm, host.cov_sqrtm)
+    assert torch.equal(host2.diffusion_squared_calibrated, host.diffusion_squared_calibrated)
+    assert int(host2.status.max()) == 0
 
 
 def test_ensemble_semilinear_sir_with_member_parameters():
