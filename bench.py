@@ -51,12 +51,19 @@ def member_parameters(num_members, x, seed):
     return y0, diff, prior
 
 
-def ncu_traffic_record():
-    """dram__bytes_read.sum + dram__bytes_write.sum of pnmol::k_run per member-step, from the committed `ncu --set full`
-    capture record profiles/r02_ncu_k_run_c5.json (written by tools/ncu_summary.py: carries the git head of the captured
-    build, the capture command and the member-steps per launch).  None when the record is missing."""
+def ncu_traffic_record(name="r02_ncu_k_run_c5"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the step kernel per member-step, from the committed `ncu --set full`
+    capture record profiles/<name>.json (written by tools/ncu_summary.py: carries the git head and the hash of the CUDA
+    sources of the captured build, the capture command and the member-steps per launch).  None when the record is
+    missing or was taken from other kernel sources than the ones this library is built from (stale capture)."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_k_run_c5.json")))
+        rec = json.load(open(os.path.join(ROOT, "profiles", name + ".json")))
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import ncu_summary
+
+        if rec.get("csrc_sha256") != ncu_summary.csrc_sha256():
+            return None
+        return rec
     except Exception:
         return None
 
@@ -337,7 +344,7 @@ def run_b200_arm(args):
                 "traffic": rec["dram_bytes_per_member_step"] * M * T if rec else None,
                 "traffic_source": (f"ncu dram__bytes_read.sum + dram__bytes_write.sum per member-step x member-steps per launch; "
                                    f"capture of build {rec['git_head']} ({rec['command']}, profiles/r02_ncu_k_run_c5_summary.csv)"
-                                   if rec else "no capture record (profiles/r02_ncu_k_run_c5.json missing)"),
+                                   if rec else "no capture record of this build (profiles/r02_ncu_k_run_c5.json missing or stale)"),
                 "kernel": "pnmol::k_run", "kernel_ms_per_launch": kernel_ms,
                 "algorithmic_flops_per_member_step": f_alg, "algorithmic_bytes_per_member_step": b_alg,
                 "peak_source": "measured in this run: cuBLAS DGEMM 4096^3 via torch.matmul(float64), best of 5 "
@@ -371,7 +378,7 @@ def run_b200_arm(args):
     if rank == 0 and world == 1 and not args.no_other_configs:
         other = other_configs_timing(dev, fp64_peak)
         # the other BASELINE configs' roofline fractions next to the headline's (same denominators)
-        roofline["other_configs"] = {k: {kk: v[kk] for kk in ("fp64_frac", "hbm_frac", "ms_per_step", "member_steps_per_sec", "path")
+        roofline["other_configs"] = {k: {kk: v[kk] for kk in ("fp64_frac", "hbm_frac", "ms_per_step", "member_steps_per_sec", "path", "dram_over_algorithmic")
                                          if kk in v} for k, v in other.items() if "error" not in v}
 
     if rank == 0:
@@ -416,8 +423,13 @@ def other_configs_timing(dev, fp64_peak):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
             f_alg = work_model(D, m, eng.d)[1]
+            b_alg = work_model(D, m, eng.d)[0]
+            rec = ncu_traffic_record("r02_ncu_k_run_large_" + name[:2])
             out[name] = {"D": D, "m": m, "path": eng.path, "ms_per_step": ms, "steps_per_sec": 1e3 / ms,
-                         "fp64_frac": f_alg / (ms * 1e-3) * 1e-12 / fp64_peak, "status": int(res["status"].max())}
+                         "fp64_frac": f_alg / (ms * 1e-3) * 1e-12 / fp64_peak, "status": int(res["status"].max()),
+                         "algorithmic_bytes_per_step": b_alg,
+                         "dram_bytes_per_step": rec["dram_bytes_per_member_step"] if rec else None,
+                         "dram_over_algorithmic": rec["dram_bytes_per_member_step"] / b_alg if rec else None}
             del solver, eng, mean, chol, s0
             torch.cuda.empty_cache()
         except Exception as exc:  # never lose the headline line to a side measurement

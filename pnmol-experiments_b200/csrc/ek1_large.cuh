@@ -228,7 +228,7 @@ static __device__ void update_stage_large(cg::grid_group& grid, const Problem& P
     update_build_left(P, b, mcur, nrows, emode, nugget, te, be, Hcol, Hval, Wl, Wr, gw, gnw);
     grid.sync();
     Shape sh;
-    sh.nt = D; sh.nbot = nbot; sh.ncols = mcur + D; sh.te = te; sh.be = be;
+    sh.nt = D; sh.nbot = nbot; sh.ncols = mcur + D; sh.te = te; sh.be = be; sh.ldr = ld;  // tile-aligned panel row lists
     pc.mark(4);
     householder_qr_large(grid, Wl, ld, sh, q, ls, pc);
     int bad = 0;
@@ -275,7 +275,7 @@ static __device__ void ek1_step_large(cg::grid_group& grid, const Problem& P, in
     grid.sync();
     pc.mark(1);
     Shape sp;
-    sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p;
+    sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? P.te_pd : P.te_p; sp.be = P.be_p; sp.ldr = P.ld;
     householder_qr_large(grid, W + (size_t)P.m * P.ld, P.ld, sp, q, ls, pc);
     if (!P.latent && !(flags & 2))
         error_estimate_large(grid, P, b, sm, q, ls, ls.pv[1], dt, E_STEP_WHITE, P.Hcol, P.Hval, P.F, P.S, err_out);
@@ -348,6 +348,9 @@ __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const 
             if (a.diff_last) a.diff_last[b] = diff_s;
             if (a.diff_sum) a.diff_sum[b] = diffsum;
             if (a.status) a.status[b] = *q.nf;
+        }
+        if (__ldcg(q.nf)) {  // the tile-aligned row lists read padding rows (times zero): leave no NaNs behind for the next member
+            for (size_t k = gtid; k < (size_t)P.ld * (P.m + P.D); k += gnt) W[k] = 0.0;
         }
         grid.sync();
     }
@@ -519,6 +522,10 @@ __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_init_large(const
         update_stage_large(grid, P, b, sm, q, ls, P.m, P.latent ? E_NUGGET_ONLY : E_STEP_PLUS_NUGGET, a.nugget, chol, nullptr,
                            nullptr, P.Hcol, P.Hval, W, o2, nullptr, pc);
         if (blockIdx.x == 0 && tid == 0 && a.status) a.status[b] = *q.nf;
+        if (__ldcg(q.nf)) {  // as in k_run_large: no NaNs in the padding rows for the next member
+            const size_t gtid = (size_t)blockIdx.x * kThreads + tid, gnt = (size_t)gridDim.x * kThreads;
+            for (size_t k = gtid; k < (size_t)P.ld * (P.m + P.D); k += gnt) W[k] = 0.0;
+        }
         grid.sync();
     }
 }

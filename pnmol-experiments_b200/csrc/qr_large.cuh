@@ -541,8 +541,13 @@ static __device__ void large_trailing_y(const double* __restrict__ W, int ld, in
 #pragma unroll
                 for (int a = 0; a < kCh; ++a) {
                     const int cl = 8 * (i0 + a) + 2 * t;
-                    xa[a][0] = (have && cl < rows) ? cp[rm.row(c0 + cl)] : 0.0;
-                    xa[a][1] = (have && cl + 1 < rows) ? cp[rm.row(c0 + cl + 1)] : 0.0;
+                    if (rm.aligned) {  // whole tiles of one segment: (segment base) + constant, no per-element row map
+                        xa[a][0] = 0.0; xa[a][1] = 0.0;
+                        if (i0 + a < nt8) tile_load<true>(cp, rm, c0 + 8 * (i0 + a), t, xa[a][0], xa[a][1]);
+                    } else {
+                        xa[a][0] = (have && cl < rows) ? cp[rm.row(c0 + cl)] : 0.0;
+                        xa[a][1] = (have && cl + 1 < rows) ? cp[rm.row(c0 + cl + 1)] : 0.0;
+                    }
                 }
 #pragma unroll
                 for (int a = 0; a < kCh; ++a) {
@@ -636,8 +641,13 @@ static __device__ void large_trailing_u(double* __restrict__ W, int ld, int ncol
 #pragma unroll
                 for (int a = 0; a < kCh; ++a) {
                     const int cl = 8 * (i0 + a) + 2 * t;
-                    xa[a][0] = (have && cl < rows) ? cp[rm.row(c0 + cl)] : 0.0;
-                    xa[a][1] = (have && cl + 1 < rows) ? cp[rm.row(c0 + cl + 1)] : 0.0;
+                    if (rm.aligned) {
+                        xa[a][0] = 0.0; xa[a][1] = 0.0;
+                        if (i0 + a < nt8) tile_load<true>(cp, rm, c0 + 8 * (i0 + a), t, xa[a][0], xa[a][1]);
+                    } else {
+                        xa[a][0] = (have && cl < rows) ? cp[rm.row(c0 + cl)] : 0.0;
+                        xa[a][1] = (have && cl + 1 < rows) ? cp[rm.row(c0 + cl + 1)] : 0.0;
+                    }
                 }
 #pragma unroll
                 for (int a = 0; a < kCh; ++a) {
@@ -652,8 +662,12 @@ static __device__ void large_trailing_u(double* __restrict__ W, int ld, int ncol
 #pragma unroll
                 for (int a = 0; a < kCh; ++a) {
                     const int cl = 8 * (i0 + a) + 2 * t;
-                    if (have && cl < rows) cp[rm.row(c0 + cl)] = xa[a][0];
-                    if (have && cl + 1 < rows) cp[rm.row(c0 + cl + 1)] = xa[a][1];
+                    if (rm.aligned) {
+                        if (have && i0 + a < nt8) tile_store<true>(cp, rm, c0 + 8 * (i0 + a), t, xa[a][0], xa[a][1]);
+                    } else {
+                        if (have && cl < rows) cp[rm.row(c0 + cl)] = xa[a][0];
+                        if (have && cl + 1 < rows) cp[rm.row(c0 + cl + 1)] = xa[a][1];
+                    }
                 }
             }
         }

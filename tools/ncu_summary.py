@@ -6,10 +6,23 @@
 """
 import argparse
 import csv
+import hashlib
 import json
 import os
 import subprocess
 import sys
+
+
+def csrc_sha256():
+    """Hash of the CUDA sources the library is built from: a capture record is valid for a build with the same hash
+    (bench.py refuses a record whose hash differs, whatever else was committed since)."""
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pnmol-experiments_b200", "csrc")
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(root)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            h.update(name.encode())
+            h.update(open(os.path.join(root, name), "rb").read())
+    return h.hexdigest()
 
 KEEP = ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "launch__", "lts__t_sector_hit_rate.pct",
         "lts__throughput.avg.pct", "sm__inst_executed.sum", "sm__inst_executed.avg.per_cycle_elapsed", "sm__inst_executed_pipe_",
@@ -38,14 +51,14 @@ def main():
     with open(args.out_prefix + "_summary.csv", "w") as f:
         f.write("metric,unit,value\n")
         f.write(f"# ncu --set full --clock-control none --import-source on; {args.cmd}; kernel {kname}; {args.member_steps} member-steps "
-                f"per launch; git head {head}; {args.note},,\n")
+                f"per launch; git head {head}; csrc sha256 {csrc_sha256()[:16]}; {args.note},,\n")
         for h, u, v in picked:
             f.write(f"{h},{u},{v}\n")
     def get(name):
         i = hdr.index(name)
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[units[i]]
         return float(vals[i]) * scale
-    rec = {"git_head": head, "kernel": kname, "command": args.cmd, "member_steps_per_launch": args.member_steps,
+    rec = {"git_head": head, "csrc_sha256": csrc_sha256(), "kernel": kname, "command": args.cmd, "member_steps_per_launch": args.member_steps,
            "dram_bytes_read": get("dram__bytes_read.sum"), "dram_bytes_write": get("dram__bytes_write.sum"),
            "dram_bytes_per_member_step": (get("dram__bytes_read.sum") + get("dram__bytes_write.sum")) / args.member_steps,
            "duration_ms_under_ncu": float(vals[hdr.index("gpu__time_duration.sum")]), "note": args.note}
