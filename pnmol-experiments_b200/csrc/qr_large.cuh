@@ -496,6 +496,19 @@ static __device__ void large_panel_factor_cluster(cg::cluster_group& cluster, do
     }
 }
 
+// 8-row tile of a lane (rows tb + 2 t, tb + 2 t + 1 of its column) for tile-aligned row lists; `vec`: even segment
+// offsets and leading dimension, i.e. one 16-byte access.
+__device__ __forceinline__ void large_tile_load(const double* __restrict__ cp, const RowMap& rm, int tb, int t, bool vec, double& x0, double& x1) {
+    const double* p = cp + (tb < rm.len1 ? rm.j0 : rm.a2 - rm.len1) + tb + 2 * t;
+    if (vec) { const double2 v = *reinterpret_cast<const double2*>(p); x0 = v.x; x1 = v.y; }
+    else { x0 = p[0]; x1 = p[1]; }
+}
+__device__ __forceinline__ void large_tile_store(double* __restrict__ cp, const RowMap& rm, int tb, int t, bool vec, double x0, double x1) {
+    double* p = cp + (tb < rm.len1 ? rm.j0 : rm.a2 - rm.len1) + tb + 2 * t;
+    if (vec) *reinterpret_cast<double2*>(p) = make_double2(x0, x1);
+    else { p[0] = x0; p[1] = x1; }
+}
+
 // S2: partial Y^T = C^T V per (row chunk, column group) item.  The item's chunk of the reflectors (RC rows x kNB) is
 // staged in shared memory by TMA (cp.async.bulk.tensor.2d, reflector-major, pitch = 2 mod 16) into one of two stages:
 // the load of the CTA's next item is in flight while the tensor cores work on the current one.
@@ -510,6 +523,7 @@ static __device__ void large_trailing_y(const double* __restrict__ W, int ld, in
     const unsigned bytes = (unsigned)(kNB * pitch * sizeof(double));
     const CUtensorMap* tmap = &q.tmapV[bi];
     unsigned n = *ls.nload;
+    const bool vec = (((rm.j0 | (rm.a2 - rm.len1) | ld) & 1) == 0) && ((reinterpret_cast<size_t>(W) & 15) == 0);
     __syncthreads();
     if (tid == 0 && (int)blockIdx.x < nitems) {
         asm volatile("fence.proxy.async;\n" ::: "memory");  // the panel team wrote the reflectors through the generic proxy
@@ -543,7 +557,7 @@ static __device__ void large_trailing_y(const double* __restrict__ W, int ld, in
                     const int cl = 8 * (i0 + a) + 2 * t;
                     if (rm.aligned) {  // whole tiles of one segment: (segment base) + constant, no per-element row map
                         xa[a][0] = 0.0; xa[a][1] = 0.0;
-                        if (i0 + a < nt8) tile_load<true>(cp, rm, c0 + 8 * (i0 + a), t, xa[a][0], xa[a][1]);
+                        if (i0 + a < nt8) large_tile_load(cp, rm, c0 + 8 * (i0 + a), t, vec, xa[a][0], xa[a][1]);
                     } else {
                         xa[a][0] = (have && cl < rows) ? cp[rm.row(c0 + cl)] : 0.0;
                         xa[a][1] = (have && cl + 1 < rows) ? cp[rm.row(c0 + cl + 1)] : 0.0;
@@ -589,6 +603,7 @@ static __device__ void large_trailing_u(double* __restrict__ W, int ld, int ncol
     const unsigned bytes = (unsigned)(kNB * pitch * sizeof(double));
     const CUtensorMap* tmap = &q.tmapV[bi];
     unsigned n = *ls.nload;
+    const bool vec = (((rm.j0 | (rm.a2 - rm.len1) | ld) & 1) == 0) && ((reinterpret_cast<size_t>(W) & 15) == 0);
     __syncthreads();
     if (tid == 0 && (int)blockIdx.x < nitems)
         large_tma_load(large_stage(ls, n & 1), tmap, ((int)blockIdx.x / ncg) * RC, 0, &ls.bars[n & 1], bytes);
@@ -643,7 +658,7 @@ static __device__ void large_trailing_u(double* __restrict__ W, int ld, int ncol
                     const int cl = 8 * (i0 + a) + 2 * t;
                     if (rm.aligned) {
                         xa[a][0] = 0.0; xa[a][1] = 0.0;
-                        if (i0 + a < nt8) tile_load<true>(cp, rm, c0 + 8 * (i0 + a), t, xa[a][0], xa[a][1]);
+                        if (i0 + a < nt8) large_tile_load(cp, rm, c0 + 8 * (i0 + a), t, vec, xa[a][0], xa[a][1]);
                     } else {
                         xa[a][0] = (have && cl < rows) ? cp[rm.row(c0 + cl)] : 0.0;
                         xa[a][1] = (have && cl + 1 < rows) ? cp[rm.row(c0 + cl + 1)] : 0.0;
@@ -663,7 +678,7 @@ static __device__ void large_trailing_u(double* __restrict__ W, int ld, int ncol
                 for (int a = 0; a < kCh; ++a) {
                     const int cl = 8 * (i0 + a) + 2 * t;
                     if (rm.aligned) {
-                        if (have && i0 + a < nt8) tile_store<true>(cp, rm, c0 + 8 * (i0 + a), t, xa[a][0], xa[a][1]);
+                        if (have && i0 + a < nt8) large_tile_store(cp, rm, c0 + 8 * (i0 + a), t, vec, xa[a][0], xa[a][1]);
                     } else {
                         if (have && cl < rows) cp[rm.row(c0 + cl)] = xa[a][0];
                         if (have && cl + 1 < rows) cp[rm.row(c0 + cl + 1)] = xa[a][1];
