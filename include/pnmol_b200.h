@@ -76,13 +76,18 @@ int pnmol_b200_profile(pnmol_b200_handle* h, int enable, uint64_t* cycles_out);
 
 /* Which kernel family serves this handle (valid after pnmol_b200_set_operator):
  *   0 = one CTA per member (blocked QR with 16-column panels; row lists up to 512 rows; the default for ensembles),
- *   2 = one WARP per member (8-column panels in the warp's shared-memory slice, per-warp tensor-core trailing
- *       updates, no block barriers; row lists up to 224 rows; opt-in, measured slower on B200),
- *   1 = the whole grid per member (multi-CTA blocked QR with FP64 tensor-core trailing updates; BASELINE
- *       configs C2-C4).
- * The environment variable PNMOL_B200_PATH=warp|cta|large overrides the choice where the problem fits (used by
+ *   2 = one WARP per member, the whole QR workspace in the warp's slice of shared memory (small state dimension,
+ *       D <~ 48: the meshes the reference tests and plots),
+ *   1 = the whole grid per member (multi-CTA blocked QR with FP64 tensor-core trailing updates fed by TMA-staged
+ *       reflector tiles; BASELINE configs C2-C4).
+ * The environment variable PNMOL_B200_PATH=small|cta|large overrides the choice where the problem fits (used by
  * the parity tests to run every family on the same inputs).  <0 = error. */
 int pnmol_b200_path(pnmol_b200_handle* h);
+
+/* Diagnostics of the multi-CTA path: the thread-block cluster size the kernels are launched with (`requested`; the
+ * panel factorisation runs on cluster 0) and the size the last pnmol_b200_run launch observed on the device
+ * (cooperative_groups::this_cluster().num_blocks(); 0 before the first run or off the multi-CTA path). */
+int pnmol_b200_cluster_size(pnmol_b200_handle* h, int* requested, int* observed);
 
 /* Create a solver handle for `batch` independent members of one discretised problem.
  * Replaces PDEFilter.__init__ + the shape bookkeeping of initialize()

@@ -488,7 +488,7 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
             if ((rc = dev_alloc(h, &q.Yp, (size_t)(maxlen / 64 + 2) * q.ycols * kNB))) return rc;
             if ((rc = dev_alloc(h, &q.vec, (size_t)P.D + 3 * (size_t)P.m + P.dd + 8))) return rc;
             if ((rc = dev_alloc(h, &q.Ld, (size_t)P.m))) return rc;
-            if ((rc = dev_alloc(h, &q.nf, 2))) return rc;   // (two words: the adaptive loop alternates by attempt parity)
+            if ((rc = dev_alloc(h, &q.nf, 4))) return rc;   // (two words: the adaptive loop alternates by attempt parity)
             CU(cudaMemset(P.W, 0, wsz * sizeof(double)));
             CU(cudaMemset(q.Vg, 0, (size_t)kNB * q.lv * sizeof(double)));
             h->have_op = true;
@@ -720,6 +720,19 @@ int pnmol_b200_profile(pnmol_b200_handle* h, int enable, uint64_t* cycles_out) {
     }
     if (h->P.prof) CU(cudaMemset(h->P.prof, 0, 24 * sizeof(uint64_t)));
     if (!enable) h->P.prof = nullptr;
+    return 0;
+}
+
+int pnmol_b200_cluster_size(pnmol_b200_handle* h, int* requested, int* observed) {
+    if (!h || !requested || !observed) return fail(-1, "null argument");
+    *requested = h->large ? h->cluster : 0;
+    *observed = 0;
+    if (h->large && h->q.nf) {
+        int32_t v = 0;
+        CU(cudaSetDevice(h->device));
+        CU(cudaMemcpy(&v, h->q.nf + 2, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        *observed = v;
+    }
     return 0;
 }
 

@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(kThreads, PNMOL_LARGE_CTAS) k_run_large(const 
     const int n = P.n, D = P.D;
     const size_t msz = (size_t)D, csz = (size_t)D * D;
     double* W = P.W;
+    if (blockIdx.x == 0 && tid == 0) q.nf[2] = (int32_t)cg::this_cluster().num_blocks();  // diagnostics: pnmol_b200_cluster_size
     PhaseClock pc;  // phase cycles as seen by CTA 0 (pnmol_b200_profile); indices as in ek1_step, 8..13 = QR: panel
     pc.start(blockIdx.x == 0 ? P.prof : nullptr);  // factor, barrier, partial Y, barrier, update, barrier
     for (int b = 0; b < P.batch; ++b) {

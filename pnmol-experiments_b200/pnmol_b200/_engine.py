@@ -123,6 +123,14 @@ class Engine:
             _lib.check(rc)
         return {0: "single_cta", 1: "multi_cta", 2: "small"}[rc]
 
+    def cluster_size(self):
+        """(requested, observed) thread-block cluster size of the multi-CTA kernels (diagnostics; (0, 0) elsewhere)."""
+        import ctypes
+
+        req, obs = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(self.lib.pnmol_b200_cluster_size(self.h, ctypes.byref(req), ctypes.byref(obs)))
+        return req.value, obs.value
+
     # ------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=torch.float64):
         return torch.empty(shape, dtype=dtype, device=self.device)

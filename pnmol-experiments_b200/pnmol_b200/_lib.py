@@ -18,6 +18,7 @@ SIGNATURES = {
     "pnmol_b200_launch_count": (c_int64, []),
     "pnmol_b200_profile": (c_int, [c_void_p, c_int, c_void_p]),
     "pnmol_b200_path": (c_int, [c_void_p]),
+    "pnmol_b200_cluster_size": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pnmol_b200_create": (c_int, [ctypes.POINTER(c_void_p)] + [c_int] * 8),
     "pnmol_b200_destroy": (c_int, [c_void_p]),
     "pnmol_b200_set_operator": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

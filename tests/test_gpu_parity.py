@@ -420,6 +420,9 @@ def test_baseline_configs_c2_c3_full_size(name, kind, bcond, num, dt):
         assert cases.mean_excess(_np(new.y.mean), st.mean) < 1
         assert cases.cov_excess(_np(new.y.cov_sqrtm), st.cov_sqrtm, n) < 1
     print(f"[{name} N={num} D={st.cov_sqrtm.shape[0]}] initialize {t_init:.3f} s, step {t_step:.3f} s (multi-CTA path)")
+    # the panel factorisation runs on a thread-block cluster of 8 CTAs: what the launch asked for is what the device saw
+    # (ncu reports launch__cluster_size 0 for these cooperative launches -- this read-back is the evidence)
+    assert solver._engine.cluster_size() == (8, 8)
 
 
 def test_baseline_config_c4_full_size():
