@@ -71,7 +71,9 @@ int64_t pnmol_b200_launch_count(void);
 /* Diagnostics: with enable != 0 the step kernel accumulates clock64 cycles per phase (thread 0 of
  * every CTA) into 24 counters; a later call copies them to cycles_out host [24] (may be NULL)
  * and resets them.  Phases: 0 predict mean + evaluate_ode, 1 build predict stack, 2 predict QR,
- * 3 error estimate, 4 build update matrix, 5 update QR, 6 triangular solves + mean, 7 outputs. */
+ * 3 error estimate, 4 build update matrix, 5 update QR, 6 triangular solves + mean, 7 outputs.
+ * The counters are only fed by a library compiled with -DPNMOL_PROFILE=1 (tools/build_variant.sh); the shipped
+ * library carries no phase marks (they cost local-memory traffic on the critical path) and reports zeros. */
 int pnmol_b200_profile(pnmol_b200_handle* h, int enable, uint64_t* cycles_out);
 
 /* Which kernel family serves this handle (valid after pnmol_b200_set_operator):

@@ -62,17 +62,29 @@ struct Problem {
 };
 
 // Phase timer: thread 0 of every CTA adds the cycles since the previous mark to prof[idx].
+// Compiled in only with -DPNMOL_PROFILE=1 (tools/build_variant.sh prof -DPNMOL_PROFILE=1): the object is passed by reference
+// through __noinline__ functions, i.e. it lives in local memory, and even a disabled mark() costs a local-memory load
+// on the critical path of the panel chain.  The shipped library carries no marks (pnmol_b200_profile then reports zeros).
+#ifndef PNMOL_PROFILE
+#define PNMOL_PROFILE 0
+#endif
 struct PhaseClock {
+#if !PNMOL_PROFILE
+    __device__ __forceinline__ void start(unsigned long long*) {}
+    __device__ __forceinline__ void mark(int) {}
+#else
     unsigned long long* prof;
     long long last;
     __device__ __forceinline__ void start(unsigned long long* p) { prof = p; if (prof && threadIdx.x == 0) last = clock64(); }
     __device__ __forceinline__ void mark(int idx) {
         if (prof && threadIdx.x == 0) {
             const long long now = clock64();
-            atomicAdd(&prof[idx], (unsigned long long)(now - last));
+            // fire-and-forget reduction (a generic-pointer atomicAdd waits for its round trip and inflates the next phase)
+            asm volatile("red.global.add.u64 [%0], %1;" ::"l"(prof + idx), "l"((unsigned long long)(now - last)) : "memory");
             last = now;
         }
     }
+#endif
 };
 
 struct Shape {  // QR row structure: rows [0,nt) top, [nt, nt+nbot) bottom
@@ -95,6 +107,7 @@ struct FastQR {       // shared-memory buffers of the blocked QR (qr_fast.cuh), 
 
 struct Smem {
     double *vbuf, *mp, *z, *y, *xw, *xat, *red, *pv, *pinv, *Vs, *xraw, *sc, *msq, *Vr, *Ts, *Gs;
+    double* ekey = nullptr;  // 4 doubles: key of the cached error-estimate factor (error_estimate_smem), or nullptr
     FastQR fq;
     double *fqbase, *fqend;
     int32_t *te_p, *be_p, *te_pd, *te_u, *be_u;  // shared-memory copies of the QR envelopes (Problem::te_p ...)
@@ -148,7 +161,7 @@ __host__ __device__ __forceinline__ size_t smem_doubles(int D, int m, int dd, in
     // (the m x ldm scratch of the error estimate and of the triangular solves aliases the panel buffers of the QR, which are
     // idle then; it only takes extra room beyond their 2 x 16 x vld doubles)
     const size_t msq = (size_t)m * ldm, bufs = 2 * (size_t)16 * vld;
-    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 80 + 1 + fastqr_doubles(vld) + (msq > bufs ? msq - bufs : 0) + 8 +
+    return (size_t)(2 * D + 4) + D + 3 * (size_t)m + dd + 16 + 2 * kMaxN + 80 + 4 + 1 + fastqr_doubles(vld) + (msq > bufs ? msq - bufs : 0) + 8 +
            (3 * (size_t)D + 2 * ((size_t)m + D) + 2) / 2 + 2 * (size_t)m * wh;
 }
 
@@ -165,6 +178,7 @@ __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vl
     s.pv = base;                base += kMaxN;
     s.pinv = base;              base += kMaxN;
     s.sc = base;                base += 80;
+    s.ekey = base;              base += 4;
     s.xraw = nullptr; s.Vs = nullptr; s.Vr = nullptr; s.Ts = nullptr; s.Gs = nullptr;
     s.fq.LP = vld;
     s.fq.slot = 0;
@@ -425,12 +439,21 @@ __device__ void evaluate_ode(const Problem& P, int b, const Smem& sm, double p0s
 // white.py:104,118 / latent.py:179,194 and iwp.py:32-53, stacked_ssm.py:16-26.
 // (w0, nw): this warp's index and the number of warps sharing the loop (CTA-local by default; grid-wide on the
 // multi-CTA path, which synchronises with a grid barrier afterwards).
+// pv_prev != nullptr (fused time loop, CTA-per-member path): the input factor is NOT read from the state buffer but taken
+// in place from where the previous step's update QR left it -- row r of the factor is column m + r of R, rows m..m + r
+// (see update_output_factor), i.e. Cl[r][k] = pv_prev[r % n] * Wp[r ld + m + k] with the previous step's Nordsieck
+// scaling pv_prev -- so that a step that is neither the last one nor part of a requested trajectory never writes and
+// re-reads the D x D factor.  Same operations in the same order as the route through the state buffer (bitwise equal).
 template <class T = CtaTeam>
 __device__ void build_predict(const Problem& P, int b, const Smem& sm, const double* __restrict__ Cl,
-                              const int32_t* te, double* Wp, int w0 = T::warp(), int nw = T::nwarps) {
+                              const int32_t* te, double* Wp, int w0 = T::warp(), int nw = T::nwarps,
+                              const double* pv_prev = nullptr, int nrows_prev = 0) {
     const int lane = T::tid() & 31;
     const int n = P.n, D = P.D, nd = P.n * P.d;
     const double ps = P.priorscale ? P.priorscale[b] : 1.0;
+    double pvp[kMaxN];
+#pragma unroll
+    for (int s = 0; s < kMaxN; ++s) pvp[s] = (pv_prev && s < n) ? pv_prev[s] : 1.0;
     // One n x n block of columns per warp and round: the n columns i = blk n + ii are combinations of the SAME n rows
     // blk n + s of the input factor (A = I (x) A_1d), so those rows are read once; two lane-chunks per round keep
     // 2 n independent (streaming, HBM) loads in flight.
@@ -442,11 +465,27 @@ __device__ void build_predict(const Problem& P, int b, const Smem& sm, const dou
         double* col0 = Wp + (size_t)i0 * P.ld;
         for (int k0 = 0; k0 <= tend; k0 += 64) {
             double v[2][kMaxN];
+            if (pv_prev) {
+                // in place: rows m + k of the block's own columns -> rows k (every load of a round before its first store;
+                // a later round reads rows >= m + k0 + 64, which no earlier round has written)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int k = k0 + 32 * u + lane;
+#pragma unroll
+                    for (int s = 0; s < kMaxN; ++s) {
+                        double c = 0.0;
+                        if (s < n && k <= i0 + s && P.m + k < nrows_prev) c = pvp[s] * col0[(size_t)s * P.ld + P.m + k];
+                        v[u][s] = (s < n && k <= tend) ? sm.pinv[s] * c : 0.0;
+                    }
+                }
+                __syncwarp();
+            } else {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int k = k0 + 32 * u + lane;
 #pragma unroll
                 for (int s = 0; s < kMaxN; ++s) v[u][s] = (s < n && k <= tend) ? sm.pinv[s] * PNMOL_STATE_LOAD(src + (size_t)s * D + k) : 0.0;
+            }
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -596,9 +635,25 @@ __device__ void error_estimate_global(const Problem& P, int b, const Smem& sm, d
 // At and the L2-resident Gram matrix (all loads independent), factorised and solved in sm.msq.
 template <class T = CtaTeam>
 __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode,
-                                    const int32_t* Hcol, const double* Hval, double* err_out) {
+                                    const int32_t* Hcol, const double* Hval, double* err_out, double* Sg = nullptr,
+                                    double* Fg = nullptr, double* key = nullptr) {
     const int tid = T::tid(), lane = tid & 31, warp = T::warp();
     const int n = P.n, d = P.d, m = P.m, ldm = P.ldm;
+    // Loop-invariant factor: for a linear PDE the rows of H depend on the member and on the Nordsieck scaling (dt) only,
+    // so S = H Q H^T + E E^T and its Cholesky factor are the same in every step of a constant-step run.  The CTA keeps
+    // the factor of its current member in its global scratch (Sg: lower triangle + diagonal of L, Fg: diag(S)) and
+    // re-reads it while the key (member, scalings, noise mode) in shared memory is unchanged -- same numbers, bit for bit.
+    const bool cacheable = key != nullptr && Sg != nullptr && Fg != nullptr && !P.semilinear;
+    const bool hit = cacheable && key[0] == (double)b && key[1] == sm.pv[0] && key[2] == p1s && key[3] == (double)emode;
+    if (hit) {
+        double* S = sm.msq;
+        for (int idx = tid; idx < m * m; idx += T::size) {
+            const int r = idx / m, c = idx - r * m;
+            if (c < r) S[r * ldm + c] = Sg[idx];
+            else if (c == r) sm.xw[r] = Sg[idx];
+        }
+        for (int r = tid; r < m; r += T::size) sm.y[r] = Fg[r];
+    } else {
     const double ps = P.priorscale ? P.priorscale[b] : 1.0;
     const double ps2 = ps * ps;
     double q00 = 0, q01 = 0, q11 = 0;
@@ -675,6 +730,18 @@ __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, dou
             for (int c = k + 1 + lane; c <= r; c += 32) S[r * ldm + c] = fma(-lrk, S[c * ldm + k], S[r * ldm + c]);
         }
     }
+    if (cacheable) {
+        T::sync();
+        for (int idx = tid; idx < m * m; idx += T::size) {
+            const int r = idx / m, c = idx - r * m;
+            if (c < r) Sg[idx] = S[r * ldm + c];
+            else if (c == r) Sg[idx] = sm.xw[r];
+        }
+        for (int r = tid; r < m; r += T::size) Fg[r] = sm.y[r];
+        if (tid == 0) { key[0] = (double)b; key[1] = sm.pv[0]; key[2] = p1s; key[3] = (double)emode; }
+    }
+    }  // (factor computed or re-read)
+    double* S = sm.msq;
     T::sync();
     // forward solve L u = z by warp 0 (column oriented: each lane owns rows lane, lane + 32, lane + 64)
     if (warp == 0) {
@@ -710,7 +777,7 @@ template <class T = CtaTeam>
 __device__ void error_estimate(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode, double nugget,
                                const int32_t* Hcol, const double* Hval, double* F, double* S, double* err_out) {
     if (P.ldm > 0 && P.m <= 96)
-        error_estimate_smem<T>(P, b, sm, p1s, dt, emode, Hcol, Hval, err_out);
+        error_estimate_smem<T>(P, b, sm, p1s, dt, emode, Hcol, Hval, err_out, S, F, T::size == kThreads ? sm.ekey : nullptr);
     else
         error_estimate_global<T>(P, b, sm, p1s, dt, emode, nugget, Hcol, Hval, F, S, err_out);
 }
@@ -1086,7 +1153,7 @@ static __device__ void update_stage(const Problem& P, int b, const Smem& sm, int
     if (out.diff_out && tid == 0) *out.diff_out = diff;
     pc.mark(6);
     int bad = update_output_mean(P, sm, out, diff);
-    bad |= update_output_factor(P, sm, out, mcur, nrows, Wr, warp, kWarps);
+    if (out.chol_out) bad |= update_output_factor(P, sm, out, mcur, nrows, Wr, warp, kWarps);  // (nullptr: the next step takes R3 in place)
     if (bad) atomicOr(nonfinite, 1);
     __syncthreads();
     pc.mark(7);

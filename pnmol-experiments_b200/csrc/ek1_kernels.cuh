@@ -40,7 +40,8 @@ struct InitArgs {
 // One EK1 step for member b: state (mean_in, chol_in) -> (mean_out, chol_out).
 static __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, double dt, double tnew,
                          const double* mean_in, const double* chol_in, double* mean_out, double* chol_out,
-                         double* err_out, double* ref_out, double* diff_out, int flags, int* nonfinite) {
+                         double* err_out, double* ref_out, double* diff_out, int flags, int* nonfinite,
+                         const double* pv_prev = nullptr, bool write_factor = true) {
     const int tid = threadIdx.x;
     PhaseClock pc;
     pc.start(P.prof);
@@ -59,7 +60,9 @@ static __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& s
     evaluate_ode(P, b, sm, sm.pv[0], sm.pv[1], Hcol, Hval);
     pc.mark(0);
     const bool dense = flags & 1;
-    build_predict(P, b, sm, chol_in, dense ? sm.te_pd : sm.te_p, W + (size_t)P.m * P.ld);
+    // (pv_prev: the previous step of this launch left its factor in W, see build_predict)
+    build_predict(P, b, sm, chol_in, dense ? sm.te_pd : sm.te_p, W + (size_t)P.m * P.ld, threadIdx.x >> 5, kWarps, pv_prev,
+                  P.D + (P.latent ? 0 : P.m));
     pc.mark(1);
     Shape sp;
     sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? sm.te_pd : sm.te_p; sp.be = sm.be_p; sp.ldr = P.ld;
@@ -71,7 +74,7 @@ static __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& s
     }
     pc.mark(3);
     UpdateOut out;
-    out.mean_out = mean_out; out.chol_out = chol_out; out.diff_out = diff_out;
+    out.mean_out = mean_out; out.chol_out = write_factor ? chol_out : nullptr; out.diff_out = diff_out;
     out.ref_out = P.latent ? nullptr : ref_out; out.scale_by_p = true;
     update_stage(P, b, sm, P.m, P.latent ? E_NONE : E_STEP_WHITE, 0.0, nullptr, sm.te_u, sm.be_u, Hcol, Hval, W, out,
                  nonfinite, pc);
@@ -85,6 +88,7 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem 
     __shared__ int nonfinite;
     __shared__ double diff_s;
     for (double* q = sm.fqbase + threadIdx.x; q < sm.fqend; q += kThreads) *q = 0.0;  // reflector buffers start finite
+    if (threadIdx.x == 0) sm.ekey[0] = -1.0;  // no cached error-estimate factor yet
     load_envelopes(P, sm);
     const int tid = threadIdx.x;
     const size_t msz = (size_t)P.D, csz = (size_t)P.D * P.D;
@@ -109,9 +113,14 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem 
             double* cout = (even ? a.chol_b : a.chol_a) + b * csz;
             // only the first step may see a user-supplied (possibly dense) factor
             const int flags = s == 0 ? a.flags : (a.flags & ~1);
+            // Fused time loop: unless a factor trajectory / marginal read-out needs it, only the last step writes the
+            // D x D factor to the state; the others hand it to their successor inside the workspace.
+            const bool fuse = !a.chol_traj && !a.std_traj && a.pv != nullptr && !(a.flags & 4);
+            const bool from_w = fuse && s > 0, to_w = fuse && s + 1 < a.nsteps;
             ek1_step(P, b, blockIdx.x, sm, dt, tnew, min_, cin_, mout, cout,
                      a.err_out ? a.err_out + (size_t)b * P.d : nullptr,
-                     a.ref_out ? a.ref_out + (size_t)b * P.d : nullptr, &diff_s, flags, &nonfinite);
+                     a.ref_out ? a.ref_out + (size_t)b * P.d : nullptr, &diff_s, flags, &nonfinite,
+                     from_w ? a.pv + (size_t)(s - 1) * P.n : nullptr, !to_w);
             __syncthreads();
             diffsum += diff_s;
             if (a.mean_traj) {
@@ -172,6 +181,7 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run_adaptive(const
     __shared__ int nonfinite;
     __shared__ double diff_s;
     for (double* q = sm.fqbase + threadIdx.x; q < sm.fqend; q += kThreads) *q = 0.0;  // reflector buffers start finite
+    if (threadIdx.x == 0) sm.ekey[0] = -1.0;  // no cached error-estimate factor yet
     load_envelopes(P, sm);
     const int tid = threadIdx.x;
     const int nu = P.n - 1;
@@ -271,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_init(const Problem
     sm.fq.slot = sm_slot(P);
     __shared__ int nonfinite;
     for (double* q = sm.fqbase + threadIdx.x; q < sm.fqend; q += kThreads) *q = 0.0;  // reflector buffers start finite
+    if (threadIdx.x == 0) sm.ekey[0] = -1.0;  // no cached error-estimate factor yet
     load_envelopes(P, sm);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = P.n, d = P.d, D = P.D, nd = P.n * P.d;

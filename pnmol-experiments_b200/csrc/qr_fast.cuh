@@ -368,6 +368,8 @@ __device__ __forceinline__ void trail_p2_mma(const P2Ops& b, const double (&z)[2
     dmma884(x0, x1, z[1][1], b.b1);
 }
 // Y'^T = -(Y^T T): yt[n][q] = Y^T[col g][reflector 8 n + 2 t + q]
+__device__ __forceinline__ void trail_apply_t_yt(const double* __restrict__ Ts, int g, int t, const double (&yt)[2][2],
+                                                 double (&z)[2][2]);
 __device__ __forceinline__ void trail_apply_t(const double* __restrict__ Ts, int g, int t, bool have, const double (&y)[2][2][2],
                                               double (&z)[2][2]) {
     double yt[2][2];
@@ -375,6 +377,10 @@ __device__ __forceinline__ void trail_apply_t(const double* __restrict__ Ts, int
     for (int n = 0; n < 2; ++n)
 #pragma unroll
         for (int q = 0; q < 2; ++q) yt[n][q] = have ? y[0][n][q] + y[1][n][q] : 0.0;
+    trail_apply_t_yt(Ts, g, t, yt, z);
+}
+__device__ __forceinline__ void trail_apply_t_yt(const double* __restrict__ Ts, int g, int t, const double (&yt)[2][2],
+                                                 double (&z)[2][2]) {
 #pragma unroll
     for (int n = 0; n < 2; ++n) { z[n][0] = 0.0; z[n][1] = 0.0; }
 #pragma unroll
@@ -548,6 +554,99 @@ __device__ __noinline__ void trailing_fast(double* __restrict__ W, int ld, int c
     }
 }
 
+// Priority update: the (at most 16) columns [cbeg, cend) of the NEXT panel, which the panel team is waiting for, are
+// brought up to date by ALL warps of the CTA instead of one warp per column group: a column group's row tiles are split
+// over kWarps / (number of groups) warps (<= kSplitTiles tiles each, all in registers); every warp forms the partial
+// Y^T of its tiles, the partials are exchanged through shared memory (`xch`: the idle panel buffer) and summed in a
+// fixed order, and every warp finishes its own tiles.  Must be called by every warp of the CTA (named barrier 5).
+constexpr int kSplitTiles = 8;
+template <int MODE>
+__device__ __noinline__ void trailing_split(double* __restrict__ W, int ld, int cbeg, int cend, const RowMap rm, unsigned buf_off,
+                                            int LP, unsigned ts_off, unsigned xch_off, PhaseClock& pc) {
+    extern __shared__ __align__(16) double smem_raw[];
+    const double* buf = smem_raw + buf_off;
+    const double* Ts = smem_raw + ts_off;
+    double* xch = smem_raw + xch_off;
+    pc.mark(20);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int ntile = (rm.len + 7) >> 3;
+    const int ngroups = (cend - cbeg + 7) >> 3;          // 1 or 2
+    const int nparts = kWarps / ngroups;
+    const int group = warp % ngroups, part = warp / ngroups;
+    const int per = 2 * ((ntile + 2 * nparts - 1) / (2 * nparts));   // tiles per part, even (operand parity is compile-time)
+    const int a0 = part * per;
+    const int a1 = a0 + per < ntile ? a0 + per : ntile;  // my tiles: [a0, a1)
+    TrailOps o;
+    {
+        const int sw1 = vsw(g), swa = vsw(2 * t), swb = vsw(2 * t + 1);
+        const double* r1 = buf + (size_t)g * LP;
+        o.p1e = r1 + swz_even(2 * t, sw1); o.p1o = r1 + swz_odd(2 * t, sw1);
+        const double* ra = buf + (size_t)(2 * t) * LP;
+        const double* rb = ra + LP;
+        o.p2ea = ra + swz_even(g, swa); o.p2oa = ra + swz_odd(g, swa);
+        o.p2eb = rb + swz_even(g, swb); o.p2ob = rb + swz_odd(g, swb);
+        o.hi = 8 * LP;
+    }
+    const int nt1 = (rm.len1 + 7) >> 3;
+    const int off1 = rm.j0 + 2 * t, off2 = rm.a2 - rm.len1 + 2 * t;
+    const int kb = cbeg + 8 * group;
+    const int col = kb + g;
+    const bool have = col < cend;
+    double* cp = W + (size_t)(have ? col : kb) * ld;
+    double xa[kSplitTiles][2];
+#pragma unroll
+    for (int i = 0; i < kSplitTiles; ++i) {
+        xa[i][0] = 0.0; xa[i][1] = 0.0;
+        if (a0 + i < a1) trail_load<MODE>(cp, rm, a0 + i, t, nt1, off1, off2, xa[i][0], xa[i][1]);
+    }
+    double y[2][2][2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int n = 0; n < 2; ++n) { y[e][n][0] = 0.0; y[e][n][1] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < kSplitTiles; ++i)
+        if (a0 + i < a1) trail_p1_mma(trail_p1_fetch(o, a0, i), xa[i][0], xa[i][1], y);
+    pc.mark(16);
+    {
+        double2* mine = reinterpret_cast<double2*>(xch + (size_t)(part * ngroups + group) * 128 + 4 * lane);
+        mine[0] = have ? make_double2(y[0][0][0] + y[1][0][0], y[0][0][1] + y[1][0][1]) : make_double2(0.0, 0.0);
+        mine[1] = have ? make_double2(y[0][1][0] + y[1][1][0], y[0][1][1] + y[1][1][1]) : make_double2(0.0, 0.0);
+    }
+    asm volatile("bar.sync 5, %0;" ::"r"(kThreads) : "memory");
+    pc.mark(17);
+    double yt[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int p = 0; p < nparts; ++p) {   // fixed order: bitwise reproducible
+        const double2* theirs = reinterpret_cast<const double2*>(xch + (size_t)(p * ngroups + group) * 128 + 4 * lane);
+        const double2 v0 = theirs[0], v1 = theirs[1];
+        yt[0][0] += v0.x; yt[0][1] += v0.y; yt[1][0] += v1.x; yt[1][1] += v1.y;
+    }
+    if (a0 >= a1) return;
+    double z[2][2];
+    trail_apply_t_yt(Ts, g, t, yt, z);
+#pragma unroll
+    for (int i = 0; i < kSplitTiles; ++i)
+        if (a0 + i < a1) trail_p2_mma(trail_p2_fetch(o, a0, i), z, xa[i][0], xa[i][1]);
+    if (have) {
+#pragma unroll
+        for (int i = 0; i < kSplitTiles; ++i)
+            if (a0 + i < a1) trail_store<MODE>(cp, rm, a0 + i, t, nt1, off1, off2, xa[i][0], xa[i][1]);
+    }
+    pc.mark(18);
+}
+
+__device__ __forceinline__ void trailing_split_dispatch(double* __restrict__ W, int ld, int cbeg, int cend, const RowMap& rm,
+                                                        unsigned buf_off, int LP, unsigned ts_off, unsigned xch_off, PhaseClock& pc) {
+    if (rm.aligned) {
+        const bool vec = (((rm.j0 | (rm.a2 - rm.len1) | ld) & 1) == 0) && ((reinterpret_cast<size_t>(W) & 15) == 0);
+        if (vec) trailing_split<2>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, xch_off, pc);
+        else trailing_split<1>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, xch_off, pc);
+    } else {
+        trailing_split<0>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, xch_off, pc);
+    }
+}
+
 __device__ __forceinline__ void trailing_dispatch(double* __restrict__ W, int ld, int cbeg, int cend, const RowMap& rm,
                                                   unsigned buf_off, int LP, unsigned ts_off, const QTeam tm) {
     if (cbeg >= cend) return;
@@ -682,6 +781,9 @@ static __device__ __noinline__ void householder_qr_fast(double* __restrict__ W, 
     const int uw = warp - kHalf;                                         // 0 .. 3
     const bool pri = in_p ? false : (uw & 1) == 1;                       // warps 5 and 7 take the priority columns
     const QTeam ut_pri{uw >> 1, 2, 2};
+#ifndef PNMOL_SPLIT_PRIORITY
+#define PNMOL_SPLIT_PRIORITY 1
+#endif
 #ifndef PNMOL_U_ODD_ONLY
 #define PNMOL_U_ODD_ONLY 0
 #endif
@@ -698,8 +800,22 @@ static __device__ __noinline__ void householder_qr_fast(double* __restrict__ W, 
         const int j1 = j0 + nbk;                       // first column of the next panel
         const bool more = j1 < nref;
         if (more) {
+            pc.mark(21);
             const int nb1 = nref - j1 < kNB ? nref - j1 : kNB;
             const RowMap rm1 = panel_rows(s, j1, j1 + nb1 - 1);
+            pc.mark(22);
+#if PNMOL_SPLIT_PRIORITY
+            // every warp takes a share of the row tiles of panel k+1's columns (the idle buffer is the exchange area)
+            trailing_split_dispatch(W, ld, j1, j1 + nb1, rm, fq.buf[bi], fq.LP, fq.Ts[bi], fq.buf[bi ^ 1], pc);
+            if (in_p) {
+                asm volatile("bar.sync 3, %0;" ::"r"(kThreads) : "memory");   // columns of panel k+1 are up to date
+                pc.mark(11);
+                panel_factor_dispatch(W, ld, s, j1, nb1, rm1, fq, bi ^ 1, j1 + nb1 < s.ncols, pt, pc);
+            } else {
+                asm volatile("bar.arrive 3, %0;" ::"r"(kThreads) : "memory");
+                trailing_dispatch(W, ld, j1 + nb1, s.ncols, rm, fq.buf[bi], fq.LP, fq.Ts[bi], QTeam{uw, kHalf, 2});
+            }
+#else
             if (in_p) {
                 asm volatile("bar.sync 3, %0;" ::"r"(kHandoff) : "memory");   // columns of panel k+1 are up to date
                 pc.mark(11);
@@ -711,6 +827,7 @@ static __device__ __noinline__ void householder_qr_fast(double* __restrict__ W, 
                 }
                 if (!PNMOL_U_ODD_ONLY || pri) trailing_dispatch(W, ld, j1 + nb1, s.ncols, rm, fq.buf[bi], fq.LP, fq.Ts[bi], ut_far);
             }
+#endif
             __syncthreads();
             pc.mark(12);
             rm = rm1;

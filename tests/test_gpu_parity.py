@@ -489,6 +489,51 @@ def test_ensemble_members_match_individual_oracle_solves(path, monkeypatch):
     assert int(host2.status.max()) == 0
 
 
+@pytest.mark.parametrize("kind,name,num", [("white_linear", "heat", 9), ("white_linear", "heat", 20), ("white_semilinear", "sir", 6),
+                                           ("latent_semilinear", "spruce", 7)])
+def test_one_launch_time_loop_equals_step_by_step(kind, name, num, monkeypatch):
+    """The persistent time loop hands the factor from step to step inside the workspace (it is written to the state only
+    by the last step) and, for a linear PDE, re-uses the loop-invariant Cholesky factor of the error estimate; both must
+    be invisible: states, error estimate, reference state and local diffusions are bitwise those of one launch per step,
+    with several members, a step-size change in the middle, and with the fusion switched off (flag 4)."""
+    from pnmol_b200 import ensemble
+
+    monkeypatch.setenv("PNMOL_B200_PATH", "cta")
+    case = cases.make_case(name, num=num, tmax=0.5)
+    pde = case["pde"]
+    solver = cases.make_solver(kind, case)
+    B = 3
+    rng = np.random.default_rng(5)
+    y0 = np.tile(pde.y0, (B, 1)) * rng.uniform(0.8, 1.2, (B, 1))
+    es = ensemble.EnsembleSolver(solver, pde, y0=y0)
+    eng = es.engine
+    mean0, chol0, _ = es.initialize()
+    dts = np.array([case["dt"]] * 3 + [0.5 * case["dt"]] * 2 + [case["dt"]])
+    m, c, t = mean0.clone(), chol0.clone(), pde.t0
+    diffs = []
+    for dt in dts:
+        m, c, err, ref, diff, status = eng.step(t, dt, m, c)
+        t += dt
+        diffs.append(diff.clone())
+        assert int(status.max()) == 0
+    for flags in (0, 4):
+        m1, c1 = mean0.clone(), chol0.clone()
+        out = eng.run(pde.t0, dts, m1, c1, flags=flags)
+        assert int(out["status"].max()) == 0
+        assert torch.equal(m1.reshape(m.shape), m) and torch.equal(c1.reshape(c.shape), c)
+        assert torch.equal(out["diff_last"], diffs[-1])
+        if err is not None:
+            assert torch.equal(out["err"], err) and torch.equal(out["ref"], ref)
+        assert torch.allclose(out["diff_sum"], torch.stack(diffs).sum(0), rtol=1e-14)
+    # an odd number of steps (result ends in the second state buffer) and a trajectory request (no fusion)
+    m2, c2 = mean0.clone(), chol0.clone()
+    out2 = eng.run(pde.t0, dts[:5], m2, c2, trajectory=True)
+    m3, c3 = mean0.clone(), chol0.clone()
+    eng.run(pde.t0, dts[:5], m3, c3)
+    assert torch.equal(m2, m3) and torch.equal(c2, c3)
+    assert torch.equal(out2["chol_traj"][-1].reshape(c2.shape), c2)
+
+
 def test_ensemble_semilinear_sir_with_member_parameters():
     from oracle import setup_np
     from pnmol_b200 import ensemble

@@ -21,6 +21,6 @@ best = 1e30
 for _ in range(R + 1):
     mean, chol = mean0.clone(), chol0.clone()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); out = es.engine.run(pde.t0, es.dts, mean, chol); e1.record(); torch.cuda.synchronize()
+    e0.record(); out = es.engine.run(pde.t0, es.dts, mean, chol, flags=int(os.environ.get('PNMOL_RUN_FLAGS', '0'))); e1.record(); torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1))
 print(f"{os.environ.get('PNMOL_B200_LIB', 'default')}: members {M} steps {T} best {best:.1f} ms -> {M * T / best * 1e3:.0f} member-steps/s status {int(out['status'].max())}")
