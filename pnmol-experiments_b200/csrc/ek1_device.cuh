@@ -101,6 +101,7 @@ struct FastQR {       // shared-memory buffers of the blocked QR (qr_fast.cuh), 
     unsigned scratch;  // 4 x 192 per-warp Gram partials
     unsigned tau;      // 2 x 16
     unsigned t4;       // 4 x (4 x 4): T factors of the sub-panels of the current panel
+    unsigned ctx;      // 40 doubles: QRCtx, the driver's uniform state (qr_fast.cuh)
     int LP;            // rows of a buffer: 64, 128 or 256, >= every panel row list
     int slot;          // which co-resident CTA of its SM this is (0, 1, ...): decides the factor warp's scheduler
 };
@@ -152,7 +153,7 @@ struct WarpTeam {
 };
 
 __host__ __device__ __forceinline__ size_t fastqr_doubles(int LP) {
-    return 2 * (size_t)16 * LP + 2 * (size_t)16 * 18 + 16 * 17 + 4 * 192 + 2 * 16 + 64;
+    return 2 * (size_t)16 * LP + 2 * (size_t)16 * 18 + 16 * 17 + 4 * 192 + 2 * 16 + 64 + 40;
 }
 
 // vld = rows of a panel buffer (LP of the blocked QR: 64, 128 or 256)
@@ -192,6 +193,7 @@ __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vl
     s.fq.scratch = (unsigned)(base - base0); base += 4 * 192;
     s.fq.tau = (unsigned)(base - base0);    base += 2 * 16;
     s.fq.t4 = (unsigned)(base - base0);     base += 64;
+    s.fq.ctx = (unsigned)(base - base0);    base += 40;
     s.fqend = base;
     s.msq = ldm > 0 ? s.fqbase : nullptr;   // aliases the panel buffers (never live at the same time)
     {

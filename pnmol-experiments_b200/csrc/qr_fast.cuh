@@ -672,15 +672,58 @@ __device__ __forceinline__ void trailing_dispatch(double* __restrict__ W, int ld
     }
 }
 
+// ---------------------------------------------------------------- driver state
+// The uniform state of one blocked QR lives in SHARED memory, not in registers: the phases below are separate
+// (non-inlined) functions that need the whole register file, so every value the driver keeps across a call is spilled
+// to local memory and re-read after it -- ncu attributed half of all long-scoreboard stalls of the step kernel to those
+// reloads (local memory does not fit the small L1 that is left next to ~190 KB of shared memory per SM).  Here every
+// value is read from shared memory where it is used; the only loop-carried registers are the iteration counters.
+struct QRPanel {           // state of one iteration of the panel loop
+    int j0, nbk, bi;       // the panel that has been factored (reflectors in buf[bi]); nbk = 0: none yet
+    int more, j1, nb1;     // the panel to factor now (into buf[bi ^ 1]), if more
+    RowMap rm, rm1;        // their row lists
+};
+struct QRCtx {
+    double* W;
+    int ld, nref;
+    Shape s;
+    FastQR fq;
+    QRPanel pn[2];         // iteration it reads pn[it & 1]; one thread writes pn[(it + 1) & 1] meanwhile
+};
+static_assert(sizeof(QRCtx) <= 40 * sizeof(double), "QRCtx must fit its slot in the FastQR carve-out");
+
+__device__ __forceinline__ QRCtx& qr_ctx(unsigned ctx_off) {
+    extern __shared__ __align__(16) double smem_raw[];
+    return *reinterpret_cast<QRCtx*>(smem_raw + ctx_off);
+}
+// the panel team of this CTA: warps 0 .. 3, team index 0 = the factor warp (see householder_qr_fast)
+__device__ __forceinline__ QTeam panel_team(const QRCtx& cx) {
+    constexpr int kHalf = kWarps / 2;
+    return QTeam{((int)(threadIdx.x >> 5) - 2 * (cx.fq.slot & 1)) & (kHalf - 1), kHalf, 1};
+}
+// state of the iteration after `p` (one thread)
+__device__ __forceinline__ void qr_advance(const QRCtx& cx, const QRPanel& p, QRPanel& q) {
+    q.j0 = p.j1; q.nbk = p.nb1; q.bi = p.bi ^ 1; q.rm = p.rm1;
+    const int j1 = p.j1 + p.nb1;
+    q.more = j1 < cx.nref;
+    q.j1 = j1;
+    q.nb1 = cx.nref - j1 < kNB ? cx.nref - j1 : kNB;
+    if (q.more) q.rm1 = panel_rows(cx.s, j1, j1 + q.nb1 - 1);
+}
+
 // ---------------------------------------------------------------- panel: load, factor, T
 // Load the panel columns j0 .. j0 + nbk - 1 restricted to the row list (entries outside a column's own envelope and
 // the rows [len, 32 R) are zero; absent columns nbk .. kNB - 1 are zero columns).
 template <int R>
-__device__ __forceinline__ void panel_load(const double* __restrict__ W, int ld, const Shape& s, int j0, int nbk,
-                                           const RowMap& rm, unsigned buf_off, int LP, unsigned tau_off, unsigned ts_off,
-                                           const QTeam tm) {
+__device__ __forceinline__ void panel_load(const QRCtx& cx, const QRPanel& p, const QTeam tm) {
     extern __shared__ __align__(16) double smem_raw[];
-    double* buf = smem_raw + buf_off;
+    const int bi = p.bi ^ 1;
+    double* buf = smem_raw + cx.fq.buf[bi];
+    const unsigned ts_off = cx.fq.Ts[bi], tau_off = cx.fq.tau + bi * kNB;
+    const int LP = cx.fq.LP, ld = cx.ld, j0 = p.j1, nbk = p.nb1;
+    const double* __restrict__ W = cx.W;
+    const RowMap rm = p.rm1;
+    const Shape s = cx.s;
     const int lane = threadIdx.x & 31;
     for (int e = tm.w * 32 + lane; e < kNB * kLdr; e += tm.nw * 32) smem_raw[ts_off + e] = 0.0;  // T starts as zero
     constexpr int CMAX = 4;  // columns per warp (teams of >= 4 warps)
@@ -688,9 +731,9 @@ __device__ __forceinline__ void panel_load(const double* __restrict__ W, int ld,
     // every load of the warp is issued before the first shared-memory store (one L2 round trip per panel)
 #pragma unroll
     for (int q = 0; q < CMAX; ++q) {
-        const int p = tm.w + q * tm.nw;
-        const bool valid = p < nbk;
-        const int jp = j0 + (valid ? p : 0);
+        const int pc_ = tm.w + q * tm.nw;
+        const bool valid = pc_ < nbk;
+        const int jp = j0 + (valid ? pc_ : 0);
         const int et = env_top(s, jp), eb = env_bot(s, jp);
         const double* col = W + (size_t)jp * ld;
 #pragma unroll
@@ -703,59 +746,69 @@ __device__ __forceinline__ void panel_load(const double* __restrict__ W, int ld,
     }
 #pragma unroll
     for (int q = 0; q < CMAX; ++q) {
-        const int p = tm.w + q * tm.nw;
-        if (p < kNB) {
-            const int sw = vsw(p);
-            double* dst = buf + (size_t)p * LP;
+        const int pc_ = tm.w + q * tm.nw;
+        if (pc_ < kNB) {
+            const int sw = vsw(pc_);
+            double* dst = buf + (size_t)pc_ * LP;
 #pragma unroll
             for (int r = 0; r < R; ++r) dst[(lane ^ sw) + 32 * r] = v[q][r];
-            if (lane == 0) smem_raw[tau_off + p] = 0.0;
+            if (lane == 0) smem_raw[tau_off + pc_] = 0.0;
         }
     }
 }
 
+// Factor the panel (p.j1, p.nb1, p.rm1) into buf[p.bi ^ 1].  Everything is re-read from shared memory at its point of
+// use (see QRCtx); c0 is the only register that lives across the calls.
 template <int R>
-__device__ __forceinline__ void panel_factor(double* __restrict__ W, int ld, const Shape& s, int j0, int nbk, const RowMap& rm,
-                                             const FastQR& fq, int bi, const QTeam tm, PhaseClock& pc) {
-    const unsigned buf_off = fq.buf[bi], tau_off = fq.tau + bi * kNB, ts_off = fq.Ts[bi];
-    const int LP = fq.LP;
-    const int ntile = (rm.len + 7) >> 3;
-    panel_load<R>(W, ld, s, j0, nbk, rm, buf_off, LP, tau_off, ts_off, tm);
-    tm.sync();
-    pc.mark(8);
-    const QTeam helpers{tm.w - 1, tm.nw - 1, -1};
-    const bool t_helper = tm.w >= 1 && tm.w <= 3;
-#pragma unroll 1
-    for (int c0 = 0; c0 < nbk; c0 += 4) {
-        const int nc = nbk - c0 < 4 ? nbk - c0 : 4;
-        const int sidx = c0 >> 2;
-        if (tm.w == 0) {
-            subpanel_factor<R>(buf_off, LP, c0, nc, tau_off, fq.t4 + 16 * sidx, W + (size_t)j0 * ld, ld, rm);
-        } else if (c0 > 0) {
-            // hidden behind the factor warp: the previous sub-panel's reflectors applied to the columns beyond this
-            // sub-panel, and the previous sub-panel's T columns
-            subpanel_apply<R>(buf_off, LP, c0 - 4, c0 + 4, nbk, fq.t4 + 16 * (sidx - 1), helpers);
-            if (t_helper) t_extend(buf_off, LP, ntile, sidx - 1, ts_off, fq.t4 + 16 * (sidx - 1), fq.scratch, tm.w - 1);
-        }
+__device__ __forceinline__ void panel_factor(const QRCtx& cx, const QRPanel& p, PhaseClock& pc) {
+    {
+        const QTeam tm = panel_team(cx);
+        panel_load<R>(cx, p, tm);
         tm.sync();
+    }
+    pc.mark(8);
+#pragma unroll 1
+    for (int c0 = 0; c0 < p.nb1; c0 += 4) {
+        {
+            const QTeam tm = panel_team(cx);
+            const int bi = p.bi ^ 1, nbk = p.nb1, sidx = c0 >> 2;
+            const unsigned buf_off = cx.fq.buf[bi];
+            if (tm.w == 0) {
+                subpanel_factor<R>(buf_off, cx.fq.LP, c0, nbk - c0 < 4 ? nbk - c0 : 4, cx.fq.tau + bi * kNB, cx.fq.t4 + 16 * sidx,
+                                   cx.W + (size_t)p.j1 * cx.ld, cx.ld, p.rm1);
+            } else if (c0 > 0) {
+                // hidden behind the factor warp: the previous sub-panel's reflectors applied to the columns beyond this
+                // sub-panel, and the previous sub-panel's T columns
+                subpanel_apply<R>(buf_off, cx.fq.LP, c0 - 4, c0 + 4, nbk, cx.fq.t4 + 16 * (sidx - 1), QTeam{tm.w - 1, tm.nw - 1, -1});
+                if (tm.w <= 3)
+                    t_extend(cx.fq.buf[p.bi ^ 1], cx.fq.LP, (p.rm1.len + 7) >> 3, (c0 >> 2) - 1, cx.fq.Ts[p.bi ^ 1],
+                             cx.fq.t4 + 16 * ((c0 >> 2) - 1), cx.fq.scratch, (int)panel_team(cx).w - 1);
+            }
+        }
+        panel_team(cx).sync();
         pc.mark(9);
-        if (c0 + 4 < nbk) {  // critical: the columns of the next sub-panel only
-            subpanel_apply<R>(buf_off, LP, c0, c0 + 4, c0 + 8 < nbk ? c0 + 8 : nbk, fq.t4 + 16 * sidx, tm);
-            tm.sync();
+        if (c0 + 4 < p.nb1) {  // critical: the columns of the next sub-panel only
+            const int nbk = p.nb1;
+            subpanel_apply<R>(cx.fq.buf[p.bi ^ 1], cx.fq.LP, c0, c0 + 4, c0 + 8 < nbk ? c0 + 8 : nbk, cx.fq.t4 + 16 * (c0 >> 2),
+                              panel_team(cx));
+            panel_team(cx).sync();
             pc.mark(10);
         }
     }
-    if (t_helper) t_extend(buf_off, LP, ntile, (nbk - 1) >> 2, ts_off, fq.t4 + 16 * ((nbk - 1) >> 2), fq.scratch, tm.w - 1);
+    {
+        const int w = panel_team(cx).w;
+        if (w >= 1 && w <= 3)
+            t_extend(cx.fq.buf[p.bi ^ 1], cx.fq.LP, (p.rm1.len + 7) >> 3, (p.nb1 - 1) >> 2, cx.fq.Ts[p.bi ^ 1],
+                     cx.fq.t4 + 16 * ((p.nb1 - 1) >> 2), cx.fq.scratch, w - 1);
+    }
     pc.mark(14);
 }
 
-__device__ __forceinline__ void panel_factor_dispatch(double* __restrict__ W, int ld, const Shape& s, int j0, int nbk,
-                                                      const RowMap& rm, const FastQR& fq, int bi, bool need_t, const QTeam tm,
-                                                      PhaseClock& pc) {
-    (void)need_t;
-    if (rm.len <= 64) panel_factor<2>(W, ld, s, j0, nbk, rm, fq, bi, tm, pc);
-    else if (rm.len <= 128) panel_factor<4>(W, ld, s, j0, nbk, rm, fq, bi, tm, pc);
-    else panel_factor<8>(W, ld, s, j0, nbk, rm, fq, bi, tm, pc);
+__device__ __forceinline__ void panel_factor_dispatch(const QRCtx& cx, const QRPanel& p, PhaseClock& pc) {
+    const int len = p.rm1.len;
+    if (len <= 64) panel_factor<2>(cx, p, pc);
+    else if (len <= 128) panel_factor<4>(cx, p, pc);
+    else panel_factor<8>(cx, p, pc);
 }
 
 // ---------------------------------------------------------------- driver
@@ -766,79 +819,53 @@ __device__ __forceinline__ void panel_factor_dispatch(double* __restrict__ W, in
 //     the first CTA of an SM and warp 2 in the second (fq.slot), so that the chains of two co-resident CTAs never share
 //     a scheduler and its FP64 pipe (measured: 218 k -> 300 k member-steps/s);
 //   * update team = warps 4 .. 7: the tensor-core trailing updates.
-// Once panel k is factored, update warps 5 and 7 (schedulers 1 and 3: never a chain's) apply it to the columns of panel
-// k+1, one column group each, and release the panel team through a named barrier; the panel team then loads and
-// factors panel k+1 into the other buffer (T factor included) while the update team applies panel k to the columns
-// beyond.  One block barrier per panel joins the teams.
+// Iteration k: (1) ALL warps bring the columns of panel k up to date with panel k-1 (trailing_split: the row tiles of
+// the 16 columns split over the 8 warps, partial products exchanged through shared memory); (2) the panel team loads
+// and factors panel k into the other buffer (T factor included) while the update team applies panel k-1 to the columns
+// beyond panel k; (3) one block barrier joins the teams.
 static __device__ __noinline__ void householder_qr_fast(double* __restrict__ W, int ld, const Shape s, const FastQR fq, PhaseClock& pc) {
-    const int warp = threadIdx.x >> 5;
-    const int nrows = s.nt + s.nbot;
-    const int nref = nrows < s.ncols ? nrows : s.ncols;
-    const QTeam all{warp, kWarps, 0};
     constexpr int kHalf = kWarps / 2;
-    const bool in_p = warp < kHalf;
-    const QTeam pt{(warp - 2 * (fq.slot & 1)) & (kHalf - 1), kHalf, 1};   // team index 0 = factor warp
-    const int uw = warp - kHalf;                                         // 0 .. 3
-    const bool pri = in_p ? false : (uw & 1) == 1;                       // warps 5 and 7 take the priority columns
-    const QTeam ut_pri{uw >> 1, 2, 2};
-#ifndef PNMOL_SPLIT_PRIORITY
-#define PNMOL_SPLIT_PRIORITY 1
-#endif
-#ifndef PNMOL_U_ODD_ONLY
-#define PNMOL_U_ODD_ONLY 0
-#endif
-    // PNMOL_U_ODD_ONLY: only warps 5 and 7 do trailing updates (no DMMA on the schedulers of the two chains)
-    const QTeam ut_far = PNMOL_U_ODD_ONLY ? QTeam{uw >> 1, 2, 2} : QTeam{pri ? 2 + (uw >> 1) : (uw >> 1), kHalf, 2};
-    constexpr int kHandoff = (kHalf + 2) * 32;                           // panel team + the two priority warps
-    int bi = 0;
-    int nbk = nref < kNB ? nref : kNB;
-    RowMap rm = panel_rows(s, 0, nbk - 1);
-    panel_factor_dispatch(W, ld, s, 0, nbk, rm, fq, bi, nbk < s.ncols, all, pc);
-    __syncthreads();
-    pc.mark(12);
-    for (int j0 = 0; j0 < nref; j0 += kNB) {
-        const int j1 = j0 + nbk;                       // first column of the next panel
-        const bool more = j1 < nref;
-        if (more) {
-            pc.mark(21);
-            const int nb1 = nref - j1 < kNB ? nref - j1 : kNB;
-            const RowMap rm1 = panel_rows(s, j1, j1 + nb1 - 1);
-            pc.mark(22);
-#if PNMOL_SPLIT_PRIORITY
-            // every warp takes a share of the row tiles of panel k+1's columns (the idle buffer is the exchange area)
-            trailing_split_dispatch(W, ld, j1, j1 + nb1, rm, fq.buf[bi], fq.LP, fq.Ts[bi], fq.buf[bi ^ 1], pc);
-            if (in_p) {
-                asm volatile("bar.sync 3, %0;" ::"r"(kThreads) : "memory");   // columns of panel k+1 are up to date
-                pc.mark(11);
-                panel_factor_dispatch(W, ld, s, j1, nb1, rm1, fq, bi ^ 1, j1 + nb1 < s.ncols, pt, pc);
-            } else {
-                asm volatile("bar.arrive 3, %0;" ::"r"(kThreads) : "memory");
-                trailing_dispatch(W, ld, j1 + nb1, s.ncols, rm, fq.buf[bi], fq.LP, fq.Ts[bi], QTeam{uw, kHalf, 2});
-            }
-#else
-            if (in_p) {
-                asm volatile("bar.sync 3, %0;" ::"r"(kHandoff) : "memory");   // columns of panel k+1 are up to date
-                pc.mark(11);
-                panel_factor_dispatch(W, ld, s, j1, nb1, rm1, fq, bi ^ 1, j1 + nb1 < s.ncols, pt, pc);
-            } else {
-                if (pri) {
-                    trailing_dispatch(W, ld, j1, j1 + nb1, rm, fq.buf[bi], fq.LP, fq.Ts[bi], ut_pri);
-                    asm volatile("bar.arrive 3, %0;" ::"r"(kHandoff) : "memory");
-                }
-                if (!PNMOL_U_ODD_ONLY || pri) trailing_dispatch(W, ld, j1 + nb1, s.ncols, rm, fq.buf[bi], fq.LP, fq.Ts[bi], ut_far);
-            }
-#endif
-            __syncthreads();
-            pc.mark(12);
-            rm = rm1;
-            nbk = nb1;
-            bi ^= 1;
-        } else {
-            if (j1 < s.ncols) trailing_dispatch(W, ld, j1, s.ncols, rm, fq.buf[bi], fq.LP, fq.Ts[bi], all);
-            __syncthreads();
-            pc.mark(11);
-        }
+    QRCtx& cx = qr_ctx(fq.ctx);
+    if (threadIdx.x == 0) {
+        cx.W = W; cx.ld = ld; cx.s = s; cx.fq = fq;
+        const int nrows = s.nt + s.nbot;
+        const int nref = nrows < s.ncols ? nrows : s.ncols;
+        cx.nref = nref;
+        QRPanel& p = cx.pn[0];   // nothing factored yet; the first panel is "next"
+        p.j0 = 0; p.nbk = 0; p.bi = 1; p.rm = RowMap{0, 0, 0, 0, false};
+        p.more = nref > 0; p.j1 = 0; p.nb1 = nref < kNB ? nref : kNB;
+        p.rm1 = panel_rows(s, 0, p.nb1 - 1);
     }
+    __syncthreads();
+    int it = 0;
+#pragma unroll 1
+    for (;; ++it) {
+        const QRPanel& p = cx.pn[it & 1];
+        if (!p.more) break;
+        if (threadIdx.x == kThreads - 1) qr_advance(cx, p, cx.pn[(it + 1) & 1]);
+        if (p.nbk > 0)   // (the idle Gram + scratch block is the exchange area)
+            trailing_split_dispatch(cx.W, cx.ld, p.j1, p.j1 + p.nb1, p.rm, cx.fq.buf[p.bi], cx.fq.LP, cx.fq.Ts[p.bi], cx.fq.Gs, pc);
+        if ((threadIdx.x >> 5) < kHalf) {
+            asm volatile("bar.sync 3, %0;" ::"r"(kThreads) : "memory");   // columns of the panel are up to date
+            pc.mark(11);
+            panel_factor_dispatch(cx, p, pc);
+        } else {
+            asm volatile("bar.arrive 3, %0;" ::"r"(kThreads) : "memory");
+            if (p.nbk > 0)
+                trailing_dispatch(cx.W, cx.ld, p.j1 + p.nb1, cx.s.ncols, p.rm, cx.fq.buf[p.bi], cx.fq.LP, cx.fq.Ts[p.bi],
+                                  QTeam{(int)(threadIdx.x >> 5) - kHalf, kHalf, 2});
+        }
+        __syncthreads();
+        pc.mark(12);
+    }
+    {   // the last panel: applied to the columns beyond it by all warps
+        const QRPanel& p = cx.pn[it & 1];
+        if (p.nbk > 0 && p.j0 + p.nbk < cx.s.ncols)
+            trailing_dispatch(cx.W, cx.ld, p.j0 + p.nbk, cx.s.ncols, p.rm, cx.fq.buf[p.bi], cx.fq.LP, cx.fq.Ts[p.bi],
+                              QTeam{(int)(threadIdx.x >> 5), kWarps, 0});
+    }
+    __syncthreads();
+    pc.mark(11);
 }
 
 }  // namespace pnmol
