@@ -638,7 +638,7 @@ __device__ void error_estimate_global(const Problem& P, int b, const Smem& sm, d
 template <class T = CtaTeam>
 __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode,
                                     const int32_t* Hcol, const double* Hval, double* err_out, double* Sg = nullptr,
-                                    double* Fg = nullptr, double* key = nullptr) {
+                                    double* Fg = nullptr, double* key = nullptr, bool defer_solve = false) {
     const int tid = T::tid(), lane = tid & 31, warp = T::warp();
     const int n = P.n, d = P.d, m = P.m, ldm = P.ldm;
     // Loop-invariant factor: for a linear PDE the rows of H depend on the member and on the Nordsieck scaling (dt) only,
@@ -745,6 +745,8 @@ __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, dou
     }  // (factor computed or re-read)
     double* S = sm.msq;
     T::sync();
+    // (defer_solve: the caller runs error_estimate_solve_warp on one warp next to other work and writes err_out itself)
+    if (defer_solve) return;
     // forward solve L u = z by warp 0 (column oriented: each lane owns rows lane, lane + 32, lane + 64)
     if (warp == 0) {
         double u[3], acc[3];
@@ -775,11 +777,41 @@ __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, dou
     T::sync();
 }
 
+// The forward solve of error_estimate_smem on ONE warp (S, the diagonal of L in sm.xw and z are in shared memory):
+// sigma = sqrt(|L^-1 z|^2 / m) -> sm.red[15].  Same operations as the solve inside error_estimate_smem.
+__device__ __forceinline__ void error_estimate_solve_warp(const Problem& P, const Smem& sm) {
+    const int lane = threadIdx.x & 31;
+    const int m = P.m, ldm = P.ldm;
+    const double* S = sm.msq;
+    double u[3], acc[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { const int r = lane + 32 * q; u[q] = r < m ? sm.z[r] : 0.0; acc[q] = 0.0; }
+    for (int k = 0; k < m; ++k) {
+        const int q = k >> 5;
+        double cand = q == 0 ? u[0] - acc[0] : q == 1 ? u[1] - acc[1] : u[2] - acc[2];
+        cand /= sm.xw[k];
+        const double uk = __shfl_sync(0xffffffffu, cand, k & 31);
+#pragma unroll
+        for (int qq = 0; qq < 3; ++qq) {
+            const int r = lane + 32 * qq;
+            if (r > k && r < m) acc[qq] = fma(S[r * ldm + k], uk, acc[qq]);
+            if (r == k) u[qq] = uk;
+        }
+    }
+    double part = 0.0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { const int r = lane + 32 * q; if (r < m) part = fma(u[q], u[q], part); }
+    part = warp_sum(part);
+    if (lane == 0) sm.red[15] = sqrt(part / m);
+}
+
 template <class T = CtaTeam>
 __device__ void error_estimate(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode, double nugget,
-                               const int32_t* Hcol, const double* Hval, double* F, double* S, double* err_out) {
+                               const int32_t* Hcol, const double* Hval, double* F, double* S, double* err_out,
+                               bool defer_solve = false) {
     if (P.ldm > 0 && P.m <= 96)
-        error_estimate_smem<T>(P, b, sm, p1s, dt, emode, Hcol, Hval, err_out, S, F, T::size == kThreads ? sm.ekey : nullptr);
+        error_estimate_smem<T>(P, b, sm, p1s, dt, emode, Hcol, Hval, err_out, S, F, T::size == kThreads ? sm.ekey : nullptr,
+                               defer_solve);
     else
         error_estimate_global<T>(P, b, sm, p1s, dt, emode, nugget, Hcol, Hval, F, S, err_out);
 }
@@ -815,6 +847,11 @@ struct UpdateOut {
     double* diff_out;  // scalar or nullptr
     double* ref_out;   // (d) or nullptr
     bool scale_by_p;   // multiply by the Nordsieck preconditioner on output
+    // Deferred error estimate (error_estimate(..., defer_solve = true) has left S in shared memory): its forward solve
+    // runs on warp 0 while the other warps assemble the left block of the update matrix.
+    bool err_solve = false;
+    double err_dt = 0.0;
+    double* err_out = nullptr;
 };
 
 // ---- part 1a: right block (rows 0..k hold R, copied from Rsrc if given; the rest of the envelope is zero)
@@ -1142,8 +1179,18 @@ static __device__ void update_stage(const Problem& P, int b, const Smem& sm, int
 
     update_build_right(P, mcur, nrows, Rsrc, te, be, Wr, warp, kWarps);
     __syncthreads();
-    update_build_left(P, b, mcur, nrows, emode, nugget, te, be, Hcol, Hval, Wl, Wr, warp, kWarps);
-    __syncthreads();
+    if (out.err_solve) {
+        if (warp == 0) error_estimate_solve_warp(P, sm);
+        else update_build_left(P, b, mcur, nrows, emode, nugget, te, be, Hcol, Hval, Wl, Wr, warp - 1, kWarps - 1);
+        __syncthreads();
+        if (out.err_out) {   // white.py:160-162 (sm.y = diag(S) is overwritten only by update_solve, after the QR)
+            const double sigma = sm.red[15];
+            for (int i = tid; i < P.d; i += kThreads) out.err_out[i] = out.err_dt * (sqrt(sm.y[i]) * sigma);
+        }
+    } else {
+        update_build_left(P, b, mcur, nrows, emode, nugget, te, be, Hcol, Hval, Wl, Wr, warp, kWarps);
+        __syncthreads();
+    }
 
     pc.mark(4);
     Shape sh;

@@ -68,12 +68,17 @@ static __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& s
     sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? sm.te_pd : sm.te_p; sp.be = sm.be_p; sp.ldr = P.ld;
     householder_qr_fast(W + (size_t)P.m * P.ld, P.ld, sp, sm.fq, pc);
     pc.mark(2);
-    if (!P.latent && !(flags & 2)) {
+    // small m: the error estimate's forward solve is deferred into update_stage (one warp, next to the build of the
+    // update matrix); its assembly / cached factor is set up here by all threads
+    const bool est = !P.latent && !(flags & 2);
+    const bool defer = est && P.ldm > 0 && P.m <= 96;
+    if (est) {
         error_estimate(P, b, sm, sm.pv[1], dt, E_STEP_WHITE, 0.0, Hcol, Hval, P.F + (size_t)slot * P.m * P.d,
-                       P.S + (size_t)slot * P.m * P.m, err_out);
+                       P.S + (size_t)slot * P.m * P.m, err_out, defer);
     }
     pc.mark(3);
     UpdateOut out;
+    out.err_solve = defer; out.err_dt = dt; out.err_out = err_out;
     out.mean_out = mean_out; out.chol_out = write_factor ? chol_out : nullptr; out.diff_out = diff_out;
     out.ref_out = P.latent ? nullptr : ref_out; out.scale_by_p = true;
     update_stage(P, b, sm, P.m, P.latent ? E_NONE : E_STEP_WHITE, 0.0, nullptr, sm.te_u, sm.be_u, Hcol, Hval, W, out,

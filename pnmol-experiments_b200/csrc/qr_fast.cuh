@@ -71,6 +71,7 @@ __device__ __noinline__ void subpanel_factor(unsigned buf_off, int LP, int c0, i
         for (int r = 0; r < R; ++r) x[q][r] = col[(lane ^ sw) + 32 * r];  // (absent columns were loaded as zero columns)
     }
     double tauv[4];
+    double gq[6];  // v_j . v_i for (j, i) = 01 02 03 12 13 23 (Gram entries of the sub-panel's T factor)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         {   // (an absent column, i >= nc, is a zero column: tau = 0, H = I, nothing is written to the workspace)
@@ -96,19 +97,28 @@ __device__ __noinline__ void subpanel_factor(unsigned buf_off, int LP, int c0, i
                     red[k] = a0 + a1;
                 }
             }
-            double e[4];
+            // ... and, in the slots of the finished columns j < i, v_j . x_i over the same rows: the Gram entries of the
+            // sub-panel's T factor ride along in this round instead of a reduction round of their own after the loop
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < i) {
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int r = 0; r < R; r += 2) { a0 = fma(x[j][r], t[r], a0); a1 = fma(x[j][r + 1], t[r + 1], a1); }
+                    red[j] = a0 + a1;
+                }
+            }
+            double e[4];   // k > i: x_k at the diagonal row; j < i: v_j at the diagonal row
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (k > i) e[k] = __shfl_sync(0xffffffffu, x[k][0], p);
+                if (k != i) e[k] = __shfl_sync(0xffffffffu, x[k][0], p);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 double tmp[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (k >= i) tmp[k] = __shfl_xor_sync(0xffffffffu, red[k], o);
+                for (int k = 0; k < 4; ++k) tmp[k] = __shfl_xor_sync(0xffffffffu, red[k], o);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (k >= i) red[k] += tmp[k];
+                for (int k = 0; k < 4; ++k) red[k] += tmp[k];
             }
             const double ss = red[i];
             // dlarfg on (alpha, ||x||^2): beta = -sign(alpha) ||(alpha, x)||, tau = (beta - alpha) / beta, v = x / (alpha - beta)
@@ -122,6 +132,10 @@ __device__ __noinline__ void subpanel_factor(unsigned buf_off, int LP, int c0, i
                 scale = __drcp_rn(al - beta);
             }
             tauv[i] = tau;
+            // v_j . v_i = scale_i (v_j . x_i below the diagonal) + v_j[diagonal row of i]   (v_i = 0 when H = I)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < i) gq[j == 0 ? i - 1 : j == 1 ? i + 1 : 5] = tau != 0.0 ? fma(scale, red[j], e[j]) : 0.0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (k > i) {
@@ -141,20 +155,6 @@ __device__ __noinline__ void subpanel_factor(unsigned buf_off, int LP, int c0, i
         }
     }
     // T factor of the sub-panel (dlarft, forward / columnwise): T[i][i] = tau_i, T[0:k, k] = -tau_k T[0:k, 0:k] (V^T v_k)[0:k]
-    double gq[6];  // v_i . v_k for (i, k) = 01 02 03 12 13 23
-    {
-        int idx = 0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int k = i + 1; k < 4; ++k) {
-                double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                for (int r = 0; r < R; r += 2) { a0 = fma(x[i][r], x[k][r], a0); a1 = fma(x[i][r + 1], x[k][r + 1], a1); }
-                gq[idx++] = a0 + a1;
-            }
-    }
-    warp_sum_n<6>(gq);
     const double t00 = tauv[0], t11 = tauv[1], t22 = tauv[2], t33 = tauv[3];
     const double t01 = -t11 * (t00 * gq[0]);
     const double t02 = -t22 * fma(t01, gq[3], t00 * gq[1]);
