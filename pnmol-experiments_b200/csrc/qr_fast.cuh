@@ -696,10 +696,27 @@ __device__ __forceinline__ QRCtx& qr_ctx(unsigned ctx_off) {
     extern __shared__ __align__(16) double smem_raw[];
     return *reinterpret_cast<QRCtx*>(smem_raw + ctx_off);
 }
-// the panel team of this CTA: warps 0 .. 3, team index 0 = the factor warp (see householder_qr_fast)
+// Teams by scheduler (a warp's scheduler is its index mod 4).  PNMOL_TEAMS_BY_SCHED = 1: the panel team is the EVEN warps
+// (schedulers 0 and 2: the two chains of an SM and their helpers), the update team the ODD warps (schedulers 1 and 3), so
+// that the tensor-pipe trailing updates -- a DMMA holds its scheduler's FP64 pipe for 16 cycles -- never sit on a scheduler
+// that runs a dependent per-column chain.  0: panel team = warps 0 .. 3, update team = warps 4 .. 7.
+#ifndef PNMOL_TEAMS_BY_SCHED
+#define PNMOL_TEAMS_BY_SCHED 0   // measured: 410 k (1) vs 419 k (0) member-steps/s at C5
+#endif
+__device__ __forceinline__ bool in_panel_team() {
+    const int warp = threadIdx.x >> 5;
+    return PNMOL_TEAMS_BY_SCHED ? (warp & 1) == 0 : warp < kWarps / 2;
+}
+__device__ __forceinline__ int update_team_index() {
+    const int warp = threadIdx.x >> 5;
+    return PNMOL_TEAMS_BY_SCHED ? warp >> 1 : warp - kWarps / 2;
+}
+// the panel team of this CTA, team index 0 = the factor warp: warp 0 in the first CTA of an SM, warp 2 in the second
 __device__ __forceinline__ QTeam panel_team(const QRCtx& cx) {
     constexpr int kHalf = kWarps / 2;
-    return QTeam{((int)(threadIdx.x >> 5) - 2 * (cx.fq.slot & 1)) & (kHalf - 1), kHalf, 1};
+    const int warp = threadIdx.x >> 5;
+    if (PNMOL_TEAMS_BY_SCHED) return QTeam{((warp >> 1) - (cx.fq.slot & 1)) & (kHalf - 1), kHalf, 1};
+    return QTeam{(warp - 2 * (cx.fq.slot & 1)) & (kHalf - 1), kHalf, 1};
 }
 // state of the iteration after `p` (one thread)
 __device__ __forceinline__ void qr_advance(const QRCtx& cx, const QRPanel& p, QRPanel& q) {
@@ -845,7 +862,7 @@ static __device__ __noinline__ void householder_qr_fast(double* __restrict__ W, 
         if (threadIdx.x == kThreads - 1) qr_advance(cx, p, cx.pn[(it + 1) & 1]);
         if (p.nbk > 0)   // (the idle Gram + scratch block is the exchange area)
             trailing_split_dispatch(cx.W, cx.ld, p.j1, p.j1 + p.nb1, p.rm, cx.fq.buf[p.bi], cx.fq.LP, cx.fq.Ts[p.bi], cx.fq.Gs, pc);
-        if ((threadIdx.x >> 5) < kHalf) {
+        if (in_panel_team()) {
             asm volatile("bar.sync 3, %0;" ::"r"(kThreads) : "memory");   // columns of the panel are up to date
             pc.mark(11);
             panel_factor_dispatch(cx, p, pc);
@@ -853,7 +870,7 @@ static __device__ __noinline__ void householder_qr_fast(double* __restrict__ W, 
             asm volatile("bar.arrive 3, %0;" ::"r"(kThreads) : "memory");
             if (p.nbk > 0)
                 trailing_dispatch(cx.W, cx.ld, p.j1 + p.nb1, cx.s.ncols, p.rm, cx.fq.buf[p.bi], cx.fq.LP, cx.fq.Ts[p.bi],
-                                  QTeam{(int)(threadIdx.x >> 5) - kHalf, kHalf, 2});
+                                  QTeam{update_team_index(), kHalf, 2});
         }
         __syncthreads();
         pc.mark(12);

@@ -14,4 +14,4 @@ PNMOL_B200_LIB=$PWD/tools/variants/prof.so python tools/phase_profile.py 592 48 
 PNMOL_B200_LIB=$PWD/tools/variants/prof.so python tools/phase_profile.py 148 48 >> gpurun_out/fin_phase_c5.txt 2>&1
 PNMOL_B200_LIB=$PWD/tools/variants/prof.so python tools/phase_profile_small.py 6 16384 > gpurun_out/fin_phase_small.txt 2>&1
 python tools/parity_margins.py gpurun_out/fin_parity_margins.json > gpurun_out/fin_margins.log 2>&1
-tail -3 gpurun_out/fin_pytest_gpu.log; cut -c1-400 gpurun_out/fin_bench.json; tail -2 gpurun_out/fin_ncu_c5.log gpurun_out/fin_ncu_small.log
+tail -3 gpurun_out/fin_pytest_gpu.log; cut -c1-400 gpurun_out/fin_bench.json; tail -n 2 gpurun_out/fin_ncu_c5.log; tail -n 2 gpurun_out/fin_ncu_small.log
