@@ -17,6 +17,7 @@
 using namespace pnmol;
 
 namespace {
+constexpr unsigned kPaceRing = 16;   // pace-keeping counters per handle (one per launch in flight)
 
 thread_local std::string g_err;
 std::atomic<int64_t> g_launches{0};
@@ -94,6 +95,8 @@ int max_panel_len(int nt, int nbot, int ncols, const int32_t* te, const int32_t*
 
 struct pnmol_b200_handle {
     int kind, device, grid, num_sms;
+    unsigned* gsync = nullptr;      // ring of pace-keeping counters (launch_run)
+    unsigned gsync_next = 0;
     Problem P;
     std::vector<void*> allocs;
     size_t smem_bytes, smem_optin;
@@ -244,7 +247,16 @@ int launch_run(pnmol_b200_handle* h, RunArgs& a, cudaStream_t st) {
         if (rc) return rc;
     } else {
         CU(cudaMemsetAsync(h->P.smslot, 0, sizeof(int) * h->num_sms, st));
-        k_run<<<h->grid, kThreads, h->smem_bytes, st>>>(h->P, a);
+        // pace keeping (ek1_kernels.cuh): one counter per launch out of a ring, so that launches of the same handle on
+        // different streams (the chunked host route) never share one; PNMOL_B200_PACE=0 switches it off
+        static const bool pace = [] { const char* e = std::getenv("PNMOL_B200_PACE"); return !e || std::atoi(e) != 0; }();
+        Problem P = h->P;
+        P.gsync = nullptr;
+        if (pace && h->gsync && a.nsteps > 1 && h->grid > 1) {
+            P.gsync = h->gsync + (h->gsync_next++ % kPaceRing);
+            CU(cudaMemsetAsync(P.gsync, 0, sizeof(unsigned), st));
+        }
+        k_run<<<h->grid, kThreads, h->smem_bytes, st>>>(P, a);
     }
     ++g_launches;
     return 0;
@@ -306,6 +318,9 @@ int pnmol_b200_create(pnmol_b200_handle** out, int kind, int d, int num_derivati
     {
         int rc = dev_alloc(h, &P.smslot, (size_t)h->num_sms);
         if (rc) { delete h; return rc; }
+        rc = dev_alloc(h, &h->gsync, (size_t)kPaceRing);
+        if (rc) { delete h; return rc; }
+        P.gsync = nullptr;
     }
     *out = h;
     return 0;
@@ -503,6 +518,9 @@ int pnmol_b200_set_operator(pnmol_b200_handle* h, const int32_t* L_col, const do
     int want = PNMOL_MIN_CTAS;
     if (const char* e = std::getenv("PNMOL_B200_CTAS_PER_SM")) want = std::max(1, std::atoi(e));
     occ = std::max(1, std::min(occ, want));
+    if (std::getenv("PNMOL_B200_VERBOSE"))
+        fprintf(stderr, "pnmol_b200: CTA-per-member path: D=%d m=%d wh=%d (H rows in %s), %zu bytes of dynamic shared memory per CTA, %d CTA(s) per SM\n",
+                P.D, P.m, P.wh, P.whs ? "shared memory" : "global scratch", h->smem_bytes, occ);
     h->grid = std::min(P.batch, occ * h->num_sms);
     if (const char* e = std::getenv("PNMOL_B200_GRID")) h->grid = std::max(1, std::min(h->grid, std::atoi(e)));  // tuning
     const size_t wsz = (size_t)P.ld * (P.m + P.D);

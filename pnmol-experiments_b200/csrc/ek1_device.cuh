@@ -59,6 +59,7 @@ struct Problem {
     double* W; int32_t* Hcol; double* Hval; double* F; double* S;
     unsigned long long* prof;  // optional clock64 phase accumulators (diagnostics)
     int* smslot;               // [number of SMs] zeroed before every launch: CTAs count themselves per SM
+    unsigned* gsync;           // pace-keeping counter of this launch (k_run), zeroed before the launch; nullptr: off
 };
 
 // Phase timer: thread 0 of every CTA adds the cycles since the previous mark to prof[idx].
@@ -153,7 +154,7 @@ struct WarpTeam {
 };
 
 __host__ __device__ __forceinline__ size_t fastqr_doubles(int LP) {
-    return 2 * (size_t)16 * LP + 2 * (size_t)16 * 18 + 16 * 17 + 4 * 192 + 2 * 16 + 64 + 40;
+    return 2 * (size_t)16 * LP + 2 * (size_t)16 * 18 + 4 * 192 + 2 * 16 + 64 + 40;
 }
 
 // vld = rows of a panel buffer (LP of the blocked QR: 64, 128 or 256)
@@ -189,7 +190,7 @@ __device__ __forceinline__ Smem carve(double* base, int D, int m, int dd, int vl
     s.fq.buf[1] = (unsigned)(base - base0); base += (size_t)16 * vld;
     s.fq.Ts[0] = (unsigned)(base - base0);  base += 16 * 18;
     s.fq.Ts[1] = (unsigned)(base - base0);  base += 16 * 18;
-    s.fq.Gs = (unsigned)(base - base0);     base += 16 * 17;
+    s.fq.Gs = (unsigned)(base - base0);     // (unused by the CTA-per-member path; no room reserved)
     s.fq.scratch = (unsigned)(base - base0); base += 4 * 192;
     s.fq.tau = (unsigned)(base - base0);    base += 2 * 16;
     s.fq.t4 = (unsigned)(base - base0);     base += 64;

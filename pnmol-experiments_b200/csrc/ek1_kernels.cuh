@@ -97,9 +97,19 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem 
     load_envelopes(P, sm);
     const int tid = threadIdx.x;
     const size_t msz = (size_t)P.D, csz = (size_t)P.D * P.D;
+    // Pace keeping (P.gsync != nullptr): after every step the CTAs of the grid wait for each other.  Members are
+    // independent, so this is not needed for correctness; it keeps the CTAs in lock-step.  The step kernel's instruction
+    // working set (hundreds of KB over a step) lives in instruction caches that are shared between SMs: while all
+    // CTAs execute the same phase at the same time a line fetched by one SM serves the others; once they drift apart
+    // every SM streams the whole kernel through the caches on its own and the step slows down by up to 40 %
+    // (DESIGN.md section 3).  All CTAs of the grid are co-resident (grid <= CTAs per SM x SMs), so waiting cannot
+    // deadlock; in round r only the min(grid, batch - r grid) CTAs that still have a member take part.
+    unsigned pace_target = 0;
     for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
         if (tid == 0) nonfinite = 0;
         double diffsum = 0.0;
+        const int first_of_round = b - (int)blockIdx.x;
+        const unsigned pace_active = (unsigned)(P.batch - first_of_round < (int)gridDim.x ? P.batch - first_of_round : (int)gridDim.x);
         __syncthreads();
         for (int s = 0; s < a.nsteps; ++s) {
             double dt, tnew;
@@ -137,6 +147,13 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem 
                 for (size_t k = tid; k < csz; k += kThreads) ct[k] = cout[k];
             }
             if (a.std_traj) marginal_std_rows(cout, P.D, P.n, P.dd, a.std_traj + ((size_t)s * P.batch + b) * P.dd, tid >> 5, kWarps);
+            if (P.gsync && pace_active > 1) {
+                pace_target += pace_active;
+                if (tid == 0) {
+                    atomicAdd(P.gsync, 1u);
+                    while (*reinterpret_cast<volatile unsigned*>(P.gsync) < pace_target) __nanosleep(200);
+                }
+            }
             __syncthreads();
         }
         if ((a.nsteps & 1) && !a.final_in_b) {  // result sits in b: bring it home

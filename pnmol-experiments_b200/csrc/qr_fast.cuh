@@ -27,6 +27,12 @@ namespace pnmol {
 // Row pairs (2 t, 2 t + 1) stay adjacent, so the pass-1 operands of a lane are one 16-byte load; both operand patterns
 // of the trailing update are bank-conflict free (128-bit loads of reflectors g, g + 8 by quarter-warps; 64-bit loads of
 // reflectors 2 t + sx by half-warps).
+// PNMOL_FEWER_VARIANTS = 1: fewer specialisations of the hot phases are instantiated in the panel loop (see
+// panel_factor_dispatch / trailing_dispatch): the kernel's instruction working set is what limits it once the CTAs of
+// the grid drift out of lock-step and stop sharing instruction-cache lines.
+#ifndef PNMOL_FEWER_VARIANTS
+#define PNMOL_FEWER_VARIANTS 0   // measured: robust against drift (grid 288: 305 k vs 268 k) but 331 k vs 432 k in lock-step at C5
+#endif
 __device__ __forceinline__ int vsw(int r) { return ((r & 2) << 1) | (((r ^ (r >> 2)) & 1) << 3); }
 
 // A team: warps [first, first + nw) of the CTA; named barrier `bar` (0 = the whole CTA).
@@ -419,7 +425,8 @@ __device__ __noinline__ void trailing_fast(double* __restrict__ W, int ld, int c
     }
     const int nt1 = (rm.len1 + 7) >> 3;                // aligned lists: tiles [0, nt1) lie in the first segment
     const int off1 = rm.j0 + 2 * t, off2 = rm.a2 - rm.len1 + 2 * t;
-    constexpr int NG = NT > 4 ? NT - 4 : 0;            // tiles [0, NG) exist for certain
+    // tiles [0, NG) exist for certain (with fewer variants a variant also serves shorter row lists: every tile is guarded)
+    constexpr int NG = PNMOL_FEWER_VARIANTS ? 0 : (NT > 4 ? NT - 4 : 0);
     for (int kb = cbeg + tm.w * 8; kb < cend; kb += tm.nw * 8) {
         const int col = kb + g;
         const bool have = col < cend;
@@ -655,15 +662,15 @@ __device__ __forceinline__ void trailing_dispatch(double* __restrict__ W, int ld
         // 16-byte accesses when every tile address is even (segment offsets and the leading dimension)
         const bool vec = (((rm.j0 | (rm.a2 - rm.len1) | ld) & 1) == 0) && ((reinterpret_cast<size_t>(W) & 15) == 0);
         if (vec) {
-            if (ntile <= 4) trailing_fast<2, 4>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+            if (!PNMOL_FEWER_VARIANTS && ntile <= 4) trailing_fast<2, 4>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
             else if (ntile <= 8) trailing_fast<2, 8>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
-            else if (ntile <= 12) trailing_fast<2, 12>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+            else if (!PNMOL_FEWER_VARIANTS && ntile <= 12) trailing_fast<2, 12>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
             else if (ntile <= 16) trailing_fast<2, 16>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
             else trailing_fast<2, 16, true>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
         } else {
-            if (ntile <= 4) trailing_fast<1, 4>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+            if (!PNMOL_FEWER_VARIANTS && ntile <= 4) trailing_fast<1, 4>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
             else if (ntile <= 8) trailing_fast<1, 8>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
-            else if (ntile <= 12) trailing_fast<1, 12>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
+            else if (!PNMOL_FEWER_VARIANTS && ntile <= 12) trailing_fast<1, 12>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
             else if (ntile <= 16) trailing_fast<1, 16>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
             else trailing_fast<1, 16, true>(W, ld, cbeg, cend, rm, buf_off, LP, ts_off, tm);
         }
@@ -822,7 +829,11 @@ __device__ __forceinline__ void panel_factor(const QRCtx& cx, const QRPanel& p, 
 }
 
 __device__ __forceinline__ void panel_factor_dispatch(const QRCtx& cx, const QRPanel& p, PhaseClock& pc) {
+    // PNMOL_FEWER_VARIANTS: one panel body (8 rows per lane) whenever the buffers have 256 rows -- the shorter variants
+    // save a few FMAs on the first panels of a factorisation but add ~90 KB of hot code to a kernel whose instruction
+    // working set already exceeds the instruction caches (instruction-cache sensitivity)
     const int len = p.rm1.len;
+    if (PNMOL_FEWER_VARIANTS && cx.fq.LP >= 256) { panel_factor<8>(cx, p, pc); return; }
     if (len <= 64) panel_factor<2>(cx, p, pc);
     else if (len <= 128) panel_factor<4>(cx, p, pc);
     else panel_factor<8>(cx, p, pc);
@@ -860,8 +871,9 @@ static __device__ __noinline__ void householder_qr_fast(double* __restrict__ W, 
         const QRPanel& p = cx.pn[it & 1];
         if (!p.more) break;
         if (threadIdx.x == kThreads - 1) qr_advance(cx, p, cx.pn[(it + 1) & 1]);
-        if (p.nbk > 0)   // (the idle Gram + scratch block is the exchange area)
-            trailing_split_dispatch(cx.W, cx.ld, p.j1, p.j1 + p.nb1, p.rm, cx.fq.buf[p.bi], cx.fq.LP, cx.fq.Ts[p.bi], cx.fq.Gs, pc);
+        if (p.nbk > 0)   // (the other panel buffer is idle until the panel team loads panel k into it: the exchange area)
+            trailing_split_dispatch(cx.W, cx.ld, p.j1, p.j1 + p.nb1, p.rm, cx.fq.buf[p.bi], cx.fq.LP, cx.fq.Ts[p.bi],
+                                    cx.fq.buf[p.bi ^ 1], pc);
         if (in_panel_team()) {
             asm volatile("bar.sync 3, %0;" ::"r"(kThreads) : "memory");   // columns of the panel are up to date
             pc.mark(11);

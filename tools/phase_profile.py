@@ -10,11 +10,19 @@ from pnmol_b200.pde import examples
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 48
-pde = examples.heat_1d_discretized(num=bench.NUM_POINTS, tmax=T * bench.DT, diffusion_rate=0.035)
-solver = white.LinearWhiteNoiseEK1(num_derivatives=2, steprule=step.Constant(bench.DT),
-                                   spatial_kernel=kernels.SquareExponential() + kernels.WhiteNoise())
-y0, diff, prior = bench.member_parameters(M, pde.mesh_spatial.points[:, 0], bench.SEED)
-es = ensemble.EnsembleSolver(solver, pde, y0=y0, diff_scale=diff, prior_scale=prior)
+if len(sys.argv) > 3 and sys.argv[3] == "sir17":   # the semilinear SIR ensemble of bench.py's side measurements
+    pde = examples.sir_1d_discretized(num=17, tmax=T * bench.DT, diffusion_rate_S=0.035, diffusion_rate_I=0.035, diffusion_rate_R=0.035)
+    solver = white.SemiLinearWhiteNoiseEK1(num_derivatives=2, steprule=step.Constant(bench.DT),
+                                           spatial_kernel=kernels.duplicate(kernels.Matern52() + kernels.WhiteNoise(), 3))
+    rng = np.random.default_rng(bench.SEED)
+    y0 = np.tile(pde.y0, (M, 1)) * rng.uniform(0.9, 1.1, (M, 1))
+    es = ensemble.EnsembleSolver(solver, pde, y0=y0, diff_scale=np.exp(rng.uniform(np.log(0.3), np.log(3.0), (M, 3))))
+else:
+    pde = examples.heat_1d_discretized(num=bench.NUM_POINTS, tmax=T * bench.DT, diffusion_rate=0.035)
+    solver = white.LinearWhiteNoiseEK1(num_derivatives=2, steprule=step.Constant(bench.DT),
+                                       spatial_kernel=kernels.SquareExponential() + kernels.WhiteNoise())
+    y0, diff, prior = bench.member_parameters(M, pde.mesh_spatial.points[:, 0], bench.SEED)
+    es = ensemble.EnsembleSolver(solver, pde, y0=y0, diff_scale=diff, prior_scale=prior)
 lib = _lib.load()
 mean, chol, _ = es.initialize()
 es.engine.run(pde.t0, es.dts, mean.clone(), chol.clone())

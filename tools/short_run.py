@@ -10,7 +10,7 @@ from pnmol_b200.pde import examples
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-pde = examples.heat_1d_discretized(num=bench.NUM_POINTS, tmax=T * bench.DT, diffusion_rate=0.035)
+pde = examples.heat_1d_discretized(num=int(sys.argv[3]) if len(sys.argv) > 3 else bench.NUM_POINTS, tmax=T * bench.DT, diffusion_rate=0.035)
 solver = white.LinearWhiteNoiseEK1(num_derivatives=2, steprule=step.Constant(bench.DT),
                                    spatial_kernel=kernels.SquareExponential() + kernels.WhiteNoise())
 y0, diff, prior = bench.member_parameters(M, pde.mesh_spatial.points[:, 0], bench.SEED)
