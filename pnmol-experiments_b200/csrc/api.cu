@@ -249,7 +249,8 @@ int launch_run(pnmol_b200_handle* h, RunArgs& a, cudaStream_t st) {
         CU(cudaMemsetAsync(h->P.smslot, 0, sizeof(int) * h->num_sms, st));
         // pace keeping (ek1_kernels.cuh): one counter per launch out of a ring, so that launches of the same handle on
         // different streams (the chunked host route) never share one; PNMOL_B200_PACE=0 switches it off
-        static const bool pace = [] { const char* e = std::getenv("PNMOL_B200_PACE"); return !e || std::atoi(e) != 0; }();
+        const char* pace_env = std::getenv("PNMOL_B200_PACE");
+        const bool pace = !pace_env || std::atoi(pace_env) != 0;
         Problem P = h->P;
         P.gsync = nullptr;
         if (pace && h->gsync && a.nsteps > 1 && h->grid > 1) {

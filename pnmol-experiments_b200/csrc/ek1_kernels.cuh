@@ -4,6 +4,9 @@
 
 namespace pnmol {
 
+#ifndef PNMOL_PACE_PER_QR
+#define PNMOL_PACE_PER_QR 0
+#endif
 struct RunArgs {
     int nsteps, flags, final_in_b;
     double pv0[kMaxN], pinv0[kMaxN], dt0, tnew0;              // single-step parameters (nsteps == 1, by value)
@@ -37,11 +40,21 @@ struct InitArgs {
     int32_t* status;
 };
 
+// Pace keeping (see k_run): thread 0 announces the CTA at the counter and waits until `target` CTAs have done so.
+// Followed by a block barrier at the caller.
+__device__ __forceinline__ void pace_wait(unsigned* gsync, unsigned target) {
+    if (threadIdx.x == 0) {
+        atomicAdd(gsync, 1u);
+        while (*reinterpret_cast<volatile unsigned*>(gsync) < target) __nanosleep(100);
+    }
+}
+
 // One EK1 step for member b: state (mean_in, chol_in) -> (mean_out, chol_out).
 static __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& sm, double dt, double tnew,
                          const double* mean_in, const double* chol_in, double* mean_out, double* chol_out,
                          double* err_out, double* ref_out, double* diff_out, int flags, int* nonfinite,
-                         const double* pv_prev = nullptr, bool write_factor = true) {
+                         const double* pv_prev = nullptr, bool write_factor = true, unsigned* pace_target = nullptr,
+                         unsigned pace_active = 0) {
     const int tid = threadIdx.x;
     PhaseClock pc;
     pc.start(P.prof);
@@ -67,6 +80,13 @@ static __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& s
     Shape sp;
     sp.nt = D; sp.nbot = D; sp.ncols = D; sp.te = dense ? sm.te_pd : sm.te_p; sp.be = sm.be_p; sp.ldr = P.ld;
     householder_qr_fast(W + (size_t)P.m * P.ld, P.ld, sp, sm.fq, pc);
+#if PNMOL_PACE_PER_QR
+    if (pace_target) {   // second pace point of the step (the first is at the end of the step, in k_run)
+        *pace_target += pace_active;
+        pace_wait(P.gsync, *pace_target);
+        __syncthreads();
+    }
+#endif
     pc.mark(2);
     // small m: the error estimate's forward solve is deferred into update_stage (one warp, next to the build of the
     // update matrix); its assembly / cached factor is set up here by all threads
@@ -135,7 +155,8 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem 
             ek1_step(P, b, blockIdx.x, sm, dt, tnew, min_, cin_, mout, cout,
                      a.err_out ? a.err_out + (size_t)b * P.d : nullptr,
                      a.ref_out ? a.ref_out + (size_t)b * P.d : nullptr, &diff_s, flags, &nonfinite,
-                     from_w ? a.pv + (size_t)(s - 1) * P.n : nullptr, !to_w);
+                     from_w ? a.pv + (size_t)(s - 1) * P.n : nullptr, !to_w,
+                     (P.gsync && pace_active > 1) ? &pace_target : nullptr, pace_active);
             __syncthreads();
             diffsum += diff_s;
             if (a.mean_traj) {
@@ -149,10 +170,7 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem 
             if (a.std_traj) marginal_std_rows(cout, P.D, P.n, P.dd, a.std_traj + ((size_t)s * P.batch + b) * P.dd, tid >> 5, kWarps);
             if (P.gsync && pace_active > 1) {
                 pace_target += pace_active;
-                if (tid == 0) {
-                    atomicAdd(P.gsync, 1u);
-                    while (*reinterpret_cast<volatile unsigned*>(P.gsync) < pace_target) __nanosleep(200);
-                }
+                pace_wait(P.gsync, pace_target);
             }
             __syncthreads();
         }

@@ -534,6 +534,36 @@ def test_one_launch_time_loop_equals_step_by_step(kind, name, num, monkeypatch):
     assert torch.equal(out2["chol_traj"][-1].reshape(c2.shape), c2)
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("grid,members", [(3, 7), (4, 4), (2, 5), (None, 6)])
+def test_pace_keeping_is_invisible_and_terminates(grid, members, monkeypatch):
+    """After every step of the persistent time loop the CTAs of the grid wait for each other (pace keeping, a
+    performance device: csrc/ek1_kernels.cuh).  Members are independent, so the results must not depend on it, and the
+    wait must terminate when the member count is not a multiple of the grid (in the last round only the CTAs that
+    still have a member take part)."""
+    from pnmol_b200 import ensemble
+
+    monkeypatch.setenv("PNMOL_B200_PATH", "cta")
+    if grid is not None:
+        monkeypatch.setenv("PNMOL_B200_GRID", str(grid))
+    case = cases.make_case("heat", num=9, tmax=0.5)
+    pde = case["pde"]
+    rng = np.random.default_rng(11)
+    y0 = np.tile(pde.y0, (members, 1)) * rng.uniform(0.8, 1.2, (members, 1))
+    es = ensemble.EnsembleSolver(cases.make_solver("white_linear", case), pde, y0=y0)
+    mean0, chol0, _ = es.initialize()
+    outs = []
+    for pace in ("1", "0"):
+        monkeypatch.setenv("PNMOL_B200_PACE", pace)
+        m, c = mean0.clone(), chol0.clone()
+        out = es.engine.run(pde.t0, es.dts, m, c)
+        torch.cuda.synchronize()
+        assert int(out["status"].max()) == 0
+        outs.append((m, c, out["diff_sum"].clone(), out["err"].clone()))
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+
+
 def test_ensemble_semilinear_sir_with_member_parameters():
     from oracle import setup_np
     from pnmol_b200 import ensemble
