@@ -153,7 +153,11 @@ int pnmol_b200_step(pnmol_b200_handle* h, double t_new, double dt, const double*
  * [nsteps, n] each.  mean / chol dev are updated in place (scratch = second state buffer
  * owned by the caller: mean_tmp, chol_tmp).  diff_sum dev [batch] receives the sum of the
  * local diffusions (for the mean of src/pnmol/pdefilter.py:95,113).  If mean_traj /
- * chol_traj are non-NULL they receive every step's state ([nsteps, batch, ...]). */
+ * chol_traj are non-NULL they receive every step's state ([nsteps, batch, ...]).
+ * Inside the launch only the last step writes the D x D factor to `chol` (unless a trajectory is requested): the
+ * others hand it to their successor inside the workspace; flags bit 2 (value 4) makes every step go through the state
+ * buffers (diagnostics; bitwise the same result).  The CTAs of the launch keep pace with each other after every step
+ * (environment PNMOL_B200_PACE=0 switches that off; performance only). */
 int pnmol_b200_run(pnmol_b200_handle* h, double t0, const double* dts, const double* precond,
                    const double* precond_inv, int nsteps, double* mean, double* chol, double* mean_tmp,
                    double* chol_tmp, double* err_out, double* ref_out, double* diff_last, double* diff_sum,

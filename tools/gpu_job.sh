@@ -1,7 +1,5 @@
-for v in head pace2; do lib=$PWD/tools/variants/$v.so; [ $v = head ] && lib=$PWD/pnmol-experiments_b200/pnmol_b200/libpnmol_b200.so
-PNMOL_B200_LIB=$lib python tools/time_run.py 4096 48 2 2>&1 | tail -1 | sed "s/.*: members/$v heat50: members/"
-PNMOL_NUM=51 PNMOL_B200_LIB=$lib python tools/time_run.py 4096 48 1 2>&1 | tail -1 | sed "s/.*: members/$v heat51: members/"
-PNMOL_NUM=54 PNMOL_B200_LIB=$lib python tools/time_run.py 4096 48 1 2>&1 | tail -1 | sed "s/.*: members/$v heat54: members/"
-PNMOL_B200_LIB=$lib PNMOL_B200_PATH=cta python tools/small_d_probe.py sir17 4096 2>&1 | tail -1 | cut -c1-100 | sed "s/^/$v /"
-done > gpurun_out/r3_sweep.log
-cat gpurun_out/r3_sweep.log
+for i in 1 2; do
+PNMOL_B200_LIB=$PWD/tools/variants/v55.so python tools/large_timing.py c4 --steps 8 2>&1 | tail -1 | cut -c1-150 | sed "s/^/v55: /"
+python tools/large_timing.py c4 --steps 8 2>&1 | tail -1 | cut -c1-150 | sed "s/^/head: /"
+done > gpurun_out/r3_c4.log
+cat gpurun_out/r3_c4.log
