@@ -466,6 +466,42 @@ __device__ void build_predict(const Problem& P, int b, const Smem& sm, const dou
         const int tend = te[i0];  // (the columns of a block share their top envelope)
         const double* src = Cl + (size_t)i0 * D;
         double* col0 = Wp + (size_t)i0 * P.ld;
+        if (pv_prev && n == 3 && tend < 192) {
+            // common case (two derivatives, fused time loop): ALL rows of the block are read before the first store --
+            // one L2 round trip per block instead of one per 64 rows; same operations in the same order as below
+            double a[3][3];
+#pragma unroll
+            for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) a[ii][q] = P.A1d[ii * 3 + q];
+            const double pi0 = sm.pinv[0], pi1 = sm.pinv[1], pi2 = sm.pinv[2];
+            double v[6][3];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int k = 32 * u + lane;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    double c = 0.0;
+                    if (k <= i0 + q && P.m + k < nrows_prev) c = pvp[q] * col0[(size_t)q * P.ld + P.m + k];
+                    v[u][q] = k <= tend ? (q == 0 ? pi0 : q == 1 ? pi1 : pi2) * c : 0.0;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int k = 32 * u + lane;
+                if (k <= tend) {
+#pragma unroll
+                    for (int ii = 0; ii < 3; ++ii) {
+                        double acc = 0.0;
+                        acc = fma(a[ii][0], v[u][0], acc);
+                        acc = fma(a[ii][1], v[u][1], acc);
+                        acc = fma(a[ii][2], v[u][2], acc);
+                        col0[(size_t)ii * P.ld + k] = acc;
+                    }
+                }
+            }
+        } else
         for (int k0 = 0; k0 <= tend; k0 += 64) {
             double v[2][kMaxN];
             if (pv_prev) {
@@ -634,20 +670,29 @@ __device__ void error_estimate_global(const Problem& P, int b, const Smem& sm, d
     T::sync();
 }
 
+__device__ __forceinline__ void error_estimate_solve_warp(const Problem& P, const Smem& sm, bool inverse);
+// room for S and X = L^-1 side by side in the idle panel buffers (2 x 16 x vld doubles)
+__device__ __forceinline__ bool err_inverse_fits(const Problem& P) { return 2 * P.m * P.ldm <= 32 * P.vld; }
+
 // Shared-memory variant for small m (P.ldm > 0): S is assembled entry by entry straight from the sparse rows of
 // At and the L2-resident Gram matrix (all loads independent), factorised and solved in sm.msq.
 template <class T = CtaTeam>
 __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode,
                                     const int32_t* Hcol, const double* Hval, double* err_out, double* Sg = nullptr,
-                                    double* Fg = nullptr, double* key = nullptr, bool defer_solve = false) {
+                                    double* Fg = nullptr, double* key = nullptr, bool defer_solve = false,
+                                    bool use_inverse = false) {
     const int tid = T::tid(), lane = tid & 31, warp = T::warp();
     const int n = P.n, d = P.d, m = P.m, ldm = P.ldm;
     // Loop-invariant factor: for a linear PDE the rows of H depend on the member and on the Nordsieck scaling (dt) only,
     // so S = H Q H^T + E E^T and its Cholesky factor are the same in every step of a constant-step run.  The CTA keeps
     // the factor of its current member in its global scratch (Sg: lower triangle + diagonal of L, Fg: diag(S)) and
     // re-reads it while the key (member, scalings, noise mode) in shared memory is unchanged -- same numbers, bit for bit.
+    // use_inverse (persistent constant-step loop): the cache holds X = L^-1 instead of L, so that every later step applies
+    // it as a matrix-vector product instead of a forward substitution (52 dependent steps on one warp)
     const bool cacheable = key != nullptr && Sg != nullptr && Fg != nullptr && !P.semilinear;
-    const bool hit = cacheable && key[0] == (double)b && key[1] == sm.pv[0] && key[2] == p1s && key[3] == (double)emode;
+    const bool inverse = cacheable && use_inverse && err_inverse_fits(P);
+    const bool hit = cacheable && key[0] == (double)b && key[1] == sm.pv[0] && key[2] == p1s &&
+                     key[3] == (double)(emode + (inverse ? 16 : 0));
     if (hit) {
         double* S = sm.msq;
         for (int idx = tid; idx < m * m; idx += T::size) {
@@ -733,6 +778,28 @@ __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, dou
             for (int c = k + 1 + lane; c <= r; c += 32) S[r * ldm + c] = fma(-lrk, S[c * ldm + k], S[r * ldm + c]);
         }
     }
+    if (inverse) {
+        // X = L^-1, one column per thread by forward substitution into a second buffer (behind S in the idle panel
+        // buffers), then back into the layout of L: strictly lower part in S, diagonal in sm.xw
+        T::sync();
+        double* X = S + (size_t)m * ldm;
+        for (int c = tid; c < m; c += T::size) {
+            X[c * ldm + c] = 1.0 / sm.xw[c];
+            for (int r = c + 1; r < m; ++r) {
+                double a0 = 0.0, a1 = 0.0;
+                int j = c;
+                for (; j + 1 < r; j += 2) { a0 = fma(S[r * ldm + j], X[j * ldm + c], a0); a1 = fma(S[r * ldm + j + 1], X[(j + 1) * ldm + c], a1); }
+                if (j < r) a0 = fma(S[r * ldm + j], X[j * ldm + c], a0);
+                X[r * ldm + c] = -(a0 + a1) / sm.xw[r];
+            }
+        }
+        T::sync();
+        for (int idx = tid; idx < m * m; idx += T::size) {
+            const int r = idx / m, c = idx - r * m;
+            if (c < r) S[r * ldm + c] = X[r * ldm + c];
+            else if (c == r) sm.xw[r] = X[r * ldm + r];
+        }
+    }
     if (cacheable) {
         T::sync();
         for (int idx = tid; idx < m * m; idx += T::size) {
@@ -741,7 +808,7 @@ __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, dou
             else if (c == r) Sg[idx] = sm.xw[r];
         }
         for (int r = tid; r < m; r += T::size) Fg[r] = sm.y[r];
-        if (tid == 0) { key[0] = (double)b; key[1] = sm.pv[0]; key[2] = p1s; key[3] = (double)emode; }
+        if (tid == 0) { key[0] = (double)b; key[1] = sm.pv[0]; key[2] = p1s; key[3] = (double)(emode + (inverse ? 16 : 0)); }
     }
     }  // (factor computed or re-read)
     double* S = sm.msq;
@@ -749,28 +816,7 @@ __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, dou
     // (defer_solve: the caller runs error_estimate_solve_warp on one warp next to other work and writes err_out itself)
     if (defer_solve) return;
     // forward solve L u = z by warp 0 (column oriented: each lane owns rows lane, lane + 32, lane + 64)
-    if (warp == 0) {
-        double u[3], acc[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) { const int r = lane + 32 * q; u[q] = r < m ? sm.z[r] : 0.0; acc[q] = 0.0; }
-        for (int k = 0; k < m; ++k) {
-            const int q = k >> 5;
-            double cand = q == 0 ? u[0] - acc[0] : q == 1 ? u[1] - acc[1] : u[2] - acc[2];
-            cand /= sm.xw[k];
-            const double uk = __shfl_sync(0xffffffffu, cand, k & 31);
-#pragma unroll
-            for (int qq = 0; qq < 3; ++qq) {
-                const int r = lane + 32 * qq;
-                if (r > k && r < m) acc[qq] = fma(S[r * ldm + k], uk, acc[qq]);
-                if (r == k) u[qq] = uk;
-            }
-        }
-        double part = 0.0;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) { const int r = lane + 32 * q; if (r < m) part = fma(u[q], u[q], part); }
-        part = warp_sum(part);
-        if (lane == 0) sm.red[15] = sqrt(part / m);
-    }
+    if (warp == 0) error_estimate_solve_warp(P, sm, inverse);
     T::sync();
     const double sigma = sm.red[15];
     if (err_out)
@@ -780,17 +826,38 @@ __device__ void error_estimate_smem(const Problem& P, int b, const Smem& sm, dou
 
 // The forward solve of error_estimate_smem on ONE warp (S, the diagonal of L in sm.xw and z are in shared memory):
 // sigma = sqrt(|L^-1 z|^2 / m) -> sm.red[15].  Same operations as the solve inside error_estimate_smem.
-__device__ __forceinline__ void error_estimate_solve_warp(const Problem& P, const Smem& sm) {
+// inverse: S / sm.xw hold X = L^-1 (strictly lower part / diagonal): u = X z, one or two rows per lane.
+__device__ __forceinline__ void error_estimate_solve_warp(const Problem& P, const Smem& sm, bool inverse) {
     const int lane = threadIdx.x & 31;
     const int m = P.m, ldm = P.ldm;
     const double* S = sm.msq;
-    double u[3], acc[3];
+    if (inverse) {
+        double part = 0.0;
+        for (int r = lane; r < m; r += 32) {
+            const double* row = S + r * ldm;
+            double a0 = sm.xw[r] * sm.z[r], a1 = 0.0;
+            int c = 0;
+            for (; c + 1 < r; c += 2) { a0 = fma(row[c], sm.z[c], a0); a1 = fma(row[c + 1], sm.z[c + 1], a1); }
+            if (c < r) a0 = fma(row[c], sm.z[c], a0);
+            const double ur = a0 + a1;
+            part = fma(ur, ur, part);
+        }
+        part = warp_sum(part);
+        if (lane == 0) sm.red[15] = sqrt(part / m);
+        return;
+    }
+    // (the reciprocals of the diagonal are formed up front, one per lane and chunk: a division inside the dependent
+    // chain of the substitution costs more than everything else in a step of it)
+    double u[3], acc[3], rd[3];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { const int r = lane + 32 * q; u[q] = r < m ? sm.z[r] : 0.0; acc[q] = 0.0; }
+    for (int q = 0; q < 3; ++q) {
+        const int r = lane + 32 * q;
+        u[q] = r < m ? sm.z[r] : 0.0; acc[q] = 0.0;
+        rd[q] = r < m ? 1.0 / sm.xw[r] : 0.0;
+    }
     for (int k = 0; k < m; ++k) {
         const int q = k >> 5;
-        double cand = q == 0 ? u[0] - acc[0] : q == 1 ? u[1] - acc[1] : u[2] - acc[2];
-        cand /= sm.xw[k];
+        const double cand = q == 0 ? (u[0] - acc[0]) * rd[0] : q == 1 ? (u[1] - acc[1]) * rd[1] : (u[2] - acc[2]) * rd[2];
         const double uk = __shfl_sync(0xffffffffu, cand, k & 31);
 #pragma unroll
         for (int qq = 0; qq < 3; ++qq) {
@@ -809,10 +876,10 @@ __device__ __forceinline__ void error_estimate_solve_warp(const Problem& P, cons
 template <class T = CtaTeam>
 __device__ void error_estimate(const Problem& P, int b, const Smem& sm, double p1s, double dt, EMode emode, double nugget,
                                const int32_t* Hcol, const double* Hval, double* F, double* S, double* err_out,
-                               bool defer_solve = false) {
+                               bool defer_solve = false, bool use_inverse = false) {
     if (P.ldm > 0 && P.m <= 96)
         error_estimate_smem<T>(P, b, sm, p1s, dt, emode, Hcol, Hval, err_out, S, F, T::size == kThreads ? sm.ekey : nullptr,
-                               defer_solve);
+                               defer_solve, use_inverse);
     else
         error_estimate_global<T>(P, b, sm, p1s, dt, emode, nugget, Hcol, Hval, F, S, err_out);
 }
@@ -851,6 +918,7 @@ struct UpdateOut {
     // Deferred error estimate (error_estimate(..., defer_solve = true) has left S in shared memory): its forward solve
     // runs on warp 0 while the other warps assemble the left block of the update matrix.
     bool err_solve = false;
+    bool err_inverse = false;   // the cached factor is X = L^-1 (error_estimate_smem, use_inverse)
     double err_dt = 0.0;
     double* err_out = nullptr;
 };
@@ -1021,14 +1089,17 @@ __device__ double update_solve(const Problem& P, const Smem& sm, int mcur, const
             if (c <= k) Rs[c * ldm + k] = Wl[(size_t)k * ld + c];
         }
         T::sync();
-        if (warp == 0) {  // forward: y_k = (z_k - sum_{c<k} R1[c][k] y_c) / R1[k][k]
-            double zz[3], acc[3];
+        if (warp == 0) {  // forward: y_k = (z_k - sum_{c<k} R1[c][k] y_c) / R1[k][k]   (reciprocals of the diagonal up front)
+            double zz[3], acc[3], rd[3];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { const int j = lane + 32 * q; zz[q] = j < mcur ? sm.z[j] : 0.0; acc[q] = 0.0; }
+            for (int q = 0; q < 3; ++q) {
+                const int j = lane + 32 * q;
+                zz[q] = j < mcur ? sm.z[j] : 0.0; acc[q] = 0.0;
+                rd[q] = j < mcur ? 1.0 / Rs[j * ldm + j] : 0.0;
+            }
             for (int k = 0; k < mcur; ++k) {
                 const int q = k >> 5;
-                double cand = q == 0 ? zz[0] - acc[0] : q == 1 ? zz[1] - acc[1] : zz[2] - acc[2];
-                cand /= Rs[k * ldm + k];
+                const double cand = q == 0 ? (zz[0] - acc[0]) * rd[0] : q == 1 ? (zz[1] - acc[1]) * rd[1] : (zz[2] - acc[2]) * rd[2];
                 const double yk = __shfl_sync(0xffffffffu, cand, k & 31);
 #pragma unroll
                 for (int qq = 0; qq < 3; ++qq) {
@@ -1039,14 +1110,17 @@ __device__ double update_solve(const Problem& P, const Smem& sm, int mcur, const
             }
         }
         if (warp == (T::nwarps > 1 ? 1 : 0)) {  // backward: x_k = (z_k - sum_{c>k} R1[k][c] x_c) / R1[k][k]
-            double zz[3];
+            double zz[3], rd[3];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { const int j = lane + 32 * q; zz[q] = j < mcur ? sm.z[j] : 0.0; }
+            for (int q = 0; q < 3; ++q) {
+                const int j = lane + 32 * q;
+                zz[q] = j < mcur ? sm.z[j] : 0.0;
+                rd[q] = j < mcur ? 1.0 / Rs[j * ldm + j] : 0.0;
+            }
             double part = 0.0;
             for (int k = mcur - 1; k >= 0; --k) {
                 const int q = k >> 5;
-                double cand = q == 0 ? zz[0] : q == 1 ? zz[1] : zz[2];
-                cand /= Rs[k * ldm + k];
+                const double cand = q == 0 ? zz[0] * rd[0] : q == 1 ? zz[1] * rd[1] : zz[2] * rd[2];
                 const double xk = __shfl_sync(0xffffffffu, cand, k & 31);
                 if (lane == 0) part = fma(xk, xk, part);
 #pragma unroll
@@ -1180,8 +1254,9 @@ static __device__ void update_stage(const Problem& P, int b, const Smem& sm, int
 
     update_build_right(P, mcur, nrows, Rsrc, te, be, Wr, warp, kWarps);
     __syncthreads();
+    pc.mark(13);
     if (out.err_solve) {
-        if (warp == 0) error_estimate_solve_warp(P, sm);
+        if (warp == 0) { error_estimate_solve_warp(P, sm, out.err_inverse); pc.mark(15); }
         else update_build_left(P, b, mcur, nrows, emode, nugget, te, be, Hcol, Hval, Wl, Wr, warp - 1, kWarps - 1);
         __syncthreads();
         if (out.err_out) {   // white.py:160-162 (sm.y = diag(S) is overwritten only by update_solve, after the QR)

@@ -54,7 +54,7 @@ static __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& s
                          const double* mean_in, const double* chol_in, double* mean_out, double* chol_out,
                          double* err_out, double* ref_out, double* diff_out, int flags, int* nonfinite,
                          const double* pv_prev = nullptr, bool write_factor = true, unsigned* pace_target = nullptr,
-                         unsigned pace_active = 0) {
+                         unsigned pace_active = 0, bool err_inverse = false) {
     const int tid = threadIdx.x;
     PhaseClock pc;
     pc.start(P.prof);
@@ -94,11 +94,12 @@ static __device__ void ek1_step(const Problem& P, int b, int slot, const Smem& s
     const bool defer = est && P.ldm > 0 && P.m <= 96;
     if (est) {
         error_estimate(P, b, sm, sm.pv[1], dt, E_STEP_WHITE, 0.0, Hcol, Hval, P.F + (size_t)slot * P.m * P.d,
-                       P.S + (size_t)slot * P.m * P.m, err_out, defer);
+                       P.S + (size_t)slot * P.m * P.m, err_out, defer, err_inverse);
     }
     pc.mark(3);
     UpdateOut out;
     out.err_solve = defer; out.err_dt = dt; out.err_out = err_out;
+    out.err_inverse = defer && err_inverse && !P.semilinear && err_inverse_fits(P);
     out.mean_out = mean_out; out.chol_out = write_factor ? chol_out : nullptr; out.diff_out = diff_out;
     out.ref_out = P.latent ? nullptr : ref_out; out.scale_by_p = true;
     update_stage(P, b, sm, P.m, P.latent ? E_NONE : E_STEP_WHITE, 0.0, nullptr, sm.te_u, sm.be_u, Hcol, Hval, W, out,
@@ -156,7 +157,8 @@ __global__ void __launch_bounds__(kThreads, PNMOL_MIN_CTAS) k_run(const Problem 
                      a.err_out ? a.err_out + (size_t)b * P.d : nullptr,
                      a.ref_out ? a.ref_out + (size_t)b * P.d : nullptr, &diff_s, flags, &nonfinite,
                      from_w ? a.pv + (size_t)(s - 1) * P.n : nullptr, !to_w,
-                     (P.gsync && pace_active > 1) ? &pace_target : nullptr, pace_active);
+                     (P.gsync && pace_active > 1) ? &pace_target : nullptr, pace_active,
+                     /* cached inverse factor of the error estimate: */ a.nsteps > 2 && a.pv != nullptr);
             __syncthreads();
             diffsum += diff_s;
             if (a.mean_traj) {

@@ -523,7 +523,9 @@ def test_one_launch_time_loop_equals_step_by_step(kind, name, num, monkeypatch):
         assert torch.equal(m1.reshape(m.shape), m) and torch.equal(c1.reshape(c.shape), c)
         assert torch.equal(out["diff_last"], diffs[-1])
         if err is not None:
-            assert torch.equal(out["err"], err) and torch.equal(out["ref"], ref)
+            # (the persistent loop of a linear PDE applies the cached INVERSE factor of the error estimate instead of a
+            # forward substitution: equal to rounding, not bitwise)
+            assert torch.allclose(out["err"], err, rtol=1e-11, atol=0) and torch.equal(out["ref"], ref)
         assert torch.allclose(out["diff_sum"], torch.stack(diffs).sum(0), rtol=1e-14)
     # an odd number of steps (result ends in the second state buffer) and a trajectory request (no fusion)
     m2, c2 = mean0.clone(), chol0.clone()

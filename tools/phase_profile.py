@@ -34,7 +34,7 @@ out = np.zeros(24, np.uint64)
 _lib.check(lib.pnmol_b200_profile(es.engine.h, 0, _lib.ptr(out)))
 names = ["mean+evaluate_ode", "build predict", "QR predict (rest)", "error estimate", "build update", "QR update (rest)", "solves+mean", "outputs",
          "qr: panel load", "qr: subpanel factor (1 warp)", "qr: subpanel apply", "qr: trailing apply", "qr: barrier after T",
-         "qr: gram V^T V", "qr: T factor", "-", "split: loads+pass1", "split: exchange barrier", "split: sum+T+pass2+stores", "-",
+         "update: right block (zero fill)", "qr: T factor", "update: error-estimate solve (warp 0)", "split: loads+pass1", "split: exchange barrier", "split: sum+T+pass2+stores", "-",
          "split: entry (row map, call)", "probe: mark-to-mark (overhead of a mark)", "probe: panel_rows", "(panel: rest = update+own -> in panel factor)"]
 tot = float(out[:24].sum())
 ms = e0.elapsed_time(e1)
