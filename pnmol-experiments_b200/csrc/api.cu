@@ -257,6 +257,18 @@ int launch_run(pnmol_b200_handle* h, RunArgs& a, cudaStream_t st) {
             P.gsync = h->gsync + (h->gsync_next++ % kPaceRing);
             CU(cudaMemsetAsync(P.gsync, 0, sizeof(unsigned), st));
         }
+        if (P.gsync) {
+            // CTAs that wait for each other must all be resident: a cooperative launch guarantees it (two such launches
+            // on different streams -- two handles on one device -- are then run one after the other instead of each
+            // holding a part of the SMs and waiting for the rest forever)
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(h->grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = h->smem_bytes; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeCooperative;
+            at[0].val.cooperative = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CU(cudaLaunchKernelEx(&cfg, k_run, P, a));
+        } else
         k_run<<<h->grid, kThreads, h->smem_bytes, st>>>(P, a);
     }
     ++g_launches;

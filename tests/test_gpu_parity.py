@@ -566,6 +566,36 @@ def test_pace_keeping_is_invisible_and_terminates(grid, members, monkeypatch):
         assert torch.equal(x, y)
 
 
+@pytest.mark.timeout(300)
+def test_two_ensembles_on_two_streams_do_not_wait_for_each_other_forever():
+    """Pace keeping makes the CTAs of a launch wait for each other, so all of them must be resident: the launch is
+    cooperative, and two persistent launches on different streams (two handles on one device) are serialised by the
+    driver instead of each holding a part of the SMs.  Both must finish and give the results of running alone."""
+    from pnmol_b200 import ensemble
+
+    case = cases.make_case("heat", num=20, tmax=0.5)
+    pde = case["pde"]
+    rng = np.random.default_rng(3)
+    members = 400   # more than one wave of resident CTAs each
+    y0 = np.tile(pde.y0, (members, 1)) * rng.uniform(0.8, 1.2, (members, 1))
+    ess = [ensemble.EnsembleSolver(cases.make_solver("white_linear", case), pde, y0=y0) for _ in range(2)]
+    inits = [es.initialize() for es in ess]
+    ref_m, ref_c = inits[0][0].clone(), inits[0][1].clone()
+    ess[0].engine.run(pde.t0, ess[0].dts, ref_m, ref_c)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    outs = []
+    for es, (m0, c0, _), st in zip(ess, inits, streams):
+        m, c = m0.clone(), c0.clone()
+        torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(st):
+            outs.append((m, c, es.engine.run(pde.t0, es.dts, m, c)))
+    torch.cuda.synchronize()
+    for m, c, out in outs:
+        assert int(out["status"].max()) == 0
+        assert torch.equal(m, ref_m) and torch.equal(c, ref_c)
+
+
 def test_ensemble_semilinear_sir_with_member_parameters():
     from oracle import setup_np
     from pnmol_b200 import ensemble
